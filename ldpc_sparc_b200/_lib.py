@@ -1,0 +1,86 @@
+"""ctypes binding of libldpcsparc_b200.so (see include/ldpc_sparc_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is
+visible when a compute entry point is called, an exception is raised.
+"""
+import ctypes as ct
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldpcsparc_b200.so")
+
+c_f32p = ct.POINTER(ct.c_float)
+c_f64p = ct.POINTER(ct.c_double)
+c_i32p = ct.POINTER(ct.c_int32)
+c_i64p = ct.POINTER(ct.c_int64)
+c_u8p = ct.POINTER(ct.c_uint8)
+c_u32p = ct.POINTER(ct.c_uint32)
+c_longp = ct.POINTER(ct.c_long)
+
+
+class LibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/ldpc_sparc_b200.h declares
+SIGNATURES = {
+    "lsb_version": (ct.c_int, []),
+    "lsb_last_error": (ct.c_char_p, []),
+    "lsb_device_count": (ct.c_int, []),
+    "lsb_launch_count": (ct.c_int64, []),
+    "lsb_launch_count_reset": (None, []),
+    "lsb_host_alloc": (ct.c_void_p, [ct.c_uint64]),
+    "lsb_host_free": (None, [ct.c_void_p]),
+    # legacy (c_ldpc.c)
+    "sumprod": (ct.c_int, [c_f64p, c_longp, c_longp, c_longp, ct.c_int, ct.c_int, ct.c_int, c_f64p, ct.c_int]),
+    "sumprod2": (ct.c_int, [c_f64p, c_longp, c_longp, c_longp, ct.c_int, ct.c_int, ct.c_int, c_f64p, ct.c_int]),
+    "minsum": (ct.c_int, [c_f64p, c_longp, c_longp, c_longp, ct.c_int, ct.c_int, ct.c_int, c_f64p, ct.c_double, ct.c_int]),
+    "Lxor": (ct.c_double, [ct.c_double, ct.c_double, ct.c_int]),
+    "Lxfb": (ct.c_double, [c_f64p, ct.c_long, ct.c_int]),
+    # batched LDPC
+    "lsb_ldpc_graph_create_qc": (ct.c_int, [c_i32p, ct.c_int, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p)]),
+    "lsb_ldpc_graph_create": (ct.c_int, [c_i64p, c_i64p, c_i64p, ct.c_int64, ct.c_int64, ct.c_int64, ct.POINTER(ct.c_void_p)]),
+    "lsb_ldpc_graph_destroy": (None, [ct.c_void_p]),
+    "lsb_ldpc_graph_info": (ct.c_int, [ct.c_void_p, c_i64p]),
+    "lsb_ldpc_decode_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_void_p]),
+    "lsb_ldpc_decode_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_void_p]),
+    "lsb_ldpc_decode_host_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double]),
+    "lsb_ldpc_decode_host_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_int]),
+}
+
+
+def lib():
+    """Loads the library once; raises LibraryError if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or ./build.sh (there is no CPU fallback)" % LIB_PATH
+            )
+        handle = ct.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError here = header/library mismatch
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().lsb_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise LibraryError("%s failed (status %d): %s" % (what, rc, last_error()))
+
+
+def require_device():
+    if lib().lsb_device_count() < 1:
+        raise LibraryError("no CUDA device visible: the decoders run on the GPU only (no CPU fallback)")
+
+
+ALGO = {"sumprod2": 0, "sumprod": 1, "minsum": 2}

@@ -1,0 +1,66 @@
+// Types shared between the BP kernels' translation units and the host API.
+#pragma once
+#include "common.cuh"
+
+namespace lsb_bp {
+
+constexpr int kMaxRows = 32;
+constexpr int kMaxCols = 64;
+constexpr int kMaxEdges = 160;
+constexpr int kMaxDcQc = 24;   // largest check degree the QC kernel unrolls
+constexpr int kMaxDc = 64;     // hard limit (generic kernel, local-memory trellis)
+constexpr int kThreads = 256;
+
+// Protograph tables of a QC code, copied to shared memory by every CTA.
+struct QcTables {
+    int z, rows, cols, n_edges, nv, nc;
+    unsigned magic;                  // ceil(2^32 / z): p / z == umulhi(p, magic) for p < 65536
+    short row_ptr[kMaxRows + 1];     // protograph edges of row r: [row_ptr[r], row_ptr[r+1])
+    short row_order[kMaxRows];       // rows sorted by degree (stable)
+    short col_ptr[kMaxCols + 1];
+    short col_shift[kMaxEdges];      // per column-list entry: shift mod z
+    int col_base[kMaxEdges];         // per column-list entry: edge*z - shift
+};
+
+template <typename T>
+struct QcLaunch {
+    const QcTables *tabs;
+    const T *llr;
+    T *app;
+    uint8_t *hard;
+    int32_t *iters;
+    long long n_frames;
+    int max_it, algo, max_dc;
+    T scale;
+    unsigned long long *queue;
+    size_t smem;
+    int *cached_grid;   // per (handle, precision, algo) launch geometry cache
+    cudaStream_t stream;
+};
+
+template <typename T>
+struct GenericLaunch {
+    const int *voff, *coff, *intrlv;
+    int nv, nc, nmsg;
+    const T *llr;
+    T *app;
+    uint8_t *hard;
+    int32_t *iters;
+    long long n_frames;
+    int max_it, algo;
+    T scale;
+    T *ws;
+    unsigned long long *queue;
+    long long grid;
+    cudaStream_t stream;
+};
+
+// defined in ldpc_bp_f32.cu / ldpc_bp_f64.cu
+template <typename T> int launch_qc(const QcLaunch<T> &a);
+template <typename T> int launch_generic(const GenericLaunch<T> &a);
+template <typename T> int generic_blocks_per_sm();
+// scalar helpers behind the legacy Lxor / Lxfb symbols (ldpc_bp_f64.cu)
+void launch_lxor(double a, double b, int corr, double *d_out);
+void launch_lxfb(double *d_L, int dc, int corr, double *d_out);
+
+}  // namespace lsb_bp

@@ -1,0 +1,429 @@
+// Device code of the batched flooding BP decoder (sm_100a) + its launchers.
+// Included by ldpc_bp_f32.cu / ldpc_bp_f64.cu, which instantiate one precision
+// each so the two compile in parallel.
+//
+// What it computes (reference: ldpc_jossy/src/c_ldpc.c, paths under
+// /root/reference): per frame, up to max_it iterations of
+//   VN pass  (c_ldpc.c:171-178): total = ch[v] + sum of the variable's edge
+//            messages in port order; every edge message <- total - message;
+//            app[v] = total
+//   CN pass  (c_ldpc.c:183-194 -> Lxfb :294-314 -> Lxor :234-251): every check
+//            rewrites its dc messages with the extrinsic LLRs from a
+//            forward/backward Lxor trellis and reports the LLR of the XOR of all
+//            its inputs; the frame stops when every check reports > 0.
+// The returned iteration count and app are the reference's (app comes from the
+// VN pass of the last executed iteration).
+//
+// How it is laid out for B200:
+//  * QC kernel (bp_qc_kernel): one CTA decodes one frame at a time out of a
+//    device-side frame queue (atomic counter -> natural load balance under
+//    early stopping).  All edge messages of the frame live in SHARED MEMORY for
+//    the whole decode, laid out [protograph edge][z]: the message of protograph
+//    entry e = (row r, column c, shift s) that belongs to check r*z+k sits at
+//    e*z + k.  Lanes walk consecutive checks (CN pass) or consecutive variables
+//    (VN pass: k = j - s mod z), so both passes are shared-memory conflict free
+//    with NO index table: addresses follow from the QC structure.  Check rows
+//    are visited in degree-sorted order so a warp runs one unrolled trellis
+//    (register arrays, compile-time dc).  HBM traffic per frame is the
+//    compulsory LLR read + APP/decision write only.
+//  * generic kernel (bp_generic_kernel): any (vdeg, cdeg, intrlv) graph, messages
+//    in a per-CTA global workspace (L1/L2 resident); serves the legacy
+//    single-frame ABI and graphs that do not fit the QC kernel.
+#pragma once
+#include "ldpc_bp_host.h"
+
+namespace lsb_bp {
+
+// ---------------------------------------------------------------- arithmetic
+template <typename T>
+struct Num;
+
+template <>
+struct Num<float> {
+    static __device__ __forceinline__ float ex2(float x)
+    {
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    // out + log(1+exp(-|a+b|)) - log(1+exp(-|a-b|)) on the MUFU pipe
+    // (ex2.approx / lg2.approx: abs. error ~2e-7 on a term added to an LLR of
+    // order 1..30; the parity bound is 1e-4 relative, tests/test_ldpc_gpu.py).
+    static __device__ __forceinline__ float add_corr(float out, float a, float b)
+    {
+        const float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+        float u = ex2(-kLog2e * fabsf(a + b));
+        float v = ex2(-kLog2e * fabsf(a - b));
+        return fmaf(kLn2, __log2f(1.0f + u) - __log2f(1.0f + v), out);
+    }
+    static __device__ __forceinline__ float with_sign_of_product(float mag, float a, float b)
+    {
+        unsigned s = (__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u;
+        return __uint_as_float(__float_as_uint(mag) | s);
+    }
+    static __device__ __noinline__ float tanh_half(float x) { return tanhf(0.5f * x); }
+    static __device__ __noinline__ float atanh2(float x) { return 2.0f * atanhf(x); }
+};
+
+template <>
+struct Num<double> {
+    // Same expression and evaluation order as the reference (c_ldpc.c:246-247).
+    // Not inlined: the fp64 path is the parity mode, and inlining libdevice
+    // exp/log into every unrolled trellis costs minutes of compile time.
+    static __device__ __noinline__ double add_corr(double out, double a, double b)
+    {
+        out += log(1 + exp(-fabs(a + b)));
+        out -= log(1 + exp(-fabs(a - b)));
+        return out;
+    }
+    static __device__ __forceinline__ double with_sign_of_product(double mag, double a, double b)
+    {
+        unsigned long long s = (__double_as_longlong(a) ^ __double_as_longlong(b)) &
+                               0x8000000000000000ull;
+        return __longlong_as_double(__double_as_longlong(mag) | s);
+    }
+    static __device__ __noinline__ double tanh_half(double x) { return tanh(x / 2.0); }
+    static __device__ __noinline__ double atanh2(double x) { return 2.0 * atanh(x); }
+};
+
+// LLR of the XOR of two bits (c_ldpc.c:234-251).  mag >= 0, so OR-ing the sign
+// bit in reproduces "sign(a)sign(b) * min(|a|,|b|)" including signed zeros.
+template <typename T, bool CORR>
+__device__ __forceinline__ T lxor(T a, T b)
+{
+    T out = Num<T>::with_sign_of_product(fmin(fabs(a), fabs(b)), a, b);
+    if (CORR) out = Num<T>::add_corr(out, a, b);
+    return out;
+}
+
+// One check node with its dc messages in registers (c_ldpc.c:294-314).
+// Returns the LLR of the XOR of all inputs (b[0] in the reference).  Lxor is
+// symmetric in its arguments, so only the association order matters and that
+// is the reference's: f[k] = f[k-1] (+) L[k], b[k] = b[k+1] (+) L[k],
+// out[k] = f[k-1] (+) b[k+1].
+template <typename T, int DC, int ALGO>
+__device__ __forceinline__ T check_node(T (&L)[DC], T scale)
+{
+    if (ALGO == LSB_BP_SUMPROD) {   // c_ldpc.c:76-102
+        T t[DC];
+        T prod = (T)1;
+#pragma unroll
+        for (int i = 0; i < DC; ++i) {
+            t[i] = Num<T>::tanh_half(L[i]);
+            prod *= t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < DC; ++i) L[i] = Num<T>::atanh2(prod / t[i]);
+        return Num<T>::atanh2(prod);
+    } else {
+        constexpr bool CORR = (ALGO == LSB_BP_SUMPROD2);
+        T b[DC];
+        b[DC - 1] = L[DC - 1];
+#pragma unroll
+        for (int i = DC - 2; i >= 0; --i) b[i] = lxor<T, CORR>(b[i + 1], L[i]);
+        T f = L[0];
+        L[0] = b[1];
+#pragma unroll
+        for (int i = 1; i < DC - 1; ++i) {
+            T out = lxor<T, CORR>(f, b[i + 1]);
+            f = lxor<T, CORR>(f, L[i]);
+            L[i] = out;
+        }
+        L[DC - 1] = f;
+        if (ALGO == LSB_BP_MINSUM) {
+#pragma unroll
+            for (int i = 0; i < DC; ++i) L[i] *= scale;
+        }
+        return b[0];
+    }
+}
+
+template <typename T, int DC, int ALGO>
+__device__ __forceinline__ T check_node_strided(T *m, int stride, T scale)
+{
+    T L[DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) L[i] = m[i * stride];
+    T syn = check_node<T, DC, ALGO>(L, scale);
+#pragma unroll
+    for (int i = 0; i < DC; ++i) m[i * stride] = L[i];
+    return syn;
+}
+
+// Any degree up to kMaxDc: same recursion with local-memory arrays (generic /
+// compatibility path only; the QC kernel never calls it).
+template <typename T, int ALGO>
+__device__ __noinline__ T check_node_dyn(T *m, int stride, int dc, T scale)
+{
+    T L[kMaxDc], b[kMaxDc];
+    for (int i = 0; i < dc; ++i) L[i] = m[i * stride];
+    T syn;
+    if (ALGO == LSB_BP_SUMPROD) {
+        T prod = (T)1;
+        for (int i = 0; i < dc; ++i) {
+            b[i] = Num<T>::tanh_half(L[i]);
+            prod *= b[i];
+        }
+        for (int i = 0; i < dc; ++i) L[i] = Num<T>::atanh2(prod / b[i]);
+        syn = Num<T>::atanh2(prod);
+    } else {
+        constexpr bool CORR = (ALGO == LSB_BP_SUMPROD2);
+        b[dc - 1] = L[dc - 1];
+        for (int i = dc - 2; i >= 0; --i) b[i] = lxor<T, CORR>(b[i + 1], L[i]);
+        T f = L[0];
+        L[0] = b[1];
+        for (int i = 1; i < dc - 1; ++i) {
+            T out = lxor<T, CORR>(f, b[i + 1]);
+            f = lxor<T, CORR>(f, L[i]);
+            L[i] = out;
+        }
+        L[dc - 1] = f;
+        if (ALGO == LSB_BP_MINSUM)
+            for (int i = 0; i < dc; ++i) L[i] *= scale;
+        syn = b[0];
+    }
+    for (int i = 0; i < dc; ++i) m[i * stride] = L[i];
+    return syn;
+}
+
+// Unrolled trellis for dc in [2, MAXDC]; MAXDC is the kernel's degree bucket.
+template <typename T, int ALGO, int MAXDC>
+__device__ __forceinline__ T check_node_bucket(T *m, int stride, int dc, T scale)
+{
+    switch (dc) {
+#define LSB_CASE(D)                                                              \
+    case D:                                                                      \
+        if (D <= MAXDC) return check_node_strided<T, (D <= MAXDC ? D : 2), ALGO>(m, stride, scale); \
+        break;
+        LSB_CASE(2) LSB_CASE(3) LSB_CASE(4) LSB_CASE(5) LSB_CASE(6) LSB_CASE(7) LSB_CASE(8)
+        LSB_CASE(9) LSB_CASE(10) LSB_CASE(11) LSB_CASE(12) LSB_CASE(13) LSB_CASE(14)
+        LSB_CASE(15) LSB_CASE(16) LSB_CASE(17) LSB_CASE(18) LSB_CASE(19) LSB_CASE(20)
+        LSB_CASE(21) LSB_CASE(22) LSB_CASE(23) LSB_CASE(24)
+#undef LSB_CASE
+        default:
+            break;
+    }
+    return (T)0;   // unreachable for a graph validated against the bucket
+}
+
+// ------------------------------------------------------------------ QC kernel
+template <int MAXDC, int ELEM>
+struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
+    static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? 5 : (MAXDC <= 16 ? 4 : 3));
+};
+
+template <typename T, int ALGO, int MAXDC>
+__global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T)>::value)
+bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *__restrict__ app,
+             uint8_t *__restrict__ hard, int32_t *__restrict__ iters, long long n_frames,
+             int max_it, T scale, unsigned long long *__restrict__ queue)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ QcTables tabs;
+    __shared__ long long s_frame;
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (int)(sizeof(QcTables) / sizeof(int)); i += kThreads)
+        reinterpret_cast<int *>(&tabs)[i] = reinterpret_cast<const int *>(g_tabs)[i];
+    __syncthreads();
+
+    const int z = tabs.z, nv = tabs.nv, nc = tabs.nc;
+    const int n_msg = tabs.n_edges * z;
+    const unsigned magic = tabs.magic;
+    T *msg = reinterpret_cast<T *>(smem_raw);   // [n_edges][z]
+    T *ch = msg + n_msg;                        // [nv]
+    T *ap = ch + nv;                            // [nv]
+
+    for (;;) {
+        if (tid == 0) s_frame = (long long)atomicAdd(queue, 1ull);
+        __syncthreads();
+        const long long f = s_frame;
+        if (f >= n_frames) break;
+
+        const T *frame_llr = llr + f * nv;
+        for (int v = tid; v < nv; v += kThreads) {
+            ch[v] = frame_llr[v];
+            ap[v] = (T)0;
+        }
+        for (int i = tid; i < n_msg; i += kThreads) msg[i] = (T)0;
+        __syncthreads();
+
+        int it = 0;
+        for (; it < max_it; ++it) {
+            // ---- variable nodes: lane = consecutive variables of a column
+            for (int v = tid; v < nv; v += kThreads) {
+                const int c = (int)__umulhi((unsigned)v, magic);
+                const int j = v - c * z;
+                const int t0 = tabs.col_ptr[c], t1 = tabs.col_ptr[c + 1];
+                T total = ch[v];
+                for (int t = t0; t < t1; ++t) {
+                    const int idx = tabs.col_base[t] + j + (j < tabs.col_shift[t] ? z : 0);
+                    total += msg[idx];
+                }
+                for (int t = t0; t < t1; ++t) {
+                    const int idx = tabs.col_base[t] + j + (j < tabs.col_shift[t] ? z : 0);
+                    msg[idx] = total - msg[idx];
+                }
+                ap[v] = total;
+            }
+            __syncthreads();
+            // ---- check nodes: lane = consecutive checks of a (degree-sorted) row
+            int unsatisfied = 0;
+            for (int p = tid; p < nc; p += kThreads) {
+                const int ri = (int)__umulhi((unsigned)p, magic);
+                const int k = p - ri * z;
+                const int r = tabs.row_order[ri];
+                const int e0 = tabs.row_ptr[r];
+                const int dc = tabs.row_ptr[r + 1] - e0;
+                T syn = check_node_bucket<T, ALGO, MAXDC>(msg + e0 * z + k, z, dc, scale);
+                unsatisfied |= (syn <= (T)0);
+            }
+            if (!__syncthreads_or(unsatisfied)) break;
+        }
+
+        if (tid == 0) iters[f] = it;
+        if (app) {
+            T *o = app + f * nv;
+            for (int v = tid; v < nv; v += kThreads) o[v] = ap[v];
+        }
+        if (hard) {
+            uint8_t *o = hard + f * nv;
+            for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
+        }
+    }
+}
+
+// ------------------------------------------------------------- generic kernel
+// Messages in the reference's own numbering (check-ordered array addressed
+// through intrlv on the variable side).  ws: per-CTA [nmsg + nv] scratch.
+template <typename T, int ALGO>
+__global__ void __launch_bounds__(kThreads)
+bp_generic_kernel(const int *__restrict__ voff, const int *__restrict__ coff,
+                  const int *__restrict__ intrlv, int nv, int nc, int nmsg,
+                  const T *__restrict__ llr, T *__restrict__ app, uint8_t *__restrict__ hard,
+                  int32_t *__restrict__ iters, long long n_frames, int max_it, T scale,
+                  T *__restrict__ ws, unsigned long long *__restrict__ queue)
+{
+    __shared__ long long s_frame;
+    const int tid = threadIdx.x;
+    T *msg = ws + (size_t)blockIdx.x * (size_t)(nmsg + nv);
+    T *ap = msg + nmsg;
+
+    for (;;) {
+        if (tid == 0) s_frame = (long long)atomicAdd(queue, 1ull);
+        __syncthreads();
+        const long long f = s_frame;
+        if (f >= n_frames) break;
+        const T *ch = llr + f * nv;
+        for (int i = tid; i < nmsg; i += kThreads) msg[i] = (T)0;
+        for (int v = tid; v < nv; v += kThreads) ap[v] = (T)0;
+        __syncthreads();
+
+        int it = 0;
+        for (; it < max_it; ++it) {
+            for (int v = tid; v < nv; v += kThreads) {
+                const int e0 = voff[v], e1 = voff[v + 1];
+                T total = ch[v];
+                for (int e = e0; e < e1; ++e) total += msg[intrlv[e]];
+                for (int e = e0; e < e1; ++e) {
+                    const int s = intrlv[e];
+                    msg[s] = total - msg[s];
+                }
+                ap[v] = total;
+            }
+            __syncthreads();
+            int unsatisfied = 0;
+            for (int c = tid; c < nc; c += kThreads) {
+                const int b0 = coff[c];
+                T syn = check_node_dyn<T, ALGO>(msg + b0, 1, coff[c + 1] - b0, scale);
+                unsatisfied |= (syn <= (T)0);
+            }
+            if (!__syncthreads_or(unsatisfied)) break;
+        }
+
+        if (tid == 0) iters[f] = it;
+        if (app) {
+            T *o = app + f * nv;
+            for (int v = tid; v < nv; v += kThreads) o[v] = ap[v];
+        }
+        if (hard) {
+            uint8_t *o = hard + f * nv;
+            for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+template <typename T, int ALGO, int MAXDC>
+int launch_qc_bucket(const QcLaunch<T> &a)
+{
+    auto kern = bp_qc_kernel<T, ALGO, MAXDC>;
+    if (*a.cached_grid == 0) {
+        LSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)a.smem));
+        int per_sm = 0;
+        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, a.smem));
+        if (per_sm < 1) per_sm = 1;
+        *a.cached_grid = per_sm * lsb::sm_count();
+    }
+    long long grid = *a.cached_grid;
+    if (grid > a.n_frames) grid = a.n_frames;
+    kern<<<(unsigned)grid, kThreads, a.smem, a.stream>>>(a.tabs, a.llr, a.app, a.hard, a.iters,
+                                                        a.n_frames, a.max_it, a.scale, a.queue);
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+template <typename T, int ALGO>
+int launch_qc_algo(const QcLaunch<T> &a)
+{
+    if (a.max_dc <= 8) return launch_qc_bucket<T, ALGO, 8>(a);
+    if (a.max_dc <= 16) return launch_qc_bucket<T, ALGO, 16>(a);
+    return launch_qc_bucket<T, ALGO, 24>(a);
+}
+
+template <typename T>
+int launch_qc(const QcLaunch<T> &a)
+{
+    switch (a.algo) {
+        case LSB_BP_SUMPROD2: return launch_qc_algo<T, LSB_BP_SUMPROD2>(a);
+        case LSB_BP_SUMPROD: return launch_qc_algo<T, LSB_BP_SUMPROD>(a);
+        default: return launch_qc_algo<T, LSB_BP_MINSUM>(a);
+    }
+}
+
+template <typename T, int ALGO>
+int launch_generic_algo(const GenericLaunch<T> &a)
+{
+    auto kern = bp_generic_kernel<T, ALGO>;
+    kern<<<(unsigned)a.grid, kThreads, 0, a.stream>>>(a.voff, a.coff, a.intrlv, a.nv, a.nc, a.nmsg,
+                                                     a.llr, a.app, a.hard, a.iters, a.n_frames,
+                                                     a.max_it, a.scale, a.ws, a.queue);
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+template <typename T>
+int launch_generic(const GenericLaunch<T> &a)
+{
+    switch (a.algo) {
+        case LSB_BP_SUMPROD2: return launch_generic_algo<T, LSB_BP_SUMPROD2>(a);
+        case LSB_BP_SUMPROD: return launch_generic_algo<T, LSB_BP_SUMPROD>(a);
+        default: return launch_generic_algo<T, LSB_BP_MINSUM>(a);
+    }
+}
+
+template <typename T>
+int generic_blocks_per_sm()
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, bp_generic_kernel<T, LSB_BP_SUMPROD2>, kThreads, 0) != cudaSuccess)
+        per_sm = 1;
+    return per_sm < 1 ? 1 : per_sm;
+}
+
+}  // namespace lsb_bp

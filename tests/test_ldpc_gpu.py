@@ -1,0 +1,268 @@
+"""GPU parity tests of the LDPC BP decoder: CUDA path (through the C-ABI) against
+the reference's golden vectors and the CPU oracle on identical inputs.
+
+Tolerances: fp64 mode -- iteration counts and hard decisions exact, LLRs to 1e-9
+relative (CUDA libm vs glibc differ in the last bits of exp/log); fp32 mode (the
+throughput mode) -- LLRs within 1e-4 relative (north_star), decisions and
+iteration counts exact on frames the reference converges on.
+"""
+import ctypes as ct
+
+import numpy as np
+import pytest
+
+import ldpc_oracle as orc
+from conftest import ALL_CODES
+from ldpc_sparc_b200 import _lib, ldpc
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-4
+
+
+def awgn_llr(c, rng, snr_db, n_frames):
+    x = c.encode(rng.randint(0, 2, (n_frames, c.K)))
+    s2 = 10 ** (-snr_db / 10)
+    return x, 2 / s2 * ((1 - 2.0 * x) + np.sqrt(s2) * rng.randn(n_frames, c.N))
+
+
+def assert_llr_close(app, ref, rtol):
+    scale = np.maximum(np.abs(ref), 1.0)
+    err = np.max(np.abs(app - ref) / scale)
+    assert err <= rtol, "max relative LLR error %.3g > %.1g" % (err, rtol)
+
+
+# ------------------------------------------------------------------ goldens
+def test_fp64_matches_reference_golden_c2(golden_ldpc):
+    c = ldpc.code("802.11n", "1/2", 81)
+    for tag in ("c2_snr12", "c2_snr16", "c2_snr20"):
+        llr, app_ref, it_ref = (golden_ldpc[tag + s] for s in ("_llr", "_app", "_it"))
+        app, it = c.decode(llr, 50, precision="fp64")
+        assert np.array_equal(it, it_ref)
+        assert_llr_close(app, app_ref, 1e-9)
+        assert np.array_equal(app < 0, app_ref < 0)
+
+
+def test_fp32_matches_reference_golden_c2(golden_ldpc):
+    c = ldpc.code("802.11n", "1/2", 81)
+    for tag in ("c2_snr12", "c2_snr16", "c2_snr20"):
+        llr, app_ref, it_ref = (golden_ldpc[tag + s] for s in ("_llr", "_app", "_it"))
+        app, it = c.decode(llr, 50, precision="fp32")
+        conv = it_ref < 50
+        assert conv.any()
+        assert np.array_equal(it[conv], it_ref[conv])
+        assert np.array_equal((app < 0)[conv], (app_ref < 0)[conv])
+        assert_llr_close(app[conv], app_ref[conv], RTOL32)
+
+
+def test_golden_families_both_rules(golden_ldpc):
+    for i, name in enumerate(golden_ldpc["fam_names"]):
+        std, rate, z, pt = str(name).split("|")
+        c = ldpc.code(std, rate, int(z), pt)
+        llr = golden_ldpc["fam%d_llr" % i]
+        for algo in ("sumprod2", "sumprod"):
+            app_ref, it_ref = golden_ldpc["fam%d_app_%s" % (i, algo)], golden_ldpc["fam%d_it_%s" % (i, algo)]
+            app, it = c.decode(llr, 40, algo, precision="fp64")
+            assert np.array_equal(it, it_ref), (name, algo)
+            assert_llr_close(app, app_ref, 1e-8)
+            app32, it32 = c.decode(llr.astype(np.float32), 40, algo, precision="fp32")
+            conv = it_ref < 40
+            assert np.array_equal(it32[conv], it_ref[conv]), (name, algo)
+            assert np.array_equal((app32 < 0)[conv], (app_ref < 0)[conv])
+            if algo == "sumprod2":
+                assert_llr_close(app32[conv], app_ref[conv], RTOL32)
+
+
+def test_lxor_lxfb_known_answers(golden_ldpc):
+    c = ldpc.code("802.11n", "1/2", 27)
+    for (a, b), (o0, o1) in zip(golden_ldpc["lxor_in"], golden_ldpc["lxor_out"]):
+        assert c.Lxor(a, b, 0) == o0
+        assert c.Lxor(a, b, 1) == pytest.approx(o1, rel=1e-12, abs=1e-15)
+    for v, ret, out in zip(golden_ldpc["lxfb_in"], golden_ldpc["lxfb_ret"], golden_ldpc["lxfb_out"]):
+        r, o = c.Lxfb(v, 1)
+        assert r == pytest.approx(ret, rel=1e-12)
+        np.testing.assert_allclose(o, out, rtol=1e-12)
+
+
+# ----------------------------------------------------- reference test semantics
+@pytest.mark.parametrize("standard,rate,z,ptype", ALL_CODES)
+def test_ldpc(standard, rate, z, ptype):
+    """The reference's own test (ldpc_jossy/py/test_ldpc.py:44-69) on the façade."""
+    mycode = ldpc.code(standard, rate, z, ptype)
+    assert len(mycode.proto[0]) == 24
+    H = mycode.pcmat()
+    assert np.sum(mycode.vdeg) == np.sum(mycode.cdeg) == np.sum(H) == len(mycode.intrlv)
+    K = mycode.K
+    rng = np.random.RandomState(0)
+    for k in range(4):
+        u = rng.randint(0, 2, K)
+        x = mycode.encode(u)
+        assert np.count_nonzero(np.mod(np.dot(x, np.transpose(H)), 2)) == 0
+        y = np.array(10 * (.5 - x), dtype=float)
+        app, it = mycode.decode(y, 'sumprod')
+        assert it == 0
+        assert np.count_nonzero(np.array(app < 0, dtype=int) != x) == 0
+        app, it = mycode.decode(y, 'sumprod2')
+        assert it == 0
+        assert np.count_nonzero(np.array(app < 0, dtype=int) != x) == 0
+    # same, batched and in both precisions
+    x = mycode.encode(rng.randint(0, 2, (64, K)))
+    for prec in ("fp32", "fp64"):
+        app, it = mycode.decode(10 * (.5 - x), 200, precision=prec)
+        assert not it.any() and np.array_equal(app < 0, x.astype(bool))
+
+
+# -------------------------------------------------------- oracle on noisy frames
+@pytest.mark.parametrize("snr_db", [1.2, 1.6, 2.0])
+def test_batch_vs_oracle_c2(snr_db):
+    """>= 1k noisy frames in total over the three Es/N0 of SURVEY 8(d)."""
+    c = ldpc.code("802.11n", "1/2", 81)
+    g = orc.Graph(c.vdeg, c.cdeg, c.intrlv)
+    rng = np.random.RandomState(int(snr_db * 10))
+    x, llr = awgn_llr(c, rng, snr_db, 352)
+    app_ref, it_ref = orc.decode_batch(g, llr, 50)
+
+    app, it = c.decode(llr, 50, precision="fp64")
+    assert np.array_equal(it, it_ref)
+    assert np.array_equal(app < 0, app_ref < 0)
+    assert_llr_close(app, app_ref, 1e-8)
+
+    app32, it32 = c.decode(llr.astype(np.float32), 50, precision="fp32")
+    conv = it_ref < 50
+    # fp32 trajectories of frames that converge follow the fp64 ones
+    agree = it32[conv] == it_ref[conv]
+    assert agree.mean() >= 0.99, "iteration counts differ on %d converged frames" % (~agree).sum()
+    sel = np.flatnonzero(conv)[agree]
+    assert np.array_equal((app32 < 0)[sel], (app_ref < 0)[sel])
+    assert_llr_close(app32[sel], app_ref[sel], RTOL32)
+    # frame / bit error counts of the whole batch are identical
+    fe_ref = ((app_ref < 0) != x.astype(bool)).any(1).sum()
+    fe_32 = ((app32 < 0) != x.astype(bool)).any(1).sum()
+    assert fe_ref == fe_32
+
+
+def test_other_codes_vs_oracle():
+    rng = np.random.RandomState(5)
+    for fam, snr in ((("802.16", "1/2", 150, "A"), 1.6), (("802.16", "5/6", 81, "A"), 5.0),
+                     (("802.11n", "3/4", 54, "A"), 4.2), (("802.16", "2/3", 54, "B"), 3.2)):
+        c = ldpc.code(*fam)
+        g = orc.Graph(c.vdeg, c.cdeg, c.intrlv)
+        x, llr = awgn_llr(c, rng, snr, 24)
+        app_ref, it_ref = orc.decode_batch(g, llr, 30)
+        app, it = c.decode(llr, 30, precision="fp64")
+        assert np.array_equal(it, it_ref), fam
+        assert_llr_close(app, app_ref, 1e-8)
+        app32, it32 = c.decode(llr, 30, precision="fp32")
+        conv = (it_ref < 30) & (it32 == it_ref)
+        assert conv.mean() > 0.7
+        assert_llr_close(app32[conv], app_ref[conv], RTOL32)
+
+
+# ------------------------------------------------------------- legacy C symbols
+def test_legacy_symbols_host_pointers():
+    """sumprod2/sumprod exactly as the reference's ctypes call site uses them
+    (ldpc.py:475-485): host double*, long* graph arrays, one frame."""
+    L = _lib.lib()
+    c = ldpc.code("802.16", "2/3", 27, "A")
+    g = orc.Graph(c.vdeg, c.cdeg, c.intrlv)
+    rng = np.random.RandomState(11)
+    x, llr = awgn_llr(c, rng, 3.4, 3)
+    vd, cd, il = (np.ascontiguousarray(a, dtype=np.int_) for a in (c.vdeg, c.cdeg, c.intrlv))
+    for f in range(3):
+        for name in ("sumprod2", "sumprod"):
+            app = np.zeros(c.N)
+            ch = np.ascontiguousarray(llr[f])
+            it = getattr(L, name)(ch.ctypes.data_as(_lib.c_f64p), vd.ctypes.data_as(_lib.c_longp),
+                                  cd.ctypes.data_as(_lib.c_longp), il.ctypes.data_as(_lib.c_longp),
+                                  c.Nv, c.Nc, c.Nmsg, app.ctypes.data_as(_lib.c_f64p), 25)
+            app_ref, it_ref = orc.decode(g, llr[f], 25, name)
+            assert it == it_ref
+            assert_llr_close(app, app_ref, 1e-8)
+    app = np.zeros(c.N)
+    it = L.minsum(ch.ctypes.data_as(_lib.c_f64p), vd.ctypes.data_as(_lib.c_longp), cd.ctypes.data_as(_lib.c_longp),
+                  il.ctypes.data_as(_lib.c_longp), c.Nv, c.Nc, c.Nmsg, app.ctypes.data_as(_lib.c_f64p), 0.7, 25)
+    app_ref, it_ref = orc.decode(g, llr[2], 25, "minsum", 0.7)
+    assert it == it_ref
+    assert_llr_close(app, app_ref, 1e-12)
+
+
+def test_generic_graph_equals_qc_kernel():
+    """The generic (vdeg, cdeg, intrlv) kernel and the QC shared-memory kernel run
+    the same operations in the same order: identical fp64 results."""
+    L = _lib.lib()
+    c = ldpc.code("802.11n", "2/3", 54)
+    rng = np.random.RandomState(2)
+    x, llr = awgn_llr(c, rng, 3.0, 40)
+    app_qc, it_qc = c.decode(llr, 20, precision="fp64")
+    h = ct.c_void_p()
+    vd, cd, il = (np.ascontiguousarray(a, dtype=np.int64) for a in (c.vdeg, c.cdeg, c.intrlv))
+    _lib.check(L.lsb_ldpc_graph_create(vd.ctypes.data_as(_lib.c_i64p), cd.ctypes.data_as(_lib.c_i64p),
+                                       il.ctypes.data_as(_lib.c_i64p), c.Nv, c.Nc, c.Nmsg, ct.byref(h)), "create")
+    app = np.zeros_like(llr)
+    it = np.zeros(len(llr), dtype=np.int32)
+    hard = np.zeros(llr.shape, dtype=np.uint8)
+    _lib.check(L.lsb_ldpc_decode_host_f64(h, llr.ctypes.data, app.ctypes.data, hard.ctypes.data, it.ctypes.data,
+                                          len(llr), 20, 0, 1.0, 1), "decode")
+    L.lsb_ldpc_graph_destroy(h)
+    assert np.array_equal(it, it_qc)
+    assert np.array_equal(app, app_qc)
+    assert np.array_equal(hard.astype(bool), app < 0)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases():
+    c = ldpc.code("802.11n", "1/2", 27)
+    rng = np.random.RandomState(4)
+    x, llr = awgn_llr(c, rng, 2.0, 5)
+    app, it = c.decode(llr[:0].reshape(0, c.N), 10)          # empty batch
+    assert app.shape == (0, c.N) and it.shape == (0,)
+    app, it = c.decode(llr, 0)                               # zero iterations: app untouched (zeros)
+    assert not it.any() and not app.any()
+    app1, it1 = c.decode(llr, 1, precision="fp64")           # one iteration: app = channel LLR
+    assert np.array_equal(app1, llr)
+    a, i = c.decode(llr[3], 50, precision="fp64")            # single frame == row of the batch
+    ab, ib = c.decode(llr, 50, precision="fp64")
+    assert isinstance(i, int) and a.dtype == np.float64 and a.shape == (c.N,)
+    assert i == ib[3] and np.array_equal(a, ab[3])
+
+
+def test_device_tensor_path_and_hard_output():
+    import torch
+    c = ldpc.code("802.11n", "1/2", 81)
+    rng = np.random.RandomState(8)
+    x, llr = awgn_llr(c, rng, 1.8, 300)
+    t = torch.from_numpy(llr.astype(np.float32)).cuda()
+    app, it = c.decode(t, 50)
+    hard, it2 = c.decode_hard(t, 50)
+    torch.cuda.synchronize()
+    app_h, it_h = c.decode(llr.astype(np.float32), 50)
+    assert np.array_equal(it.cpu().numpy(), it_h) and np.array_equal(it2.cpu().numpy(), it_h)
+    assert np.array_equal(app.cpu().numpy().astype(np.float64), app_h)
+    assert np.array_equal(hard.cpu().numpy().astype(bool), app_h < 0)
+
+
+# ------------------------------------- full size (BASELINE config 2): properties
+def test_full_size_symmetry_and_noiseless():
+    """65 536 frames, 50 iterations.  (i) noiseless codewords: it == 0, no errors.
+    (ii) decoder symmetry: for any codeword x, decode(llr * (1-2x)) ==
+    decode(llr) * (1-2x) bit for bit (every operation of the decoder commutes
+    with a sign pattern that satisfies all checks), so the all-zero-codeword
+    batch predicts the random-codeword batch exactly."""
+    import torch
+    c = ldpc.code("802.11n", "1/2", 81)
+    F = 65536
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    rng = np.random.RandomState(0)
+    x = c.encode(rng.randint(0, 2, (256, c.K)))                      # 256 codewords, tiled
+    sgn = torch.from_numpy(1.0 - 2.0 * x).float().cuda().repeat(F // 256, 1)
+    s2 = 10 ** (-1.6 / 10)
+    llr0 = (2 / s2) * (1.0 + (s2 ** 0.5) * torch.randn((F, c.N), device="cuda", generator=gen))
+    app0, it0 = c.decode(llr0, 50)
+    app1, it1 = c.decode(llr0 * sgn, 50)
+    assert torch.equal(it0, it1)
+    assert torch.equal(app0 * sgn, app1)
+    assert int(it0.min()) >= 1 and int(it0.max()) <= 50
+    frame_err = ((app0 < 0).any(1)).float().mean().item()
+    assert frame_err < 0.05          # 802.11n r1/2 n=1944 at 1.6 dB: BLER ~ 1e-2 (results.txt:366-372)
+    app, it = c.decode(10 * sgn * 0.5, 50)
+    assert int(it.max()) == 0 and torch.equal(app < 0, sgn < 0)
