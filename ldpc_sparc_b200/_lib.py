@@ -7,7 +7,8 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldpcsparc_b200.so")
+# LDPC_SPARC_B200_LIB: alternative build of the same library (A/B kernel experiments)
+LIB_PATH = os.environ.get("LDPC_SPARC_B200_LIB") or os.path.join(_HERE, "libldpcsparc_b200.so")
 
 c_f32p = ct.POINTER(ct.c_float)
 c_f64p = ct.POINTER(ct.c_double)

@@ -373,8 +373,7 @@ int lsb_ldpc_graph_create_qc(const int32_t *proto, int rows, int cols, int z,
             const int e = edge_id[r * cols + c];
             if (e < 0) continue;
             const int s = proto[r * cols + c] % z;
-            t.col_shift[nt] = (short)s;
-            t.col_base[nt] = e * z - s;
+            t.col_entry[nt] = make_int2(e * z - s, s);
             ++nt;
         }
     }

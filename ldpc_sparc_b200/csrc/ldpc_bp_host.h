@@ -18,8 +18,7 @@ struct QcTables {
     short row_ptr[kMaxRows + 1];     // protograph edges of row r: [row_ptr[r], row_ptr[r+1])
     short row_order[kMaxRows];       // rows sorted by degree (stable)
     short col_ptr[kMaxCols + 1];
-    short col_shift[kMaxEdges];      // per column-list entry: shift mod z
-    int col_base[kMaxEdges];         // per column-list entry: edge*z - shift
+    int2 col_entry[kMaxEdges];       // per column-list entry: (edge*z - shift, shift mod z)
 };
 
 template <typename T>

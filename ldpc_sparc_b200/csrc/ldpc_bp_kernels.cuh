@@ -32,6 +32,18 @@
 #pragma once
 #include "ldpc_bp_host.h"
 
+// Which fp32 Lxor calls use the 3-MUFU series form of the correction instead of
+// the 4-MUFU lg2 form (see Num<float>::add_corr): bit 0 = backward chain,
+// bit 1 = forward chain, bit 2 = combine step.  Tuned on B200.
+#ifndef LSB_BP_SERIES_MASK
+#define LSB_BP_SERIES_MASK 0
+#endif
+// 1: fp32 sumprod2 takes the stop-rule syndrome from the sign/min rule (same sign
+// and zero as the corrected value, saves one Lxor per check)
+#ifndef LSB_BP_CHEAP_SYNDROME
+#define LSB_BP_CHEAP_SYNDROME 1
+#endif
+
 namespace lsb_bp {
 
 // ---------------------------------------------------------------- arithmetic
@@ -46,15 +58,34 @@ struct Num<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
         return y;
     }
-    // out + log(1+exp(-|a+b|)) - log(1+exp(-|a-b|)) on the MUFU pipe
-    // (ex2.approx / lg2.approx: abs. error ~2e-7 on a term added to an LLR of
-    // order 1..30; the parity bound is 1e-4 relative, tests/test_ldpc_gpu.py).
+    // fp32 sumprod2 messages are kept in the LOG2 DOMAIN: every LLR is scaled by
+    // log2(e) when the frame is loaded (kIn) and by ln 2 when APP is stored (kOut).
+    // The variable-node rule is linear and the stopping rule looks at signs only,
+    // so nothing else changes, and Lxor becomes
+    //   sign*min + lg2(1 + 2^-|a+b|) - lg2(1 + 2^-|a-b|)
+    // with no multiplies: 4 MUFU (2 EX2 + 2 LG2) and 9 other instructions.
+    // (LSB_BP_CORR_LG2 = 0 selects the 3-MUFU variant instead: lg2((1+u)/(1+v)) =
+    // 2 log2(e) atanh(w), w = (u-v)/(2+u+v), |w| <= 1/3, one MUFU.RCP and an odd
+    // series through w^13; it measured slower on B200 because the kernel is bound
+    // by issue slots, not by the MUFU pipe -- see DESIGN.md.)
+    // Abs. error of the correction ~2e-7; parity bound 1e-4 relative.
+    template <bool SERIES>
     static __device__ __forceinline__ float add_corr(float out, float a, float b)
     {
-        const float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-        float u = ex2(-kLog2e * fabsf(a + b));
-        float v = ex2(-kLog2e * fabsf(a - b));
-        return fmaf(kLn2, __log2f(1.0f + u) - __log2f(1.0f + v), out);
+        const float u = ex2(-fabsf(a + b));
+        const float v = ex2(-fabsf(a - b));
+        if (!SERIES) return out + (__log2f(1.0f + u) - __log2f(1.0f + v));
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((u + v) + 2.0f));
+        const float w = (u - v) * r;
+        const float w2 = w * w;
+        float p = fmaf(w2, 1.0f / 13.0f, 1.0f / 11.0f);
+        p = fmaf(p, w2, 1.0f / 9.0f);
+        p = fmaf(p, w2, 1.0f / 7.0f);
+        p = fmaf(p, w2, 1.0f / 5.0f);
+        p = fmaf(p, w2, 1.0f / 3.0f);
+        p = fmaf(p, w2, 1.0f);
+        return fmaf(2.0f * 1.4426950408889634f, w * p, out);
     }
     static __device__ __forceinline__ float with_sign_of_product(float mag, float a, float b)
     {
@@ -70,6 +101,7 @@ struct Num<double> {
     // Same expression and evaluation order as the reference (c_ldpc.c:246-247).
     // Not inlined: the fp64 path is the parity mode, and inlining libdevice
     // exp/log into every unrolled trellis costs minutes of compile time.
+    template <bool SERIES>
     static __device__ __noinline__ double add_corr(double out, double a, double b)
     {
         out += log(1 + exp(-fabs(a + b)));
@@ -86,13 +118,25 @@ struct Num<double> {
     static __device__ __noinline__ double atanh2(double x) { return 2.0 * atanh(x); }
 };
 
+// Scale applied to LLRs entering / leaving a decode (see Num<float>::add_corr).
+template <typename T, int ALGO>
+struct Domain {
+    static __device__ __forceinline__ T in(T x) { return x; }
+    static __device__ __forceinline__ T out(T x) { return x; }
+};
+template <>
+struct Domain<float, LSB_BP_SUMPROD2> {
+    static __device__ __forceinline__ float in(float x) { return x * 1.4426950408889634f; }
+    static __device__ __forceinline__ float out(float x) { return x * 0.6931471805599453f; }
+};
+
 // LLR of the XOR of two bits (c_ldpc.c:234-251).  mag >= 0, so OR-ing the sign
 // bit in reproduces "sign(a)sign(b) * min(|a|,|b|)" including signed zeros.
-template <typename T, bool CORR>
+template <typename T, bool CORR, bool SERIES = false>
 __device__ __forceinline__ T lxor(T a, T b)
 {
     T out = Num<T>::with_sign_of_product(fmin(fabs(a), fabs(b)), a, b);
-    if (CORR) out = Num<T>::add_corr(out, a, b);
+    if (CORR) out = Num<T>::template add_corr<SERIES>(out, a, b);
     return out;
 }
 
@@ -117,16 +161,22 @@ __device__ __forceinline__ T check_node(T (&L)[DC], T scale)
         return Num<T>::atanh2(prod);
     } else {
         constexpr bool CORR = (ALGO == LSB_BP_SUMPROD2);
+        constexpr bool F32 = sizeof(T) == 4;
+        constexpr bool S_BWD = F32 && (LSB_BP_SERIES_MASK & 1), S_FWD = F32 && (LSB_BP_SERIES_MASK & 2),
+                       S_CMB = F32 && (LSB_BP_SERIES_MASK & 4);
         T b[DC];
         b[DC - 1] = L[DC - 1];
 #pragma unroll
-        for (int i = DC - 2; i >= 0; --i) b[i] = lxor<T, CORR>(b[i + 1], L[i]);
+        for (int i = DC - 2; i >= 1; --i) b[i] = lxor<T, CORR, S_BWD>(b[i + 1], L[i]);
+        // b[0] only feeds the stopping rule "<= 0": the uncorrected value has the
+        // same sign and the same zeros (|correction| < min(|a|,|b|))
+        b[0] = (F32 && LSB_BP_CHEAP_SYNDROME) ? lxor<T, false>(b[1], L[0]) : lxor<T, CORR, S_BWD>(b[1], L[0]);
         T f = L[0];
         L[0] = b[1];
 #pragma unroll
         for (int i = 1; i < DC - 1; ++i) {
-            T out = lxor<T, CORR>(f, b[i + 1]);
-            f = lxor<T, CORR>(f, L[i]);
+            T out = lxor<T, CORR, S_CMB>(f, b[i + 1]);
+            f = lxor<T, CORR, S_FWD>(f, L[i]);
             L[i] = out;
         }
         L[DC - 1] = f;
@@ -206,6 +256,54 @@ __device__ __forceinline__ T check_node_bucket(T *m, int stride, int dc, T scale
     return (T)0;   // unreachable for a graph validated against the bucket
 }
 
+// One variable node of a QC column (c_ldpc.c:171-178): total = ch + sum of its
+// dv edge messages in port order (= increasing protograph row); every message is
+// replaced by total - message.  entry[t] = (edge*z - shift, shift): the message
+// of variable j on that edge sits at edge*z + (j - shift mod z).
+template <typename T, int DV>
+__device__ __forceinline__ T variable_node(T *msg, const int2 *entry, int j, int z, T total)
+{
+    int idx[DV];
+    T m[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) {
+        const int2 e = entry[i];
+        idx[i] = e.x + j + (j < e.y ? z : 0);
+        m[i] = msg[idx[i]];
+    }
+#pragma unroll
+    for (int i = 0; i < DV; ++i) total += m[i];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) msg[idx[i]] = total - m[i];
+    return total;
+}
+
+template <typename T>
+__device__ __forceinline__ T variable_node_any(T *msg, const int2 *entry, int dv, int j, int z, T total)
+{
+    switch (dv) {
+#define LSB_CASE(D) \
+    case D:         \
+        return variable_node<T, D>(msg, entry, j, z, total);
+        LSB_CASE(1) LSB_CASE(2) LSB_CASE(3) LSB_CASE(4) LSB_CASE(5) LSB_CASE(6) LSB_CASE(7) LSB_CASE(8)
+        LSB_CASE(9) LSB_CASE(10) LSB_CASE(11) LSB_CASE(12)
+#undef LSB_CASE
+        default:
+            break;
+    }
+    T sum = total;
+    for (int t = 0; t < dv; ++t) {
+        const int2 e = entry[t];
+        sum += msg[e.x + j + (j < e.y ? z : 0)];
+    }
+    for (int t = 0; t < dv; ++t) {
+        const int2 e = entry[t];
+        const int idx = e.x + j + (j < e.y ? z : 0);
+        msg[idx] = sum - msg[idx];
+    }
+    return sum;
+}
+
 // ------------------------------------------------------------------ QC kernel
 template <int MAXDC, int ELEM>
 struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
@@ -242,7 +340,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
 
         const T *frame_llr = llr + f * nv;
         for (int v = tid; v < nv; v += kThreads) {
-            ch[v] = frame_llr[v];
+            ch[v] = Domain<T, ALGO>::in(frame_llr[v]);
             ap[v] = (T)0;
         }
         for (int i = tid; i < n_msg; i += kThreads) msg[i] = (T)0;
@@ -254,17 +352,9 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
             for (int v = tid; v < nv; v += kThreads) {
                 const int c = (int)__umulhi((unsigned)v, magic);
                 const int j = v - c * z;
-                const int t0 = tabs.col_ptr[c], t1 = tabs.col_ptr[c + 1];
-                T total = ch[v];
-                for (int t = t0; t < t1; ++t) {
-                    const int idx = tabs.col_base[t] + j + (j < tabs.col_shift[t] ? z : 0);
-                    total += msg[idx];
-                }
-                for (int t = t0; t < t1; ++t) {
-                    const int idx = tabs.col_base[t] + j + (j < tabs.col_shift[t] ? z : 0);
-                    msg[idx] = total - msg[idx];
-                }
-                ap[v] = total;
+                const int t0 = tabs.col_ptr[c];
+                ap[v] = variable_node_any<T>(msg, tabs.col_entry + t0, tabs.col_ptr[c + 1] - t0, j, z,
+                                             ch[v]);
             }
             __syncthreads();
             // ---- check nodes: lane = consecutive checks of a (degree-sorted) row
@@ -284,7 +374,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
         if (tid == 0) iters[f] = it;
         if (app) {
             T *o = app + f * nv;
-            for (int v = tid; v < nv; v += kThreads) o[v] = ap[v];
+            for (int v = tid; v < nv; v += kThreads) o[v] = Domain<T, ALGO>::out(ap[v]);
         }
         if (hard) {
             uint8_t *o = hard + f * nv;
@@ -323,7 +413,7 @@ bp_generic_kernel(const int *__restrict__ voff, const int *__restrict__ coff,
         for (; it < max_it; ++it) {
             for (int v = tid; v < nv; v += kThreads) {
                 const int e0 = voff[v], e1 = voff[v + 1];
-                T total = ch[v];
+                T total = Domain<T, ALGO>::in(ch[v]);
                 for (int e = e0; e < e1; ++e) total += msg[intrlv[e]];
                 for (int e = e0; e < e1; ++e) {
                     const int s = intrlv[e];
@@ -344,7 +434,7 @@ bp_generic_kernel(const int *__restrict__ voff, const int *__restrict__ coff,
         if (tid == 0) iters[f] = it;
         if (app) {
             T *o = app + f * nv;
-            for (int v = tid; v < nv; v += kThreads) o[v] = ap[v];
+            for (int v = tid; v < nv; v += kThreads) o[v] = Domain<T, ALGO>::out(ap[v]);
         }
         if (hard) {
             uint8_t *o = hard + f * nv;

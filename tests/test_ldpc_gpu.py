@@ -68,9 +68,17 @@ def test_golden_families_both_rules(golden_ldpc):
             app32, it32 = c.decode(llr.astype(np.float32), 40, algo, precision="fp32")
             conv = it_ref < 40
             assert np.array_equal(it32[conv], it_ref[conv]), (name, algo)
-            assert np.array_equal((app32 < 0)[conv], (app_ref < 0)[conv])
             if algo == "sumprod2":
+                assert np.array_equal((app32 < 0)[conv], (app_ref < 0)[conv]), (name, algo)
                 assert_llr_close(app32[conv], app_ref[conv], RTOL32)
+            else:
+                # The tanh-product rule saturates: tanh(m/2) rounds to 1 for |m| > ~17 in
+                # fp32 (|m| > ~37 in the reference's fp64), after which atanh gives inf and
+                # inf - inf = NaN at the variable nodes.  This is the instability the
+                # reference documents (c_ldpc.c:116-127) and why sumprod2 is the default;
+                # fp32 parity is asserted where the rule is still finite.
+                ok = np.isfinite(app32) & np.isfinite(app_ref) & conv[:, None]
+                assert np.array_equal((app32 < 0)[ok], (app_ref < 0)[ok]), (name, algo)
 
 
 def test_lxor_lxfb_known_answers(golden_ldpc):
@@ -153,9 +161,13 @@ def test_other_codes_vs_oracle():
         assert np.array_equal(it, it_ref), fam
         assert_llr_close(app, app_ref, 1e-8)
         app32, it32 = c.decode(llr, 30, precision="fp32")
-        conv = (it_ref < 30) & (it32 == it_ref)
-        assert conv.mean() > 0.7
-        assert_llr_close(app32[conv], app_ref[conv], RTOL32)
+        conv = it_ref < 30
+        assert conv.sum() >= 6, fam
+        agree = it32[conv] == it_ref[conv]
+        assert agree.mean() >= 0.9, (fam, it32[conv], it_ref[conv])
+        sel = np.flatnonzero(conv)[agree]
+        assert np.array_equal((app32 < 0)[sel], (app_ref < 0)[sel]), fam
+        assert_llr_close(app32[sel], app_ref[sel], RTOL32)
 
 
 # ------------------------------------------------------------- legacy C symbols
@@ -266,3 +278,21 @@ def test_full_size_symmetry_and_noiseless():
     assert frame_err < 0.05          # 802.11n r1/2 n=1944 at 1.6 dB: BLER ~ 1e-2 (results.txt:366-372)
     app, it = c.decode(10 * sgn * 0.5, 50)
     assert int(it.max()) == 0 and torch.equal(app < 0, sgn < 0)
+
+
+def test_full_size_statistics_match_recorded_campaign():
+    """The reference's recorded campaign for this code (ldpc_jossy/data/results.txt:787:
+    Es/N0 = 1.60654 dB, sumprod2, <= 200 its): 125 625 blocks, 100 block errors,
+    2 122 217 iterations in total, i.e. 16.893 iterations per block and BLER 8.0e-4.
+    65 536 fresh frames through the CUDA decoder must reproduce both statistics."""
+    import torch
+    c = ldpc.code("802.11n", "1/2", 81)
+    F = 65536
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    s2 = 10 ** (-1.6065359012310576 / 10)
+    llr = (2 / s2) * (1.0 + (s2 ** 0.5) * torch.randn((F, c.N), device="cuda", generator=gen))
+    hard, it = c.decode_hard(llr, 200)
+    mean_it = it.double().mean().item()
+    bler = hard.any(1).double().mean().item()
+    assert abs(mean_it - 2122217 / 125625) < 0.15, mean_it      # sigma of the mean ~ 0.03
+    assert 2e-4 < bler < 2.4e-3, bler                            # 8e-4 +- Poisson noise of both samples
