@@ -134,6 +134,70 @@ int lsb_ldpc_decode_host_f64(const lsb_ldpc_graph *g, const double *llr,
 void *lsb_host_alloc(uint64_t bytes);
 void lsb_host_free(void *p);
 
+/* ------------------------------------- (3) SPARC, sub-sampled DCT design matrix
+ * Replaces the closures sparc_transforms() returns (sparc_public/sparc.py:703-880:
+ * Ab(x) = A x, Az(y) = A^T y) and the AMP loop sparc_amp() (sparc.py:883-999) for
+ * real, unmodulated SPARCs (K = 1), for many frames that share one design.
+ *
+ * A design handle holds, on the device, the base matrix W [Lr x Lc] (a scalar
+ * W is 1x1, a power-allocation vector 1xB, sparc.py:570-589) and per non-zero
+ * block the row / column orderings that generate_ordering() draws
+ * (sparc.py:735-775): order0 [Lr, Lc, Mr] and order1 [Lr, Lc, Mc], entries in
+ * [1, w), Mr = n/Lr, Mc = L*M/Lc, w = 2^ceil(log2(max(Mr, Mc) + 1)); entries of
+ * zero blocks are ignored.  Block (r,c) of A is
+ *   sqrt(W[r,c]/L) * sqrt(2) * cos(pi * order0[i] * (2*order1[j] + 1) / (2w)).
+ */
+typedef struct lsb_sparc_design lsb_sparc_design;
+
+int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n,
+                            const uint32_t *order0, const uint32_t *order1,
+                            lsb_sparc_design **out);
+void lsb_sparc_design_destroy(lsb_sparc_design *g);
+/* L, M, n, Lr, Lc, w, non-zero blocks, shared-memory bytes of the fp32 AMP kernel */
+int lsb_sparc_design_info(const lsb_sparc_design *g, int64_t info[8]);
+
+/* out[f, n] = A x[f, L*M]  and  out[f, L*M] = A^T y[f, n]; device pointers,
+ * asynchronous on `stream`. */
+int lsb_sparc_ab_dev_f32(const lsb_sparc_design *g, const float *x, float *out,
+                         int64_t n_frames, void *stream);
+int lsb_sparc_ab_dev_f64(const lsb_sparc_design *g, const double *x, double *out,
+                         int64_t n_frames, void *stream);
+int lsb_sparc_az_dev_f32(const lsb_sparc_design *g, const float *y, float *out,
+                         int64_t n_frames, void *stream);
+int lsb_sparc_az_dev_f64(const lsb_sparc_design *g, const double *y, double *out,
+                         int64_t n_frames, void *stream);
+
+/* decode_params of the reference (sparc.py:151-170) + the channel noise variance */
+typedef struct lsb_sparc_amp_params {
+    double awgn_var;
+    double rtol;           /* early-stop relative tolerance on psi (default 1e-6)   */
+    double atol;           /* absolute tolerance; the reference uses 2e-15 (:916)   */
+    int32_t t_max;         /* the loop runs at most t_max - 1 iterations (:931)     */
+    int32_t phi_est_method;/* 1: awgn_var + gamma, 2: mean(z^2)  (:949-955)         */
+} lsb_sparc_amp_params;
+
+/* Outputs of one batched AMP decode (device pointers; optional ones may be NULL).
+ * beta_soft / s_last have the element type of the entry point. */
+typedef struct lsb_sparc_amp_out {
+    int32_t *idx;      /* [F, L]          MAP decision: argmax of s per section (:997) */
+    int32_t *t_final;  /* [F]             iterations run, as the reference returns it  */
+    double *psi;       /* [F, Lc]         final psi                                    */
+    float *nmse;       /* [F, t_max, Lc]  NMSE per iteration; needs idx0   (optional)  */
+    void *beta_soft;   /* [F, L*M]        beta of the last iteration       (optional)  */
+    void *s_last;      /* [F, L*M]        s of the last iteration          (optional)  */
+    double *tau_trace; /* [F, t_max, Lc]  tau per iteration                (optional)  */
+    double *psi_trace; /* [F, t_max, Lc]  psi per iteration                (optional)  */
+} lsb_sparc_amp_out;
+
+/* y [F, n] received words; idx0 [F, L] true section indices (NULL unless nmse is
+ * wanted -- the reference takes beta0 for the same purpose, sparc.py:889). */
+int lsb_sparc_amp_dev_f32(lsb_sparc_design *g, const float *y, int64_t n_frames,
+                          const lsb_sparc_amp_params *p, const int32_t *idx0,
+                          const lsb_sparc_amp_out *out, void *stream);
+int lsb_sparc_amp_dev_f64(lsb_sparc_design *g, const double *y, int64_t n_frames,
+                          const lsb_sparc_amp_params *p, const int32_t *idx0,
+                          const lsb_sparc_amp_out *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,17 @@ class LibraryError(RuntimeError):
     pass
 
 
+class AmpParams(ct.Structure):      # lsb_sparc_amp_params
+    _fields_ = [("awgn_var", ct.c_double), ("rtol", ct.c_double), ("atol", ct.c_double),
+                ("t_max", ct.c_int32), ("phi_est_method", ct.c_int32)]
+
+
+class AmpOut(ct.Structure):         # lsb_sparc_amp_out
+    _fields_ = [("idx", ct.c_void_p), ("t_final", ct.c_void_p), ("psi", ct.c_void_p), ("nmse", ct.c_void_p),
+                ("beta_soft", ct.c_void_p), ("s_last", ct.c_void_p), ("tau_trace", ct.c_void_p),
+                ("psi_trace", ct.c_void_p)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/ldpc_sparc_b200.h declares
@@ -49,6 +60,16 @@ SIGNATURES = {
     "lsb_ldpc_decode_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_void_p]),
     "lsb_ldpc_decode_host_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double]),
     "lsb_ldpc_decode_host_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_int]),
+    # SPARC (sub-sampled DCT design)
+    "lsb_sparc_design_create": (ct.c_int, [c_f64p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_u32p, c_u32p, ct.POINTER(ct.c_void_p)]),
+    "lsb_sparc_design_destroy": (None, [ct.c_void_p]),
+    "lsb_sparc_design_info": (ct.c_int, [ct.c_void_p, c_i64p]),
+    "lsb_sparc_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    "lsb_sparc_ab_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    "lsb_sparc_az_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    "lsb_sparc_az_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    "lsb_sparc_amp_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
+    "lsb_sparc_amp_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
 }
 
 

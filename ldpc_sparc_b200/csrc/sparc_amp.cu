@@ -1,0 +1,685 @@
+// SPARC AMP decoder and Ab/Az operators for the sub-sampled DCT design, sm_100a.
+//
+// Reference: sparc_public/sparc.py -- sparc_amp :883-999, sparc_transforms
+// :703-880, msg_vector_mmse_estimator :402-465 (K = 1), msg_vector_map_estimator
+// :467-512 (K = 1).  One CTA decodes one frame at a time out of a device-side
+// frame queue (frames stop early, at different iterations).  Per frame the
+// residual z and the A*beta accumulator live in shared memory next to the FFT
+// buffer; beta / s stream through a per-CTA global scratch (L2 resident).  Per
+// AMP iteration (t >= 1 for the first half):
+//   acc_r = sum_c A_rc beta_c            (one DCT-II per non-zero block)
+//   z     = y - acc + (gamma_r / phi_prev_r) z
+//   phi_r = awgn_var + gamma_r   |   mean(z_r^2)                    (phi_est_method)
+//   tau_c = (L phi / n) / W_c    |   (L / Mr) / sum_r W_rc / phi_r
+//   s_c   = beta_c + tau_c sum_r A_rc^T (z_r / phi_r)   (one DCT-III per block)
+//   beta  = section-wise softmax(s / tau)  (warp shuffles, per-section max shift)
+//   psi_c = 1 - sum(beta_c^2) / (L/Lc), evaluated as sum beta (1 - beta) in fp64
+//   stop when |psi - psi_prev| <= atol + rtol |psi_prev| for every c      (:984)
+// and finally the MAP decision argmax_section(s) (:997).
+#include "common.cuh"
+#include "sparc_dct.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace lsb_sparc;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxLr = 64, kMaxLc = 64;
+constexpr int kCounters = 64;
+
+struct DesignDev {
+    int L, M, n, Lr, Lc, Mr, Mc, w, h, n_blocks, logM;
+    const BlockDev *blocks;        // sorted by (c, r)
+    const int *col_first;          // [Lc + 1] range of blocks of column c
+    const double *W;               // [Lr * Lc]
+};
+
+struct AmpParams {
+    double awgn_var, rtol, atol;
+    int t_max, phi_method;
+};
+
+struct AmpOut {
+    int32_t *idx;        // [F, L] MAP section decisions
+    int32_t *t_final;    // [F]
+    double *psi;         // [F, Lc] final psi
+    float *nmse;         // [F, t_max, Lc] or null (needs idx0)
+    void *beta_soft;     // [F, LM] T or null: beta of the last iteration
+    void *s_last;        // [F, LM] T or null: s of the last iteration
+    double *tau_trace;   // [F, t_max, Lc] or null
+    double *psi_trace;   // [F, t_max, Lc] or null
+};
+
+template <typename T> __device__ __forceinline__ T warp_max(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- A_rc x : scatter a column block into the FFT buffer, DCT-II, leave Y in buf
+template <typename T>
+__device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
+                              const T *x /* Mc entries of the column block, or null */, int one_hot_pos,
+                              int Mc, int H, int tid)
+{
+    T *bf = reinterpret_cast<T *>(buf);
+    for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
+    __syncthreads();
+    if (x) {
+        for (int j = tid; j < Mc; j += kThreads) bf[b.ab_scatter[j]] = x[j];
+    }
+    __syncthreads();
+    fft_inplace<T, false>(buf, tb, tid, kThreads);
+    dct2_post<T>(buf, tb, tid, kThreads);
+}
+
+// ---- A_rc^T y : scatter a row block into the FFT buffer, DCT-III, leave X in buf
+template <typename T>
+__device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
+                                const T *y /* Mr entries of the row block */, T yscale, int Mr, int H, int tid)
+{
+    T *bf = reinterpret_cast<T *>(buf);
+    for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
+    __syncthreads();
+    for (int i = tid; i < Mr; i += kThreads) bf[b.az_scatter[i]] = y[i] * yscale;
+    __syncthreads();
+    dct3_pre<T>(buf, tb, tid, kThreads);
+    fft_inplace<T, true>(buf, tb, tid, kThreads);
+}
+
+template <typename T> struct Scale;
+template <> struct Scale<float> { static __device__ __forceinline__ float get(const BlockDev &b) { return b.scale; } };
+template <> struct Scale<double> { static __device__ __forceinline__ double get(const BlockDev &b) { return b.scale_d; } };
+
+// ------------------------------------------------------------ operator kernels
+// out[f, n] = A x[f, LM]   (reference Ab, sparc.py:786-789,811-819,851-862)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+ab_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ x, T *__restrict__ out, long long n_frames)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    typedef typename Cplx<T>::type T2;
+    const int H = 1 << d.h;
+    T2 *buf = reinterpret_cast<T2 *>(smem);
+    T *acc = reinterpret_cast<T *>(buf + H);   // [n]
+    const int tid = threadIdx.x;
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        for (int i = tid; i < d.n; i += kThreads) acc[i] = (T)0;
+        for (int bi = 0; bi < d.n_blocks; ++bi) {
+            const BlockDev b = d.blocks[bi];
+            block_forward<T>(buf, tb, b, x + f * (long long)d.L * d.M + (long long)b.c * d.Mc, -1, d.Mc, H, tid);
+            const T *bf = reinterpret_cast<const T *>(buf);
+            const T sc = Scale<T>::get(b);
+            for (int i = tid; i < d.Mr; i += kThreads) acc[b.r * d.Mr + i] += sc * bf[b.ab_gather[i]];
+            __syncthreads();
+        }
+        for (int i = tid; i < d.n; i += kThreads) out[f * d.n + i] = acc[i];
+        __syncthreads();
+    }
+}
+
+// out[f, LM] = A^T y[f, n]   (reference Az, sparc.py:791-794,821-829,864-875)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+az_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ y, T *__restrict__ out, long long n_frames)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    typedef typename Cplx<T>::type T2;
+    const int H = 1 << d.h;
+    T2 *buf = reinterpret_cast<T2 *>(smem);
+    const int tid = threadIdx.x;
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        T *o = out + f * (long long)d.L * d.M;
+        for (int c = 0; c < d.Lc; ++c) {
+            for (int bi = d.col_first[c]; bi < d.col_first[c + 1]; ++bi) {
+                const BlockDev b = d.blocks[bi];
+                block_transpose<T>(buf, tb, b, y + f * d.n + b.r * d.Mr, (T)1, d.Mr, H, tid);
+                const T *bf = reinterpret_cast<const T *>(buf);
+                const T sc = Scale<T>::get(b);
+                const bool first = bi == d.col_first[c];
+                for (int j = tid; j < d.Mc; j += kThreads) {
+                    const T v = sc * bf[b.az_gather[j]];
+                    T *dst = o + (long long)c * d.Mc + j;
+                    *dst = first ? v : *dst + v;
+                }
+                __syncthreads();
+            }
+            if (d.col_first[c] == d.col_first[c + 1])
+                for (int j = tid; j < d.Mc; j += kThreads) o[(long long)c * d.Mc + j] = (T)0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ AMP kernel
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_all,
+           const int32_t *__restrict__ idx0, AmpOut o, T *__restrict__ scratch, long long n_frames,
+           unsigned long long *__restrict__ queue)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    typedef typename Cplx<T>::type T2;
+    const int H = 1 << d.h;
+    const int LM = d.L * d.M;
+    T2 *buf = reinterpret_cast<T2 *>(smem);
+    T *z = reinterpret_cast<T *>(buf + H);     // [n]
+    T *acc = z + d.n;                          // [n]
+    __shared__ double psi[kMaxLc], psi_prev[kMaxLc], tau[kMaxLc], nm[kMaxLc];
+    __shared__ double phi[kMaxLr], phi_prev[kMaxLr], gam[kMaxLr], zsq[kMaxLr];
+    __shared__ long long s_frame;
+    __shared__ int s_stop;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    T *beta = scratch + (size_t)blockIdx.x * 2 * (size_t)LM;   // per-CTA scratch
+    T *s = beta + LM;
+    const int secs_per_col = d.Mc / d.M;                       // sections per column block
+    const double sec_norm = (double)d.L / d.Lc;
+
+    for (;;) {
+        if (tid == 0) s_frame = (long long)atomicAdd(queue, 1ull);
+        __syncthreads();
+        const long long f = s_frame;
+        if (f >= n_frames) break;
+        const T *y = y_all + f * d.n;
+
+        for (int i = tid; i < d.n; i += kThreads) z[i] = y[i];            // z = y   (:915)
+        if (tid < d.Lc) psi[tid] = 1.0;                                   // gamma = W.1/Lc  (:918,926)
+        if (tid < kMaxLr) { phi[tid] = 0.0; }
+        __syncthreads();
+
+        int t = 0;
+        for (; t < p.t_max - 1; ++t) {
+            // ---- gamma_r (and, for t > 0, the Onsager coefficient and the new residual)
+            if (tid < d.Lr) {
+                double g = 0.0;
+                for (int c = 0; c < d.Lc; ++c) g += d.W[tid * d.Lc + c] * psi[c];
+                gam[tid] = g / d.Lc;
+                phi_prev[tid] = phi[tid];
+                zsq[tid] = 0.0;
+            }
+            if (tid < d.Lc) psi_prev[tid] = psi[tid];
+            __syncthreads();
+            if (t > 0) {
+                for (int i = tid; i < d.n; i += kThreads) acc[i] = (T)0;
+                for (int bi = 0; bi < d.n_blocks; ++bi) {
+                    const BlockDev b = d.blocks[bi];
+                    block_forward<T>(buf, tb, b, beta + (size_t)b.c * d.Mc, -1, d.Mc, H, tid);
+                    const T *bf = reinterpret_cast<const T *>(buf);
+                    const T sc = Scale<T>::get(b);
+                    for (int i = tid; i < d.Mr; i += kThreads) acc[b.r * d.Mr + i] += sc * bf[b.ab_gather[i]];
+                    __syncthreads();
+                }
+                for (int i = tid; i < d.n; i += kThreads) {                 // z = y - A beta + b z  (:944-946)
+                    const int r = i / d.Mr;
+                    const T coef = (T)(gam[r] / phi_prev[r]);
+                    z[i] = (y[i] - acc[i]) + coef * z[i];
+                }
+                __syncthreads();
+            }
+            // ---- phi (:949-955)
+            if (p.phi_method == 2) {
+                for (int r = 0; r < d.Lr; ++r) {
+                    double part = 0.0;
+                    for (int i = tid; i < d.Mr; i += kThreads) { const double v = (double)z[r * d.Mr + i]; part += v * v; }
+                    part = warp_sum(part);
+                    if (lane == 0) atomicAdd(&zsq[r], part);
+                }
+                __syncthreads();
+            }
+            if (tid < d.Lr) phi[tid] = p.phi_method == 1 ? p.awgn_var + gam[tid] : zsq[tid] / d.Mr;
+            __syncthreads();
+            // ---- tau (:958-969)
+            if (tid < d.Lc) {
+                double tc;
+                if (d.Lr == 1) {
+                    tc = ((double)d.L * phi[0] / d.n) / d.W[tid];
+                } else {
+                    double acc_w = 0.0;
+                    for (int r = 0; r < d.Lr; ++r) acc_w += d.W[r * d.Lc + tid] / phi[r];
+                    tc = ((double)d.L / d.Mr) / acc_w;
+                }
+                tau[tid] = tc;
+                psi[tid] = 0.0;
+                nm[tid] = 0.0;
+                if (o.tau_trace) o.tau_trace[(f * p.t_max + t) * d.Lc + tid] = tc;
+            }
+            __syncthreads();
+            // ---- s = beta + tau * Az(z / phi), column block by column block (:972), then the denoiser
+            for (int c = 0; c < d.Lc; ++c) {
+                const T tau_c = (T)tau[c];
+                T *s_c = s + (size_t)c * d.Mc;
+                const T *beta_c = beta + (size_t)c * d.Mc;
+                const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
+                for (int bi = b0; bi < b1; ++bi) {
+                    const BlockDev b = d.blocks[bi];
+                    block_transpose<T>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid);
+                    const T *bf = reinterpret_cast<const T *>(buf);
+                    const T sc = Scale<T>::get(b) * tau_c;
+                    for (int j = tid; j < d.Mc; j += kThreads) {
+                        const T v = sc * bf[b.az_gather[j]];
+                        if (bi == b0) s_c[j] = (t > 0 ? beta_c[j] : (T)0) + v;
+                        else s_c[j] += v;
+                    }
+                    __syncthreads();
+                }
+                // denoiser: sections of M entries, beta = softmax(s / tau) (:429-432)
+                double psi_part = 0.0, nm_part = 0.0;
+                const T inv_tau = (T)1 / tau_c;
+                if (d.M >= 32) {
+                    const int per_lane = d.M >> 5;
+                    for (int sec = warp; sec < secs_per_col; sec += kThreads / 32) {
+                        T *ss = s_c + (size_t)sec * d.M;
+                        T mx = -INFINITY;
+                        for (int k = 0; k < per_lane; ++k) mx = fmax(mx, ss[lane + 32 * k]);
+                        mx = warp_max(mx);
+                        T sum = (T)0;
+                        for (int k = 0; k < per_lane; ++k) sum += exp((ss[lane + 32 * k] - mx) * inv_tau);
+                        sum = warp_sum(sum);
+                        const T inv = (T)1 / sum;
+                        const int truth = idx0 ? idx0[f * d.L + c * secs_per_col + sec] : -1;
+                        double q = 0.0, e2 = 0.0;
+                        for (int k = 0; k < per_lane; ++k) {
+                            const int j = lane + 32 * k;
+                            const T e = exp((ss[j] - mx) * inv_tau);
+                            const T bta = e * inv;
+                            beta[(size_t)c * d.Mc + (size_t)sec * d.M + j] = bta;
+                            // 1 - sum beta^2 = sum beta (1 - beta); 1 - beta = (sum - e) / sum without cancellation
+                            q += (double)bta * (double)((sum - e) * inv);
+                            const double dlt = (double)bta - (j == truth ? 1.0 : 0.0);
+                            e2 += dlt * dlt;
+                        }
+                        psi_part += q;
+                        nm_part += e2;
+                    }
+                } else {
+                    // M < 32: one lane per entry, 32/M sections per warp pass
+                    const int spw = 32 / d.M;                 // sections per warp
+                    const int sub = lane / d.M, k = lane % d.M;
+                    for (int sec0 = warp * spw; sec0 < secs_per_col; sec0 += (kThreads / 32) * spw) {
+                        const int sec = sec0 + sub;
+                        const bool live = sec < secs_per_col;
+                        const T v = live ? s_c[(size_t)sec * d.M + k] : (T)0;
+                        T mx = v;
+                        for (int off = d.M >> 1; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                        const T e = exp((v - mx) * inv_tau);
+                        T sum = e;
+                        for (int off = d.M >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                        if (live) {
+                            const T inv = (T)1 / sum;
+                            const T bta = e * inv;
+                            beta[(size_t)c * d.Mc + (size_t)sec * d.M + k] = bta;
+                            psi_part += (double)bta * (double)((sum - e) * inv);
+                            const int truth = idx0 ? idx0[f * d.L + c * secs_per_col + sec] : -1;
+                            const double dlt = (double)bta - (k == truth ? 1.0 : 0.0);
+                            nm_part += dlt * dlt;
+                        }
+                    }
+                }
+                psi_part = warp_sum(psi_part);
+                nm_part = warp_sum(nm_part);
+                if (lane == 0) {
+                    atomicAdd(&psi[c], psi_part);
+                    atomicAdd(&nm[c], nm_part);
+                }
+                __syncthreads();
+            }
+            // ---- psi, nmse, early stop (:976-986)
+            if (tid == 0) {
+                int stop = t > 0;
+                for (int c = 0; c < d.Lc; ++c) {
+                    psi[c] /= sec_norm;
+                    if (!(fabs(psi[c] - psi_prev[c]) <= p.atol + p.rtol * fabs(psi_prev[c]))) stop = 0;
+                    if (o.psi_trace) o.psi_trace[(f * p.t_max + t) * d.Lc + c] = psi[c];
+                    if (o.nmse) o.nmse[(f * p.t_max + t + 1) * d.Lc + c] = (float)(nm[c] / sec_norm);
+                }
+                s_stop = stop;
+                if (stop && o.nmse)                                   // nmse[t:] = nmse[t]  (:985)
+                    for (int tt = t + 1; tt < p.t_max; ++tt)
+                        for (int c = 0; c < d.Lc; ++c)
+                            o.nmse[(f * p.t_max + tt) * d.Lc + c] = o.nmse[(f * p.t_max + t) * d.Lc + c];
+            }
+            __syncthreads();
+            if (s_stop) break;
+        }
+        const int t_final = (t < p.t_max - 1) ? t + 1 : p.t_max - 1;   // t + 1 after a break, else last t + 1
+
+        // ---- outputs: MAP decision on s (:997), final psi, optional soft state
+        if (tid == 0) o.t_final[f] = t_final;
+        if (tid < d.Lc) o.psi[f * d.Lc + tid] = psi[tid];
+        for (int sec = warp; sec < d.L; sec += kThreads / 32) {
+            const T *ss = s + (size_t)sec * d.M;
+            T best = -INFINITY;
+            int arg = 0x7fffffff;
+            for (int j = lane; j < d.M; j += 32) {
+                const T v = ss[j];
+                if (v > best) { best = v; arg = j; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const T ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            if (lane == 0) o.idx[f * d.L + sec] = arg;
+        }
+        if (o.beta_soft) {
+            T *dst = reinterpret_cast<T *>(o.beta_soft) + f * LM;
+            for (int i = tid; i < LM; i += kThreads) dst[i] = beta[i];
+        }
+        if (o.s_last) {
+            T *dst = reinterpret_cast<T *>(o.s_last) + f * LM;
+            for (int i = tid; i < LM; i += kThreads) dst[i] = s[i];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+struct lsb_sparc_design {
+    int device = 0;
+    DesignDev dev{};
+    std::vector<void *> allocs;
+    FftTables<float> tb32{};
+    FftTables<double> tb64{};
+    unsigned long long *d_queue = nullptr;
+    std::atomic<unsigned> next_queue{0};
+    std::mutex mu;
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    cudaEvent_t scratch_event = nullptr;
+    int amp_grid[2] = {0, 0};
+};
+
+namespace {
+
+template <typename T>
+int dev_upload(lsb_sparc_design *g, const T **dst, const std::vector<T> &src)
+{
+    void *p = nullptr;
+    LSB_CUDA(cudaMalloc(&p, src.size() * sizeof(T)));
+    g->allocs.push_back(p);
+    LSB_CUDA(cudaMemcpy(p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T *)p;
+    return LSB_OK;
+}
+
+template <typename T, typename T2>
+int make_tables(lsb_sparc_design *g, FftTables<T> *tb, int h)
+{
+    const int H = 1 << h;
+    const double N = 2.0 * H;
+    const double PI = 3.14159265358979323846;
+    std::vector<T2> tw(H), q(H / 2 + 1), pt(H + 1);
+    for (int k = 0; k < H; ++k) tw[k] = T2{(T)cos(2 * PI * k / H), (T)-sin(2 * PI * k / H)};
+    for (int k = 0; k <= H / 2; ++k) q[k] = T2{(T)cos(2 * PI * k / N), (T)-sin(2 * PI * k / N)};
+    for (int k = 0; k <= H; ++k) pt[k] = T2{(T)cos(PI * k / (2 * N)), (T)-sin(PI * k / (2 * N))};
+    int rc;
+    if ((rc = dev_upload(g, &tb->tw, tw))) return rc;
+    if ((rc = dev_upload(g, &tb->q, q))) return rc;
+    if ((rc = dev_upload(g, &tb->pt, pt))) return rc;
+    tb->h = h;
+    return LSB_OK;
+}
+
+inline int brev_host(int k, int h)
+{
+    int r = 0;
+    for (int i = 0; i < h; ++i) r |= ((k >> i) & 1) << (h - 1 - i);
+    return r;
+}
+
+int check_device(const lsb_sparc_design *g)
+{
+    int dev = -1;
+    LSB_CUDA(cudaGetDevice(&dev));
+    LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);
+    return LSB_OK;
+}
+
+size_t amp_smem(const DesignDev &d, size_t elem) { return ((size_t)d.w + 2 * (size_t)d.n) * elem; }
+size_t ab_smem(const DesignDev &d, size_t elem) { return ((size_t)d.w + (size_t)d.n) * elem; }
+size_t az_smem(const DesignDev &d, size_t elem) { return (size_t)d.w * elem; }
+
+template <typename T> const FftTables<T> &tables(const lsb_sparc_design *g);
+template <> const FftTables<float> &tables<float>(const lsb_sparc_design *g) { return g->tb32; }
+template <> const FftTables<double> &tables<double>(const lsb_sparc_design *g) { return g->tb64; }
+
+template <typename T>
+int run_op(const lsb_sparc_design *g, bool transpose, const T *in, T *out, int64_t n_frames, cudaStream_t st)
+{
+    LSB_REQUIRE(g && in && out, "null pointer");
+    LSB_REQUIRE(n_frames >= 0, "negative frame count");
+    if (n_frames == 0) return LSB_OK;
+    int rc = check_device(g);
+    if (rc) return rc;
+    const size_t smem = transpose ? az_smem(g->dev, sizeof(T)) : ab_smem(g->dev, sizeof(T));
+    LSB_REQUIRE(smem <= (size_t)lsb::max_smem_optin(), "transform size %d needs %zu B of shared memory (max %d)",
+                g->dev.w, smem, lsb::max_smem_optin());
+    long long grid = (long long)lsb::sm_count() * 4;
+    if (grid > n_frames) grid = n_frames;
+    if (transpose) {
+        LSB_CUDA(cudaFuncSetAttribute(az_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        az_kernel<T><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out, (long long)n_frames);
+    } else {
+        LSB_CUDA(cudaFuncSetAttribute(ab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ab_kernel<T><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out, (long long)n_frames);
+    }
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+template <typename T>
+int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_amp_params *pp,
+            const int32_t *idx0, const lsb_sparc_amp_out *po, cudaStream_t st)
+{
+    LSB_REQUIRE(g && y && pp && po && po->idx && po->t_final && po->psi, "null pointer");
+    LSB_REQUIRE(pp->t_max > 1, "t_max must be > 1");
+    LSB_REQUIRE(pp->phi_est_method == 1 || pp->phi_est_method == 2, "phi_est_method must be 1 or 2");
+    LSB_REQUIRE(n_frames >= 0, "negative frame count");
+    LSB_REQUIRE(!po->nmse || idx0, "nmse output needs the true section indices idx0");
+    if (n_frames == 0) return LSB_OK;
+    int rc = check_device(g);
+    if (rc) return rc;
+    const size_t smem = amp_smem(g->dev, sizeof(T));
+    LSB_REQUIRE(smem + 4096 <= (size_t)lsb::max_smem_optin(),
+                "design needs %zu B of shared memory per CTA (transform size %d, n %d): unsupported", smem,
+                g->dev.w, g->dev.n);
+    auto kern = amp_kernel<T>;
+    int &cached = g->amp_grid[sizeof(T) == 8];
+    if (cached == 0) {
+        LSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        cached = per_sm * lsb::sm_count();
+    }
+    long long grid = cached < n_frames ? cached : n_frames;
+    const size_t need = (size_t)cached * 2 * (size_t)g->dev.L * g->dev.M * sizeof(double);
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (g->scratch_bytes < need) {
+        LSB_CUDA(cudaDeviceSynchronize());
+        if (g->d_scratch) cudaFree(g->d_scratch);
+        g->d_scratch = nullptr;
+        g->scratch_bytes = 0;
+        LSB_CUDA(cudaMalloc(&g->d_scratch, need));
+        g->scratch_bytes = need;
+    }
+    if (!g->scratch_event) LSB_CUDA(cudaEventCreateWithFlags(&g->scratch_event, cudaEventDisableTiming));
+    else LSB_CUDA(cudaStreamWaitEvent(st, g->scratch_event, 0));
+    unsigned long long *queue = g->d_queue + (g->next_queue.fetch_add(1) % kCounters);
+    LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+    AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method};
+    AmpOut o{po->idx, po->t_final, po->psi, po->nmse, po->beta_soft, po->s_last, po->tau_trace, po->psi_trace};
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o, (T *)g->d_scratch,
+                                                (long long)n_frames, queue);
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    LSB_CUDA(cudaEventRecord(g->scratch_event, st));
+    return LSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n, const uint32_t *order0,
+                            const uint32_t *order1, lsb_sparc_design **out)
+{
+    LSB_REQUIRE(W && order0 && order1 && out, "null pointer");
+    LSB_REQUIRE(Lr >= 1 && Lr <= kMaxLr && Lc >= 1 && Lc <= kMaxLc, "base matrix %dx%d outside [1,%d]x[1,%d]", Lr,
+                Lc, kMaxLr, kMaxLc);
+    LSB_REQUIRE(L > 0 && M > 0 && (M & (M - 1)) == 0 && n > 0, "bad L / M / n");
+    LSB_REQUIRE(((long long)L * M) % Lc == 0 && n % Lr == 0 && L % Lc == 0, "Lc must divide L and LM, Lr must divide n");
+    const int Mr = n / Lr, Mc = (int)((long long)L * M / Lc);
+    LSB_REQUIRE(Mc % M == 0, "column blocks must hold whole sections");
+    int w = 1;
+    while (w < (Mr > Mc ? Mr : Mc) + 1) w <<= 1;
+    LSB_REQUIRE(w >= 4 && w <= 32768, "transform size %d outside [4, 32768] (larger designs not built yet)", w);
+    int h = 0;
+    while ((2 << h) < w) ++h;   // H = w/2 = 2^h
+    const int H = w / 2, N = w;
+
+    lsb_sparc_design *g = new (std::nothrow) lsb_sparc_design();
+    if (!g) return LSB_ERR_NOMEM;
+    if (cudaGetDevice(&g->device) != cudaSuccess) {
+        lsb::set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+        delete g;
+        return LSB_ERR_NO_DEVICE;
+    }
+    int rc = LSB_OK;
+    std::vector<BlockDev> blocks;
+    std::vector<int> col_first(Lc + 1, 0);
+    std::vector<uint16_t> t_abs(Mc), t_abg(Mr), t_azs(Mr), t_azg(Mc);
+    auto slot_of_freq = [&](int K, bool reversed) -> int {   // where (Y[K]) / (c[K]) lives
+        int slot, comp;
+        if (K < H) { slot = K; comp = 0; }
+        else if (K == H) { slot = 0; comp = 1; }
+        else { slot = N - K; comp = 1; }
+        if (reversed) slot = brev_host(slot, h);
+        return 2 * slot + comp;
+    };
+    auto makhoul = [&](int p) -> int { return (p & 1) ? N - 1 - (p - 1) / 2 : p / 2; };
+    for (int c = 0; c < Lc && !rc; ++c) {
+        col_first[c] = (int)blocks.size();
+        for (int r = 0; r < Lr && !rc; ++r) {
+            const double wrc = W[r * Lc + c];
+            if (wrc == 0.0) continue;
+            if (wrc < 0.0) { lsb::set_error("negative base-matrix entry"); rc = LSB_ERR_INVALID; break; }
+            const uint32_t *o0 = order0 + ((size_t)r * Lc + c) * Mr;
+            const uint32_t *o1 = order1 + ((size_t)r * Lc + c) * Mc;
+            for (int j = 0; j < Mc; ++j) {
+                const int p = (int)o1[j];
+                if (p < 1 || p >= N) { lsb::set_error("order1 entry %d outside [1, %d)", p, N); rc = LSB_ERR_INVALID; break; }
+                const int m = makhoul(p);
+                t_abs[j] = (uint16_t)m;
+                t_azg[j] = (uint16_t)(2 * brev_host(m >> 1, h) + (m & 1));
+            }
+            for (int i = 0; i < Mr && !rc; ++i) {
+                const int K = (int)o0[i];
+                if (K < 1 || K >= N) { lsb::set_error("order0 entry %d outside [1, %d)", K, N); rc = LSB_ERR_INVALID; break; }
+                t_abg[i] = (uint16_t)slot_of_freq(K, true);
+                t_azs[i] = (uint16_t)slot_of_freq(K, false);
+            }
+            if (rc) break;
+            BlockDev b;
+            b.r = r;
+            b.c = c;
+            b.scale_d = std::sqrt(2.0 * wrc / L);
+            b.scale = (float)b.scale_d;
+            if ((rc = dev_upload(g, &b.ab_scatter, t_abs))) break;
+            if ((rc = dev_upload(g, &b.ab_gather, t_abg))) break;
+            if ((rc = dev_upload(g, &b.az_scatter, t_azs))) break;
+            if ((rc = dev_upload(g, &b.az_gather, t_azg))) break;
+            blocks.push_back(b);
+        }
+    }
+    col_first[Lc] = (int)blocks.size();
+    if (!rc && blocks.empty()) { lsb::set_error("base matrix has no non-zero entry"); rc = LSB_ERR_INVALID; }
+    DesignDev &d = g->dev;
+    d.L = L; d.M = M; d.n = n; d.Lr = Lr; d.Lc = Lc; d.Mr = Mr; d.Mc = Mc; d.w = w; d.h = h;
+    d.n_blocks = (int)blocks.size();
+    d.logM = 0;
+    while ((1 << d.logM) < M) ++d.logM;
+    if (!rc) rc = dev_upload(g, &d.blocks, blocks);
+    if (!rc) rc = dev_upload(g, &d.col_first, col_first);
+    if (!rc) rc = dev_upload(g, &d.W, std::vector<double>(W, W + (size_t)Lr * Lc));
+    if (!rc) rc = make_tables<float, float2>(g, &g->tb32, h);
+    if (!rc) rc = make_tables<double, double2>(g, &g->tb64, h);
+    if (!rc) {
+        cudaError_t e = cudaMalloc((void **)&g->d_queue, kCounters * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(g->d_queue, 0, kCounters * sizeof(unsigned long long));
+        if (e != cudaSuccess) { lsb::set_error("queue alloc: %s", cudaGetErrorString(e)); rc = LSB_ERR_CUDA; }
+    }
+    if (rc) {
+        lsb_sparc_design_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return LSB_OK;
+}
+
+void lsb_sparc_design_destroy(lsb_sparc_design *g)
+{
+    if (!g) return;
+    cudaDeviceSynchronize();
+    for (void *p : g->allocs) cudaFree(p);
+    cudaFree(g->d_queue);
+    cudaFree(g->d_scratch);
+    if (g->scratch_event) cudaEventDestroy(g->scratch_event);
+    delete g;
+}
+
+int lsb_sparc_design_info(const lsb_sparc_design *g, int64_t info[8])
+{
+    LSB_REQUIRE(g && info, "null pointer");
+    const DesignDev &d = g->dev;
+    info[0] = d.L; info[1] = d.M; info[2] = d.n; info[3] = d.Lr; info[4] = d.Lc; info[5] = d.w;
+    info[6] = d.n_blocks; info[7] = (int64_t)amp_smem(d, 4);
+    return LSB_OK;
+}
+
+int lsb_sparc_ab_dev_f32(const lsb_sparc_design *g, const float *x, float *out, int64_t n_frames, void *stream)
+{
+    return run_op<float>(g, false, x, out, n_frames, (cudaStream_t)stream);
+}
+int lsb_sparc_ab_dev_f64(const lsb_sparc_design *g, const double *x, double *out, int64_t n_frames, void *stream)
+{
+    return run_op<double>(g, false, x, out, n_frames, (cudaStream_t)stream);
+}
+int lsb_sparc_az_dev_f32(const lsb_sparc_design *g, const float *y, float *out, int64_t n_frames, void *stream)
+{
+    return run_op<float>(g, true, y, out, n_frames, (cudaStream_t)stream);
+}
+int lsb_sparc_az_dev_f64(const lsb_sparc_design *g, const double *y, double *out, int64_t n_frames, void *stream)
+{
+    return run_op<double>(g, true, y, out, n_frames, (cudaStream_t)stream);
+}
+
+int lsb_sparc_amp_dev_f32(lsb_sparc_design *g, const float *y, int64_t n_frames, const lsb_sparc_amp_params *p,
+                          const int32_t *idx0, const lsb_sparc_amp_out *out, void *stream)
+{
+    return run_amp<float>(g, y, n_frames, p, idx0, out, (cudaStream_t)stream);
+}
+int lsb_sparc_amp_dev_f64(lsb_sparc_design *g, const double *y, int64_t n_frames, const lsb_sparc_amp_params *p,
+                          const int32_t *idx0, const lsb_sparc_amp_out *out, void *stream)
+{
+    return run_amp<double>(g, y, n_frames, p, idx0, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// Shared-memory sub-sampled DCT operators for SPARC design matrices (sm_100a).
+//
+// Reference semantics (sparc_public/sparc.py:648-701 sub_dct, :703-880
+// sparc_transforms): block (r, c) of the design matrix is
+//     A_rc[i, j] = sqrt(W[r,c]/L) * sqrt(2) * cos(pi * o0[i] * (2*o1[j] + 1) / (2w))
+// with o0 (Mr row indices) and o1 (Mc column indices) drawn from 1..w-1.
+//   Ab block:  out_r[i] += scale * Y[o0[i]],  Y[k] = sum_n x[n] cos(pi k (2n+1)/(2w)),
+//              x = the column block's entries scattered to positions o1  (DCT-II)
+//   Az block:  out_c[j] += scale * X[o1[j]],  X[n] = sum_k y[k] cos(pi k (2n+1)/(2w)),
+//              y = the row block's entries scattered to positions o0     (DCT-III)
+//
+// Each length-w real transform runs as ONE complex FFT of H = w/2 points held in
+// shared memory (Makhoul's even/odd permutation + the real-FFT split), in place:
+// decimation-in-frequency radix-8/4/2 passes, natural order in, bit-reversed
+// order out.  The permutations (o0/o1, Makhoul, bit reversal) are folded on the
+// host into four uint16 index tables per block, so the device scatters and
+// gathers straight between the frame vectors and the FFT buffer:
+//   ab_scatter[j] : float slot of x[o1[j]] in the FFT input
+//   ab_gather[i]  : float slot of Y[o0[i]] after dct2_post
+//   az_scatter[i] : float slot of y[o0[i]] before dct3_pre
+//   az_gather[j]  : float slot of X[o1[j]] after the inverse FFT
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lsb_sparc {
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float> { typedef float2 type; };
+template <> struct Cplx<double> { typedef double2 type; };
+
+template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b)
+{
+    return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T2> __device__ __forceinline__ T2 cconj(T2 a) { return {a.x, -a.y}; }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV, typename T2> __device__ __forceinline__ T2 mul_mi(T2 a)
+{
+    return INV ? T2{-a.y, a.x} : T2{a.y, -a.x};
+}
+
+// Twiddle tables of one transform size (device pointers):
+//   tw[k] = exp(-2 pi i k / H), k < H          (FFT passes)
+//   q[k]  = exp(-2 pi i k / N), k <= H/2       (real-FFT split), N = 2H = w
+//   pt[k] = exp(-i pi k / (2N)), k <= H        (DCT phase)
+template <typename T>
+struct FftTables {
+    const typename Cplx<T>::type *tw, *q, *pt;
+    int h;   // log2(H)
+};
+
+template <bool INV, typename T2> __device__ __forceinline__ T2 twiddle(const T2 *tw, int idx)
+{
+    T2 w = __ldg(tw + idx);
+    return INV ? cconj(w) : w;
+}
+
+// radix-2 DIF butterfly: a' = a + b, b' = (a - b) * w
+template <typename T2> __device__ __forceinline__ void bfly(T2 &a, T2 &b, T2 w)
+{
+    T2 d = csub(a, b);
+    a = cadd(a, b);
+    b = cmul(d, w);
+}
+template <typename T2> __device__ __forceinline__ void bfly1(T2 &a, T2 &b)   // w = 1
+{
+    T2 d = csub(a, b);
+    a = cadd(a, b);
+    b = d;
+}
+
+// One in-place DIF pass of radix 2^LOGR over sub-transforms of size S (S >= R).
+// Thread q handles positions g*S + j + m*(S/R), m < R (g = q / (S/R), j = q % (S/R)).
+template <typename T, int LOGR, bool INV>
+__device__ __forceinline__ void fft_pass(typename Cplx<T>::type *buf, const typename Cplx<T>::type *tw,
+                                         int H, int logS, int tid, int nthreads)
+{
+    typedef typename Cplx<T>::type T2;
+    constexpr int R = 1 << LOGR;
+    const int logQ = logS - LOGR;           // log2(S/R)
+    const int stride = 1 << logQ;
+    const int tw_step = H >> logS;          // table step of w_S
+    const T kR = (T)0.70710678118654752440;
+    for (int q = tid; q < (H >> LOGR); q += nthreads) {
+        const int j = q & (stride - 1);
+        const int base = ((q >> logQ) << logS) + j;
+        T2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = buf[base + m * stride];
+        const T2 w1 = twiddle<INV>(tw, j * tw_step);
+        if (LOGR == 1) {
+            bfly(v[0], v[1], w1);
+        } else if (LOGR == 2) {
+            const T2 w2 = twiddle<INV>(tw, 2 * j * tw_step);
+            bfly(v[0], v[2], w1);
+            bfly(v[1], v[3], mul_mi<INV>(w1));          // w1 * w_4^1
+            bfly(v[0], v[1], w2);
+            bfly(v[2], v[3], w2);
+        } else {
+            const T2 w2 = twiddle<INV>(tw, 2 * j * tw_step);
+            const T2 w4 = twiddle<INV>(tw, 4 * j * tw_step);
+            const T2 r8 = INV ? T2{kR, kR} : T2{kR, -kR};  // w_8^1
+            const T2 w1b = cmul(w1, r8);
+            bfly(v[0], v[4], w1);
+            bfly(v[1], v[5], w1b);
+            bfly(v[2], v[6], mul_mi<INV>(w1));          // w1 * w_8^2
+            bfly(v[3], v[7], mul_mi<INV>(w1b));         // w1 * w_8^3
+            const T2 w2b = mul_mi<INV>(w2);             // w2 * w_4^1
+            bfly(v[0], v[2], w2);
+            bfly(v[1], v[3], w2b);
+            bfly(v[4], v[6], w2);
+            bfly(v[5], v[7], w2b);
+            bfly(v[0], v[1], w4);
+            bfly(v[2], v[3], w4);
+            bfly(v[4], v[5], w4);
+            bfly(v[6], v[7], w4);
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) buf[base + m * stride] = v[m];
+    }
+}
+
+// Complete in-place FFT of H = 2^h points (h >= 1).  Ends with __syncthreads().
+template <typename T, bool INV>
+__device__ void fft_inplace(typename Cplx<T>::type *buf, const FftTables<T> &tb, int tid, int nthreads)
+{
+    const int h = tb.h, H = 1 << h;
+    int n8 = h / 3, rem = h - 3 * n8, n4 = 0, n2 = 0;
+    if (rem == 2) n4 = 1;
+    else if (rem == 1) { if (n8 >= 1) { n8 -= 1; n4 = 2; } else n2 = 1; }
+    int logS = h;
+    for (int i = 0; i < n8; ++i) { fft_pass<T, 3, INV>(buf, tb.tw, H, logS, tid, nthreads); logS -= 3; __syncthreads(); }
+    for (int i = 0; i < n4; ++i) { fft_pass<T, 2, INV>(buf, tb.tw, H, logS, tid, nthreads); logS -= 2; __syncthreads(); }
+    for (int i = 0; i < n2; ++i) { fft_pass<T, 1, INV>(buf, tb.tw, H, logS, tid, nthreads); logS -= 1; __syncthreads(); }
+}
+
+__device__ __forceinline__ int bitrev(int k, int h) { return (int)(__brev((unsigned)k) >> (32 - h)); }
+
+// After the forward FFT of the packed sequence: slot brev(k) <- (Y[k], Y[N-k]),
+// slot 0 <- (Y[0], Y[H]).  Ends with __syncthreads().
+template <typename T>
+__device__ void dct2_post(typename Cplx<T>::type *buf, const FftTables<T> &tb, int tid, int nthreads)
+{
+    typedef typename Cplx<T>::type T2;
+    const int h = tb.h, H = 1 << h;
+    for (int k = tid; k <= (H >> 1); k += nthreads) {
+        if (k == 0) {
+            const T2 z = buf[0];
+            buf[0] = T2{z.x + z.y, (z.x - z.y) * (T)0.70710678118654752440};
+            continue;
+        }
+        const int pa = bitrev(k, h), pb = bitrev(H - k, h);
+        const T2 za = buf[pa], zb = buf[pb];
+        // E = (za + conj(zb))/2, O = -i (za - conj(zb))/2
+        const T2 E = {(T)0.5 * (za.x + zb.x), (T)0.5 * (za.y - zb.y)};
+        const T2 D = {(T)0.5 * (za.x - zb.x), (T)0.5 * (za.y + zb.y)};
+        const T2 O = {D.y, -D.x};
+        const T2 qO = cmul(__ldg(tb.q + k), O);
+        const T2 Vk = cadd(E, qO);                 // V[k]
+        const T2 Vm = cconj(csub(E, qO));          // V[H-k]
+        const T2 ta = cmul(__ldg(tb.pt + k), Vk);
+        buf[pa] = T2{ta.x, -ta.y};
+        if (pb != pa) {
+            const T2 t2 = cmul(__ldg(tb.pt + (H - k)), Vm);
+            buf[pb] = T2{t2.x, -t2.y};
+        }
+    }
+    __syncthreads();
+}
+
+// Before the inverse FFT: natural slot k holds (c[k], c[N-k]), slot 0 holds
+// (c[0], c[H]); rewritten in place with the packed spectrum Zs[k].  Ends with
+// __syncthreads().
+template <typename T>
+__device__ void dct3_pre(typename Cplx<T>::type *buf, const FftTables<T> &tb, int tid, int nthreads)
+{
+    typedef typename Cplx<T>::type T2;
+    const int h = tb.h, H = 1 << h;
+    for (int k = tid; k <= (H >> 1); k += nthreads) {
+        if (k == 0) {
+            const T2 c = buf[0];
+            const T wH = c.y * (T)0.70710678118654752440;
+            buf[0] = T2{c.x + wH, c.x - wH};
+            continue;
+        }
+        const int kb = H - k;
+        const T2 ca = buf[k], cb = buf[kb];
+        // W[k] = conj(pt[k]) (c[k] - i c[N-k]) / 2
+        const T2 Wa = cmul(cconj(__ldg(tb.pt + k)), T2{(T)0.5 * ca.x, (T)-0.5 * ca.y});
+        const T2 Wb = cmul(cconj(__ldg(tb.pt + kb)), T2{(T)0.5 * cb.x, (T)-0.5 * cb.y});
+        const T2 A = cadd(Wa, cconj(Wb));
+        const T2 B = cmul(csub(Wa, cconj(Wb)), cconj(__ldg(tb.q + k)));
+        buf[k] = T2{A.x - B.y, A.y + B.x};                      // A + iB
+        if (kb != k) buf[kb] = T2{A.x + B.y, -A.y + B.x};      // conj(A) + i conj(B)
+    }
+    __syncthreads();
+}
+
+// Device view of one non-zero block of the design.
+struct BlockDev {
+    int r, c;
+    float scale;                       // sqrt(2 W[r,c] / L)
+    double scale_d;
+    const uint16_t *ab_scatter, *ab_gather, *az_scatter, *az_gather;
+};
+
+}  // namespace lsb_sparc

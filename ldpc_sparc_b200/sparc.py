@@ -1,0 +1,500 @@
+"""Drop-in for the reference's ``sparc_public/sparc.py`` (real, unmodulated SPARCs).
+
+Same function names, argument meaning, dict semantics (``check_code_params``
+normalises ``code_params`` IN PLACE, ``sparc_encode`` adds ``n`` / ``R_actual``),
+assertion-style validation and return tuples as the reference (sparc.py:17-74),
+with the design-matrix operators and the AMP decoder running on the GPU through
+libldpcsparc_b200.so:
+
+* ``sparc_encode`` returns ``Ab`` / ``Az`` callables that still work as
+  ``Ab(x)`` / ``Az(y)`` on host arrays and carry the device-resident design, so
+  ``sparc_decode`` (which receives them from the encoder, sparc_sim.py:21-24)
+  runs fully on the GPU;
+* ``sparc_decode`` with ``y`` of shape ``[n]`` behaves like the reference; with
+  ``[F, n]`` (numpy or CUDA tensor) it decodes F frames that share one design and
+  returns batched outputs (``beta`` is then the ``[F, L]`` array of decided
+  section indices instead of F dense one-hot vectors).
+
+Complex / K-PSK modulated SPARCs (sparc.py:203-299,433-459,488-510,593-646) are
+not built: they raise NotImplementedError (there is no CPU fallback).
+"""
+import ctypes as ct
+from copy import copy
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_PRECISION = "fp32"
+
+
+def is_power_of_2(x):
+    return (x > 0) and ((x & (x - 1)) == 0)
+
+
+# ------------------------------------------------------------ parameter checks
+def check_code_params(code_params):
+    """Validates and normalises ``code_params`` in place (reference sparc.py:77-149)."""
+    code_params_copy = {}
+
+    def in_code_param_list(code_param_list):
+        if all([(item in code_params) for item in code_param_list]):
+            for item in code_param_list:
+                code_params_copy[item] = copy(code_params[item])
+        else:
+            raise Exception('Need code parameters {}.'.format(code_param_list))
+
+    for item in ['complex', 'modulated', 'power_allocated', 'spatially_coupled']:
+        if item not in code_params:
+            code_params[item] = False
+        else:
+            assert type(code_params[item]) == bool, "'{}' must be boolean".format(item)
+        code_params_copy[item] = copy(code_params[item])
+
+    code_param_list = ['P', 'R', 'L', 'M']
+    in_code_param_list(code_param_list)
+    P, R, L, M = map(code_params.get, code_param_list)
+    assert (type(P) == float or type(P) == np.float64) and P > 0
+    assert (type(R) == float or type(R) == np.float64) and R > 0
+    assert type(L) == int and L > 0
+    assert type(M) == int and M > 0 and is_power_of_2(M)
+
+    if code_params['modulated']:
+        in_code_param_list(['K'])
+        K = code_params['K']
+        assert type(K) == int and K > 1 and is_power_of_2(K)
+        if not code_params['complex']:
+            assert K == 2, 'Real-modulated SPARCs requires K=2'
+
+    if code_params['power_allocated']:
+        in_code_param_list(['B', 'R_PA_ratio'])
+        B, R_PA_ratio = map(code_params.get, ['B', 'R_PA_ratio'])
+        assert type(B) == int and B > 1
+        assert L % B == 0, 'B must divide L'
+        assert type(R_PA_ratio) == float or type(R_PA_ratio) == np.float64
+        assert R_PA_ratio >= 0
+
+    if code_params['spatially_coupled']:
+        in_code_param_list(['omega', 'Lambda'])
+        omega, Lambda = map(code_params.get, ['omega', 'Lambda'])
+        assert type(omega) == int and omega > 1
+        assert type(Lambda) == int and Lambda >= (2 * omega - 1)
+        assert L % Lambda == 0, 'Lambda must divide L'
+
+    if code_params['power_allocated'] and code_params['spatially_coupled']:
+        assert L % (Lambda * B) == 0, 'Lambda*B must divide L'
+
+    code_params.clear()
+    code_params.update(dict(code_params_copy))
+
+
+def check_decode_params(decode_params):
+    """Reference sparc.py:151-170."""
+    if not all([(item in decode_params) for item in ['t_max']]):
+        raise Exception('Need decode parameters {}.'.format(['t_max']))
+    for key, val in {'rtol': 1e-6, 'phi_est_method': 1}.items():
+        if key not in decode_params:
+            decode_params[key] = val
+    t_max, rtol, phi_est_method = map(decode_params.get, ['t_max', 'rtol', 'phi_est_method'])
+    assert type(t_max) == int and t_max > 1
+    assert type(rtol) == float and 0 < rtol < 1
+    assert phi_est_method == 1 or phi_est_method == 2
+
+
+def _require_real_unmodulated(code_params):
+    if code_params.get('complex') or code_params.get('modulated'):
+        raise NotImplementedError(
+            "complex / K-PSK modulated SPARCs are not built in the B200 path yet (no CPU fallback)")
+
+
+# ---------------------------------------------------------------- bit helpers
+def rnd_bin_arr(k, rand_seed):
+    """Reference sparc.py:174-180."""
+    assert type(k) == int
+    rng = np.random.RandomState(rand_seed)
+    return rng.randint(2, size=k, dtype='bool')
+
+
+def bin_arr_2_int(bin_array):
+    """Reference sparc.py:182-189."""
+    assert bin_array.dtype == 'bool'
+    k = bin_array.size
+    assert 0 < k < 64
+    return bin_array.dot(1 << np.arange(k)[::-1])
+
+
+def int_2_bin_arr(integer, arr_length):
+    """Reference sparc.py:191-197 with its numpy-1.x meaning ('0' -> False)."""
+    assert integer >= 0
+    return np.array([c == '1' for c in np.binary_repr(integer, arr_length)], dtype=bool)
+
+
+def section_indices(bin_arr, M):
+    """Section index (MSB first) of every logM-bit group; ``[..., L*logM] -> [..., L]``."""
+    logM = int(round(np.log2(M)))
+    b = np.asarray(bin_arr).astype(np.int64)
+    assert b.shape[-1] % logM == 0
+    return b.reshape(b.shape[:-1] + (-1, logM)).dot(1 << np.arange(logM)[::-1])
+
+
+def indices_2_bin_arr(idx, M):
+    """Inverse of section_indices; ``[..., L] -> [..., L*logM]`` bool."""
+    logM = int(round(np.log2(M)))
+    idx = np.asarray(idx)
+    bits = (idx[..., None] >> np.arange(logM)[::-1]) & 1
+    return bits.reshape(idx.shape[:-1] + (-1,)).astype(bool)
+
+
+def rnd_msg_vector(L, M, rand_seed, K=1):
+    """Reference sparc.py:303-328 (K = 1)."""
+    if K != 1:
+        raise NotImplementedError("modulated SPARCs are not built")
+    rng = np.random.RandomState(rand_seed)
+    assert type(M) == int and M > 0 and is_power_of_2(M)
+    msg_vector = np.zeros((L, M))
+    msg_vector[(np.arange(L), rng.randint(0, M, L))] = 1
+    return msg_vector.ravel()
+
+
+def bin_arr_2_msg_vector(bin_arr, M, K=1):
+    """Reference sparc.py:330-364 (K = 1)."""
+    if K != 1:
+        raise NotImplementedError("modulated SPARCs are not built")
+    assert type(M) == int and M > 0 and is_power_of_2(M)
+    idx = section_indices(bin_arr, M)
+    msg_vector = np.zeros(idx.size * M)
+    msg_vector[np.arange(idx.size) * M + idx] = 1
+    return msg_vector
+
+
+def msg_vector_2_bin_arr(msg_vector, M, K=1):
+    """Reference sparc.py:366-400 (K = 1)."""
+    if K != 1:
+        raise NotImplementedError("modulated SPARCs are not built")
+    assert type(msg_vector) == np.ndarray
+    assert type(M) == int and M > 0 and is_power_of_2(M)
+    assert msg_vector.size % M == 0
+    L = msg_vector.size // M
+    idxs1, idxs2 = np.nonzero(msg_vector.reshape(L, M))
+    assert np.array_equal(idxs1, np.arange(L))   # exactly 1 nonzero in each row
+    return indices_2_bin_arr(idxs2, M)
+
+
+def msg_vector_map_estimator(s, M, K=1):
+    """Reference sparc.py:467-512 (K = 1): one-hot of the per-section argmax.
+    (Output formatting on the host; inside ``sparc_amp`` the decision is taken on
+    the GPU.)"""
+    if K != 1:
+        raise NotImplementedError("modulated SPARCs are not built")
+    assert type(s) == np.ndarray
+    assert s.size % M == 0
+    L = s.size // M
+    beta = np.zeros((L, M))
+    beta[np.arange(L), s.real.reshape(L, -1).argmax(axis=1)] = 1
+    return beta.ravel()
+
+
+# ------------------------------------------------------------- base matrix W
+def pa_iterative(P, sigmaSqr, B, R_PA):
+    """Iterative power allocation (reference sparc.py:516-533)."""
+    Q = np.zeros(B)
+    for b in range(B):
+        phi = sigmaSqr + P - Q.mean()
+        Pblock = 2 * np.log(2) * R_PA * phi
+        Pspread = (B * P - Q.sum()) / (B - b)
+        if Pblock > Pspread:
+            Q[b:b + 1] = Pblock
+        else:
+            Q[b:] = Pspread
+            break
+    Q /= Q.mean() / P
+    return Q
+
+
+def sc_basic(Q, omega, Lambda):
+    """(omega, Lambda) spatially coupled base matrix (reference sparc.py:535-568)."""
+    assert type(Q) == np.ndarray
+    Lr = Lambda + omega - 1
+    if Q.ndim == 0:
+        W = np.zeros((Lr, Lambda))
+        for c in range(Lambda):
+            W[c:c + omega, c] = Q * Lr / omega
+    elif Q.ndim == 1:
+        B = Q.size
+        W = np.zeros((Lr, Lambda * B))
+        for c in range(Lambda):
+            for r in range(c, c + omega):
+                W[r, c * B:(c + 1) * B] = Q * Lr / omega
+    else:
+        raise Exception('Something wrong with Q')
+    assert np.isclose(W.mean(), np.mean(Q)), "Average base matrix values must equal P"
+    return W
+
+
+def create_base_matrix(P, power_allocated=False, spatially_coupled=False, **kwargs):
+    """Reference sparc.py:570-589."""
+    if not power_allocated:
+        Q = np.array(P)
+    else:
+        awgn_var, B, R, R_PA_ratio = map(kwargs.get, ['awgn_var', 'B', 'R', 'R_PA_ratio'])
+        Q = pa_iterative(P, awgn_var, B, R * R_PA_ratio)
+    if not spatially_coupled:
+        return Q
+    omega, Lambda = map(kwargs.get, ['omega', 'Lambda'])
+    return sc_basic(Q, omega, Lambda)
+
+
+# ----------------------------------------------------------- design + operators
+class Design:
+    """Sub-sampled DCT design matrix: host description + device handle.
+
+    Orderings are drawn exactly as the reference's generate_ordering
+    (sparc.py:735-775): one ``RandomState(rand_seed)``, two ``arange(1, w)`` arrays
+    shuffled in place, cumulatively, once per non-zero block."""
+
+    def __init__(self, W, L, M, n, rand_seed):
+        assert type(W) == np.ndarray
+        assert type(L) == int and type(M) == int and type(n) == int
+        assert L > 0 and M > 0 and n > 0
+        self.W, self.L, self.M, self.n = W, L, M, n
+        if W.ndim == 0:
+            Wm = W.reshape(1, 1).astype(float)
+        elif W.ndim == 1:
+            Wm = W.reshape(1, -1).astype(float)
+            assert L % W.size == 0
+        elif W.ndim == 2:
+            Wm = W.astype(float)
+            assert L % W.shape[1] == 0
+            assert n % W.shape[0] == 0
+        else:
+            raise Exception('Something wrong with base matrix input W')
+        self.Wm = np.ascontiguousarray(Wm)
+        self.Lr, self.Lc = Wm.shape
+        self.Mr, self.Mc = n // self.Lr, L * M // self.Lc
+        self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 1, self.Mc + 1))))
+        idxs0 = np.arange(1, self.w, dtype=np.uint32)
+        idxs1 = np.arange(1, self.w, dtype=np.uint32)
+        rng = np.random.RandomState(rand_seed)
+        self.order0 = np.zeros((self.Lr, self.Lc, self.Mr), dtype=np.uint32)
+        self.order1 = np.zeros((self.Lr, self.Lc, self.Mc), dtype=np.uint32)
+        for r in range(self.Lr):
+            for c in range(self.Lc):
+                if Wm[r, c] != 0:
+                    rng.shuffle(idxs0)
+                    rng.shuffle(idxs1)
+                    self.order0[r, c] = idxs0[:self.Mr]
+                    self.order1[r, c] = idxs1[:self.Mc]
+        self._handle = None
+
+    def handle(self):
+        if self._handle is None:
+            _lib.require_device()
+            h = ct.c_void_p()
+            rc = _lib.lib().lsb_sparc_design_create(
+                self.Wm.ctypes.data_as(_lib.c_f64p), self.Lr, self.Lc, self.L, self.M, self.n,
+                self.order0.ctypes.data_as(_lib.c_u32p), self.order1.ctypes.data_as(_lib.c_u32p), ct.byref(h))
+            if rc == -1 and "transform size" in _lib.last_error():
+                raise NotImplementedError(_lib.last_error())
+            _lib.check(rc, "lsb_sparc_design_create")
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.lib().lsb_sparc_design_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def apply(self, vec, transpose, precision="fp64"):
+        """A @ vec (transpose=False, length L*M -> n) or A.T @ vec, on the GPU.
+        ``vec`` is ``[len]`` or ``[F, len]``; numpy in -> float64 numpy out, CUDA
+        tensor in -> tensor out."""
+        import torch
+        n_in = self.n if transpose else self.L * self.M
+        n_out = self.L * self.M if transpose else self.n
+        is_tensor = isinstance(vec, torch.Tensor)
+        dt = torch.float64 if precision == "fp64" else torch.float32
+        if is_tensor:
+            x = vec.to(dt)
+        else:
+            _lib.require_device()
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(vec, dtype=np.float64))).to("cuda").to(dt)
+        single = x.dim() == 1
+        assert x.shape[-1] == n_in, "x must be %d long" % n_in
+        x = x.reshape(-1, n_in).contiguous()
+        out = torch.empty((x.shape[0], n_out), dtype=dt, device=x.device)
+        L_ = _lib.lib()
+        fn = {(False, "fp32"): L_.lsb_sparc_ab_dev_f32, (False, "fp64"): L_.lsb_sparc_ab_dev_f64,
+              (True, "fp32"): L_.lsb_sparc_az_dev_f32, (True, "fp64"): L_.lsb_sparc_az_dev_f64}[(transpose, precision)]
+        with torch.cuda.device(x.device):
+            _lib.check(fn(self.handle(), x.data_ptr(), out.data_ptr(), x.shape[0],
+                          torch.cuda.current_stream().cuda_stream), "lsb_sparc_ab/az")
+        if single:
+            out = out[0]
+        return out if is_tensor else out.cpu().numpy().astype(np.float64)
+
+
+class _Operator:
+    """Callable returned by sparc_transforms: ``Ab(x)`` / ``Az(y)`` (sparc.py:786-875)."""
+
+    def __init__(self, design, transpose):
+        self.design, self.transpose = design, transpose
+
+    def __call__(self, v, precision="fp64"):
+        return self.design.apply(v, self.transpose, precision)
+
+
+def sparc_transforms(W, L, M, n, rand_seed, csparc=False):
+    """Returns ``Ab(x)`` (A times x, x of length L*M) and ``Az(y)`` (A transpose
+    times y, y of length n) for the sub-sampled DCT design (reference sparc.py:703-880)."""
+    if csparc:
+        raise NotImplementedError("complex SPARCs (sub-sampled FFT design) are not built")
+    design = Design(W, L, M, n, rand_seed)
+    return _Operator(design, False), _Operator(design, True)
+
+
+# -------------------------------------------------------------------- encoder
+def sparc_encode(code_params, awgn_var, rand_seed):
+    """Encode a random message to a SPARC codeword (reference sparc.py:17-53).
+    Returns ``bits_in, beta0, x, Ab, Az``."""
+    check_code_params(code_params)
+    _require_real_unmodulated(code_params)
+    R, L, M = map(code_params.get, ['R', 'L', 'M'])
+    bit_len = int(round(L * np.log2(M)))
+    bits_in = rnd_bin_arr(bit_len, rand_seed)
+    beta0 = bin_arr_2_msg_vector(bits_in, M, 1)
+
+    tmp = code_params.copy()
+    tmp.update({'awgn_var': awgn_var})
+    W = create_base_matrix(**tmp)
+
+    n = int(round(bit_len / R))
+    if W.ndim == 2:
+        Lr, _ = W.shape
+        Mr = int(round(n / Lr))
+        n = Mr * Lr
+    R_actual = bit_len / n
+    code_params.update({'n': n, 'R_actual': R_actual})
+
+    Ab, Az = sparc_transforms(W, L, M, n, rand_seed, code_params['complex'])
+    x = Ab(beta0)
+    return bits_in, beta0, x, Ab, Az
+
+
+# -------------------------------------------------------------------- decoder
+def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None, Az=None,
+              precision=None, return_soft=False, return_trace=False):
+    """AMP decoder (reference sparc.py:883-999).  Returns ``beta, t_final, nmse, psi``
+    (single frame: dense one-hot ``beta``; batch: ``[F, L]`` section indices).
+    With ``return_soft`` / ``return_trace`` a dict of extra arrays (soft beta, s,
+    per-iteration tau and psi) is appended -- used by the parity tests."""
+    import torch
+    _require_real_unmodulated(code_params)
+    P, R, L, M, n = map(code_params.get, ['P', 'R', 'L', 'M', 'n'])
+    tmp = code_params.copy()
+    tmp.update({'awgn_var': awgn_var})
+    W = create_base_matrix(**tmp)
+    assert 0 <= W.ndim <= 2
+    t_max, rtol, phi_est_method = map(decode_params.get, ['t_max', 'rtol', 'phi_est_method'])
+    assert phi_est_method == 1 or phi_est_method == 2
+
+    if (Ab is None) or (Az is None):
+        Ab, Az = sparc_transforms(W, L, M, n, rand_seed, code_params['complex'])
+    if not isinstance(Ab, _Operator):
+        raise TypeError("Ab/Az must come from this module's sparc_transforms / sparc_encode "
+                        "(arbitrary Python closures cannot run on the GPU)")
+    design = Ab.design
+    precision = precision or DEFAULT_PRECISION
+    dt = torch.float64 if precision == "fp64" else torch.float32
+    np_dt = np.float64 if precision == "fp64" else np.float32
+
+    is_tensor = isinstance(y, torch.Tensor)
+    if is_tensor:
+        yt = y.to(dt)
+    else:
+        _lib.require_device()
+        yt = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64))).to("cuda").to(dt)
+    single = yt.dim() == 1
+    assert yt.shape[-1] == n
+    yt = yt.reshape(-1, n).contiguous()
+    F, dev = yt.shape[0], yt.device
+    Lc = design.Lc
+
+    idx0 = None
+    if beta0 is not None:
+        b0 = beta0.cpu().numpy() if isinstance(beta0, torch.Tensor) else np.asarray(beta0)
+        if b0.shape[-1] == L * M:                       # dense message vector(s), as the reference passes
+            b0 = b0.reshape(-1, L, M).argmax(axis=2)
+        b0 = np.broadcast_to(b0.reshape(-1, L), (F, L)) if b0.reshape(-1, L).shape[0] in (1, F) else None
+        if b0 is not None:
+            idx0 = torch.from_numpy(np.ascontiguousarray(b0, dtype=np.int32)).to(dev)
+
+    idx = torch.empty((F, L), dtype=torch.int32, device=dev)
+    t_final = torch.empty(F, dtype=torch.int32, device=dev)
+    psi = torch.empty((F, Lc), dtype=torch.float64, device=dev)
+    nmse = torch.ones((F, t_max, Lc), dtype=torch.float32, device=dev) if idx0 is not None else None
+    beta_soft = torch.empty((F, L * M), dtype=dt, device=dev) if return_soft else None
+    s_last = torch.empty((F, L * M), dtype=dt, device=dev) if return_soft else None
+    tau_tr = torch.zeros((F, t_max, Lc), dtype=torch.float64, device=dev) if return_trace else None
+    psi_tr = torch.zeros((F, t_max, Lc), dtype=torch.float64, device=dev) if return_trace else None
+
+    params = _lib.AmpParams(float(awgn_var), float(rtol), 2 * np.finfo(float).resolution, int(t_max), int(phi_est_method))
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    out = _lib.AmpOut(ptr(idx), ptr(t_final), ptr(psi), ptr(nmse), ptr(beta_soft), ptr(s_last), ptr(tau_tr), ptr(psi_tr))
+    fn = _lib.lib().lsb_sparc_amp_dev_f64 if precision == "fp64" else _lib.lib().lsb_sparc_amp_dev_f32
+    with torch.cuda.device(dev):
+        _lib.check(fn(design.handle(), yt.data_ptr(), F, ct.byref(params), ptr(idx0), ct.byref(out),
+                      torch.cuda.current_stream().cuda_stream), "lsb_sparc_amp_dev")
+
+    extra = {}
+    if return_soft:
+        extra.update(beta_soft=beta_soft, s=s_last)
+    if return_trace:
+        extra.update(tau=tau_tr, psi=psi_tr)
+
+    if is_tensor and not single:
+        res = (idx, t_final, nmse, psi)
+        return res + (extra,) if extra else res
+
+    t_np = t_final.cpu().numpy()
+    psi_np = psi.cpu().numpy()
+    idx_np = idx.cpu().numpy()
+    if nmse is not None:
+        nm = nmse.cpu().numpy().astype(np.float64)   # the kernel applies nmse[t:] = nmse[t] on early stop (sparc.py:985)
+    else:
+        nm = np.ones((F, t_max, Lc))
+    if W.ndim == 0:
+        nm = nm[:, :, 0]
+    extra = {k: v.cpu().numpy() for k, v in extra.items()}
+    if single:
+        beta = np.zeros((L, M))
+        beta[np.arange(L), idx_np[0]] = 1
+        psi_out = psi_np[0, 0] if W.ndim == 0 else psi_np[0]
+        res = (beta.ravel(), int(t_np[0]), nm[0], psi_out)
+        extra = {k: v[0] for k, v in extra.items()}
+    else:
+        res = (idx_np, t_np, nm, psi_np[:, 0] if W.ndim == 0 else psi_np)
+    return res + (extra,) if extra else res
+
+
+def sparc_decode(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None, Az=None, precision=None):
+    """Decode SPARC codeword(s) (reference sparc.py:55-74).  Returns
+    ``bits_out, beta, t_final, nmse, expect_err``."""
+    import torch
+    check_decode_params(decode_params)
+    beta, t_final, nmse, psi = sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab, Az,
+                                         precision=precision)
+    M = code_params['M']
+    if isinstance(beta, torch.Tensor):                  # batched device path
+        expect_err = psi.mean(dim=1) >= 0.001
+        logM = int(round(np.log2(M)))
+        shifts = torch.arange(logM - 1, -1, -1, device=beta.device, dtype=torch.int32)
+        bits_out = ((beta.unsqueeze(-1) >> shifts) & 1).reshape(beta.shape[0], -1).bool()
+        return bits_out, beta, t_final, nmse, expect_err
+    if beta.ndim == 1 and beta.size == code_params['L'] * M:      # single frame: dense one-hot beta
+        expect_err = psi.mean() >= 0.001
+        return msg_vector_2_bin_arr(beta, M, 1), beta, t_final, nmse, expect_err
+    psi2 = np.asarray(psi).reshape(len(beta), -1)
+    return indices_2_bin_arr(beta, M), beta, t_final, nmse, psi2.mean(axis=1) >= 0.001

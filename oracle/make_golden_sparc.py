@@ -1,0 +1,87 @@
+"""SPARC golden vectors from the UNMODIFIED reference (see make_golden.py).
+
+sparc_public: for every case the reference's sparc_encode -> awgn_channel ->
+sparc_decode chain is run under oracle/ref_shims.py, with
+msg_vector_mmse_estimator wrapped (not edited) to record the per-iteration
+(s, tau, beta).  Stored per case/seed: code/decode params, awgn_var, seed, bits_in,
+x, y, and the reference's bits_out, section decisions, t_final, nmse, final psi,
+per-iteration tau / psi, and the last iteration's s and soft beta.
+"""
+import json
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+SPARC_CASES = {
+    # BASELINE config 1: power-allocated, L=1024 M=32 R=1.5 (n=3413, w=4096, 32 blocks)
+    "c1_pa": (dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9), dict(t_max=25), 1.0),
+    # regular (single block, w=8192)
+    "reg": (dict(P=15.0, R=1.3, L=256, M=32), dict(t_max=25), 1.0),
+    # spatially coupled (9x8 band matrix, 16 non-zero blocks, w=2048)
+    "sc": (dict(P=15.0, R=1.4, L=256, M=32, spatially_coupled=True, omega=2, Lambda=8), dict(t_max=25), 1.0),
+    # SC + PA, M=16 (< warp), residual-variance estimate from z (phi_est_method=2), low SNR (errors)
+    "sc_pa_m16": (dict(P=15.0, R=1.4, L=256, M=16, spatially_coupled=True, omega=3, Lambda=8, power_allocated=True,
+                       B=2, R_PA_ratio=0.5), dict(t_max=20, phi_est_method=2), 1.0),
+    # M=64 (> warp), tighter rtol
+    "reg_m64": (dict(P=7.0, R=1.0, L=128, M=64), dict(t_max=30, rtol=1e-4), 1.0),
+}
+SEEDS = ([1, 2], [5, 6])
+
+
+def run_reference(ref, cp, dp, var, seed):
+    R, RS = ref["sparc"], ref["sparc_sim"]
+    cp, dp = dict(cp), dict(dp)
+    bits_i, beta0, x, Ab, Az = R.sparc_encode(cp, var, seed)
+    y = RS.awgn_channel(x, var, seed)
+    trace = []
+    orig = R.msg_vector_mmse_estimator
+
+    def spy(s, tau, M, K=1):
+        out = orig(s, tau, M, K)
+        trace.append((s.copy(), np.copy(tau), out.copy()))
+        return out
+
+    R.msg_vector_mmse_estimator = spy
+    try:
+        bits_o, beta, T, nmse, expect = R.sparc_decode(y, cp, dp, var, seed, beta0, Ab, Az)
+    finally:
+        R.msg_vector_mmse_estimator = orig
+    L, M = cp["L"], cp["M"]
+    W = R.create_base_matrix(**dict(cp, awgn_var=var))
+    Lc = 1 if W.ndim == 0 else W.shape[-1]
+    Mc = L * M // Lc
+    tau_it = np.array([np.broadcast_to(np.asarray(t[1], dtype=float).reshape(-1), (L * M,))[::Mc] if np.ndim(t[1]) else
+                       np.full(Lc, float(t[1])) for t in trace])
+    psi_it = np.array([1 - (t[2] ** 2).reshape(Lc, -1).sum(axis=1) / (L / Lc) for t in trace])
+    return dict(bits_in=bits_i, x=x, y=y, bits_out=bits_o, idx=beta.reshape(L, M).argmax(1).astype(np.int32),
+                t_final=np.array(T), nmse=np.asarray(nmse), expect_err=np.array(bool(expect)),
+                tau_it=tau_it, psi_it=psi_it, s_last=trace[-1][0].astype(np.float32),
+                beta_soft=trace[-1][2].astype(np.float32), n=np.array(cp["n"]))
+
+
+def make_sparc(ref):
+    out = {}
+    meta = {}
+    for name, (cp, dp, var) in SPARC_CASES.items():
+        meta[name] = dict(code_params=cp, decode_params=dp, awgn_var=var, seeds=[list(s) for s in SEEDS])
+        for si, seed in enumerate(SEEDS):
+            r = run_reference(ref, cp, dp, var, seed)
+            for k, v in r.items():
+                out["%s_s%d_%s" % (name, si, k)] = v
+            print(name, seed, "t_final", int(r["t_final"]), "section errors",
+                  int((r["idx"] != (r["bits_in"].reshape(-1, int(np.log2(cp["M"]))).astype(int)
+                                    .dot(1 << np.arange(int(np.log2(cp["M"])))[::-1]))).sum()), "n", int(r["n"]))
+    out["meta_json"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(GOLD, "sparc_reference.npz"), **out)
+    print("sparc_reference.npz: %.1f kB" % (os.path.getsize(os.path.join(GOLD, "sparc_reference.npz")) / 1e3))
+
+
+def make_sophie(ref):
+    try:
+        from make_golden_sophie import make_sophie as _mk
+    except ImportError:
+        print("sophie goldens: generator not present yet")
+        return
+    _mk(ref)

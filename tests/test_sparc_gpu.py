@@ -1,0 +1,182 @@
+"""GPU parity tests of the SPARC path (sub-sampled DCT design): Ab/Az operators and
+the AMP decoder against the reference's golden vectors and the numpy oracle.
+
+Tolerances: fp64 mode -- per-iteration tau / psi to 1e-9 relative, t_final and
+section decisions exact; fp32 mode (throughput) -- tau / psi / beta within 1e-4
+relative (north_star), section decisions exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sparc_oracle as so
+from conftest import GOLDEN
+from ldpc_sparc_b200 import sparc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(os.path.join(GOLDEN, "sparc_reference.npz"))
+    return g, json.loads(str(g["meta_json"]))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+# ------------------------------------------------------------------ operators
+@pytest.mark.parametrize("shape", ["scalar", "vector", "matrix"])
+def test_ab_az_against_dense_matrix(shape):
+    rng = np.random.RandomState(1)
+    if shape == "scalar":
+        W, L, M, n = np.array(3.0), 16, 8, 70
+    elif shape == "vector":
+        W, L, M, n = np.array([1.0, 2.5, 0.5, 4.0]), 16, 16, 100
+    else:
+        W, L, M, n = so.sc_basic(np.array([2.0, 1.0]), 2, 3), 12, 8, 48
+    Ab, Az = sparc.sparc_transforms(W, L, M, n, [3, 4])
+    A = so.Design(W, L, M, n, [3, 4]).dense()
+    x, y = rng.randn(5, L * M), rng.randn(5, n)
+    for prec, tol in (("fp64", 1e-11), ("fp32", 2e-5)):
+        ax = Ab(x, precision=prec)
+        ay = Az(y, precision=prec)
+        assert ax.shape == (5, n) and ay.shape == (5, L * M)
+        assert np.max(np.abs(ax - x @ A.T)) <= tol * np.max(np.abs(x @ A.T))
+        assert np.max(np.abs(ay - y @ A)) <= tol * np.max(np.abs(y @ A))
+    # single vectors, as the reference closures are called
+    assert np.allclose(Ab(x[0]), A @ x[0], rtol=1e-10, atol=1e-10)
+    assert np.allclose(Az(y[0]), A.T @ y[0], rtol=1e-10, atol=1e-10)
+    # adjointness <Ax, y> == <x, A^T y>
+    assert np.isclose(np.dot(Ab(x[1]), y[1]), np.dot(x[1], Az(y[1])), rtol=1e-10)
+
+
+def test_operators_c1_size_vs_oracle(gold):
+    """BASELINE config 1 design (w = 4096, 32 blocks): encode x = A beta0 equals the
+    reference's codeword, A^T y equals the oracle's."""
+    g, meta = gold
+    m = meta["c1_pa"]
+    cp = dict(m["code_params"])
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], m["seeds"][0])
+    assert cp["n"] == 3413 and np.array_equal(bits_in, g["c1_pa_s0_bits_in"])
+    assert rel_err(x, g["c1_pa_s0_x"]) < 1e-9 or np.max(np.abs(x - g["c1_pa_s0_x"])) < 1e-10
+    y = g["c1_pa_s0_y"]
+    d = so.Design(sparc.create_base_matrix(**dict(cp, awgn_var=1.0)), 1024, 32, 3413, m["seeds"][0])
+    ref = d.Az(y)
+    assert np.max(np.abs(Az(y) - ref)) < 1e-10 * np.max(np.abs(ref))
+    assert np.max(np.abs(Az(y, precision="fp32") - ref)) < 2e-5 * np.max(np.abs(ref))
+
+
+# ---------------------------------------------------------------- AMP goldens
+def _decode_case(g, meta, name, si, precision, **kw):
+    m = meta[name]
+    pre = "%s_s%d_" % (name, si)
+    cp, dp = dict(m["code_params"]), dict(m["decode_params"])
+    seed = m["seeds"][si]
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], seed)
+    sparc.check_decode_params(dp)
+    y = g[pre + "y"]
+    out = sparc.sparc_amp(y, cp, dp, m["awgn_var"], seed, beta0, Ab, Az, precision=precision,
+                          return_soft=True, return_trace=True)
+    return pre, cp, dp, out
+
+
+@pytest.mark.parametrize("name", ["c1_pa", "reg", "sc", "sc_pa_m16", "reg_m64"])
+def test_amp_fp64_matches_reference_golden(gold, name):
+    g, meta = gold
+    for si in range(2):
+        pre, cp, dp, (beta, t_final, nmse, psi, ex) = _decode_case(g, meta, name, si, "fp64")
+        T = int(g[pre + "t_final"])
+        assert t_final == T
+        assert np.array_equal(beta.reshape(-1, cp["M"]).argmax(1), g[pre + "idx"])
+        assert rel_err(ex["tau"][:T], g[pre + "tau_it"]) < 1e-9
+        ref_psi = g[pre + "psi_it"]
+        assert np.max(np.abs(ex["psi"][:T] - ref_psi)) <= 1e-9 * np.max(np.abs(ref_psi)) + 1e-13
+        assert np.max(np.abs(ex["s"] - g[pre + "s_last"])) <= 2e-6 * np.max(np.abs(g[pre + "s_last"]))   # golden s is fp32
+        assert np.allclose(nmse, g[pre + "nmse"], rtol=1e-5, atol=1e-7)                                      # nmse out is fp32
+
+
+@pytest.mark.parametrize("name", ["c1_pa", "reg", "sc", "sc_pa_m16", "reg_m64"])
+def test_amp_fp32_matches_reference_golden(gold, name):
+    g, meta = gold
+    for si in range(2):
+        pre, cp, dp, (beta, t_final, nmse, psi, ex) = _decode_case(g, meta, name, si, "fp32")
+        T = int(g[pre + "t_final"])
+        assert np.array_equal(beta.reshape(-1, cp["M"]).argmax(1), g[pre + "idx"])       # decisions exact
+        # The reference stops when every psi_c moved by < 1e-6 relative (sparc.py:984);
+        # fp32 iterates reach that only once they are bitwise stationary, which can
+        # take a few more iterations (never fewer): decisions are unaffected.
+        assert T - 1 <= t_final <= dp["t_max"] - 1, (t_final, T)
+        Tc = min(T, t_final)
+        assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < 1e-4
+        ref_psi = g[pre + "psi_it"][:Tc]
+        # psi within 1e-4 relative, plus an absolute floor: once a block has converged
+        # (psi ~ 1e-6) psi = sum beta(1-beta) is exp(-gap/tau) with gap/tau ~ 10..100, so
+        # the fp32 rounding of s is amplified by 1/tau; tau (the quantity the decoder
+        # uses) stays within 1e-4 because it depends on sum_c W_c psi_c only
+        assert np.all(np.abs(ex["psi"][:Tc] - ref_psi) <= 1e-4 * ref_psi + 2e-8)
+        if t_final == T:
+            ref_beta = g[pre + "beta_soft"].astype(np.float64)
+            assert np.max(np.abs(ex["beta_soft"] - ref_beta)) < 1e-4
+
+
+def test_sparc_decode_dropin_single_frame(gold):
+    """sparc_encode -> awgn -> sparc_decode exactly as sparc_sim.py:21-24 calls them."""
+    g, meta = gold
+    m = meta["c1_pa"]
+    for si in range(2):
+        pre = "c1_pa_s%d_" % si
+        cp, dp = dict(m["code_params"]), dict(m["decode_params"])
+        seed = m["seeds"][si]
+        bits_i, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], seed)
+        y = so.awgn_channel(x, m["awgn_var"], seed)
+        assert np.max(np.abs(y - g[pre + "y"])) < 1e-9
+        bits_o, beta, T, nmse, expect = sparc.sparc_decode(g[pre + "y"], cp, dp, m["awgn_var"], seed, beta0, Ab, Az,
+                                                           precision="fp64")
+        assert bits_o.dtype == bool and np.array_equal(bits_o, g[pre + "bits_out"])
+        assert beta.shape == (1024 * 32,) and beta.sum() == 1024 and T == int(g[pre + "t_final"])
+        assert nmse.shape == (25, 32) and bool(expect) == bool(g[pre + "expect_err"])
+        # decoder that rebuilds the transforms from rand_seed (Ab = Az = None, sparc.py:910-911)
+        bits_o2, _, T2, _, _ = sparc.sparc_decode(g[pre + "y"], cp, dp, m["awgn_var"], seed, beta0, precision="fp64")
+        assert np.array_equal(bits_o2, bits_o) and T2 == T
+
+
+def test_batched_decode_vs_oracle():
+    """64 frames sharing one design (C1 shape), messages and noise per frame: section
+    decisions identical to the oracle's frame by frame, in both precisions."""
+    import torch
+    cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
+    dp = dict(t_max=25)
+    sparc.check_code_params(cp)
+    sparc.check_decode_params(dp)
+    W = sparc.create_base_matrix(**dict(cp, awgn_var=1.0))
+    n = 3413
+    cp["n"] = n
+    Ab, Az = sparc.sparc_transforms(W, 1024, 32, n, [1, 2])
+    rng = np.random.RandomState(0)
+    F = 64
+    idx0 = rng.randint(0, 32, (F, 1024))
+    beta0 = np.zeros((F, 1024 * 32))
+    beta0[np.arange(F)[:, None], np.arange(1024)[None, :] * 32 + idx0] = 1
+    y = Ab(beta0) + rng.randn(F, n)
+    d = so.Design(W, 1024, 32, n, [1, 2])
+    ref = [so.sparc_decode(y[f], cp, dp, 1.0, d, beta0[f]) for f in range(8)]
+    for prec in ("fp64", "fp32"):
+        bits, idx, T, nmse, expect = sparc.sparc_decode(y, cp, dp, 1.0, [1, 2], idx0, Ab, Az, precision=prec)
+        assert idx.shape == (F, 1024) and bits.shape == (F, 5120) and nmse.shape == (F, 25, 32)
+        for f in range(8):
+            assert np.array_equal(idx[f], ref[f][1].reshape(1024, 32).argmax(1)), (prec, f)
+            assert np.array_equal(bits[f], ref[f][0])
+            if prec == "fp64":
+                assert T[f] == ref[f][2]
+                assert np.allclose(nmse[f], ref[f][3], rtol=1e-5, atol=1e-7)
+        assert (idx != idx0).mean() < 5e-3                       # section error rate of this operating point
+    # device-tensor path returns tensors and the same decisions
+    yt = torch.from_numpy(y).cuda()
+    bits_t, idx_t, T_t, _, _ = sparc.sparc_decode(yt, cp, dp, 1.0, [1, 2], None, Ab, Az)
+    assert np.array_equal(idx_t.cpu().numpy(), idx)
+    assert np.array_equal(bits_t.cpu().numpy(), bits)

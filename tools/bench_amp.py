@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Throughput of the batched SPARC AMP decoder on BASELINE config 1 (sparc_public,
+power-allocated, L=1024 M=32 R=1.5, sub-sampled DCT design, t_max=25, awgn_var=1).
+
+Prints one JSON object: decoded info bits/s, frames/s, mean iterations, section error
+rate, and the achieved fraction of the HBM state-streaming model of SURVEY 8(d)
+(303 100 B per frame-iteration).  `python tools/bench_amp.py [--frames F] [--steps K]`.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_FRAME_ITER = 303100
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=8192)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--precision", default="fp32")
+    args = ap.parse_args()
+    import torch
+    from ldpc_sparc_b200 import sparc
+
+    cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
+    dp = dict(t_max=25)
+    sparc.check_code_params(cp)
+    sparc.check_decode_params(dp)
+    W = sparc.create_base_matrix(**dict(cp, awgn_var=1.0))
+    n = int(round(1024 * 5 / 1.5))
+    cp["n"] = n
+    Ab, Az = sparc.sparc_transforms(W, 1024, 32, n, [1, 2])
+    F = args.frames
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    idx0 = torch.randint(0, 32, (F, 1024), device="cuda", generator=gen, dtype=torch.int32)
+    y = torch.empty((F, n), device="cuda", dtype=torch.float32)
+    for f0 in range(0, F, 1024):     # x = A beta0 in chunks (beta0 is 128 KB per frame)
+        f1 = min(F, f0 + 1024)
+        beta0 = torch.zeros((f1 - f0, 1024 * 32), device="cuda", dtype=torch.float32)
+        beta0.view(f1 - f0, 1024, 32).scatter_(2, idx0[f0:f1].long().unsqueeze(-1), 1.0)
+        y[f0:f1] = Ab(beta0, precision="fp32") + torch.randn((f1 - f0, n), device="cuda", generator=gen)
+    del beta0
+
+    def step():
+        return sparc.sparc_decode(y, cp, dp, 1.0, [1, 2], None, Ab, Az, precision=args.precision)
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    bits, idx, T, _, _ = out
+    its = T.double().mean().item()
+    frame_iters = float(T.sum().item())
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    achieved = BYTES_PER_FRAME_ITER * frame_iters / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "workload": "sparc_public AMP decode, PA L=1024 M=32 R=1.5 (n=%d), t_max=25, %d frames sharing one design" % (n, F),
+        "precision": args.precision, "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
+        "info_bits_per_s": F * 5120 / (ms * 1e-3), "mean_iterations": its,
+        "section_error_rate": float((idx != idx0).float().mean().item()),
+        "roofline": {"bound": "hbm (state-streaming model; really shared-memory/FFT bound, DESIGN.md)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
+    }))
+
+
+if __name__ == "__main__":
+    main()
