@@ -165,7 +165,7 @@ az_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ y, T *__restrict__
 
 // ------------------------------------------------------------------ AMP kernel
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
 amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_all,
            const int32_t *__restrict__ idx0, AmpOut o, T *__restrict__ scratch, long long n_frames,
            unsigned long long *__restrict__ queue)
@@ -424,13 +424,11 @@ int make_tables(lsb_sparc_design *g, FftTables<T> *tb, int h)
     const int H = 1 << h;
     const double N = 2.0 * H;
     const double PI = 3.14159265358979323846;
-    std::vector<T2> tw(H), q(H / 2 + 1), pt(H + 1);
+    std::vector<T2> tw(H), pt(H + 1);
     for (int k = 0; k < H; ++k) tw[k] = T2{(T)cos(2 * PI * k / H), (T)-sin(2 * PI * k / H)};
-    for (int k = 0; k <= H / 2; ++k) q[k] = T2{(T)cos(2 * PI * k / N), (T)-sin(2 * PI * k / N)};
     for (int k = 0; k <= H; ++k) pt[k] = T2{(T)cos(PI * k / (2 * N)), (T)-sin(PI * k / (2 * N))};
     int rc;
     if ((rc = dev_upload(g, &tb->tw, tw))) return rc;
-    if ((rc = dev_upload(g, &tb->q, q))) return rc;
     if ((rc = dev_upload(g, &tb->pt, pt))) return rc;
     tb->h = h;
     return LSB_OK;
@@ -572,7 +570,7 @@ int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n
         else if (K == H) { slot = 0; comp = 1; }
         else { slot = N - K; comp = 1; }
         if (reversed) slot = brev_host(slot, h);
-        return 2 * slot + comp;
+        return 2 * swz(slot) + comp;
     };
     auto makhoul = [&](int p) -> int { return (p & 1) ? N - 1 - (p - 1) / 2 : p / 2; };
     for (int c = 0; c < Lc && !rc; ++c) {
@@ -587,8 +585,8 @@ int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n
                 const int p = (int)o1[j];
                 if (p < 1 || p >= N) { lsb::set_error("order1 entry %d outside [1, %d)", p, N); rc = LSB_ERR_INVALID; break; }
                 const int m = makhoul(p);
-                t_abs[j] = (uint16_t)m;
-                t_azg[j] = (uint16_t)(2 * brev_host(m >> 1, h) + (m & 1));
+                t_abs[j] = (uint16_t)(2 * swz(m >> 1) + (m & 1));
+                t_azg[j] = (uint16_t)(2 * swz(brev_host(m >> 1, h)) + (m & 1));
             }
             for (int i = 0; i < Mr && !rc; ++i) {
                 const int K = (int)o0[i];

@@ -44,13 +44,19 @@ template <bool INV, typename T2> __device__ __forceinline__ T2 mul_mi(T2 a)
 
 // Twiddle tables of one transform size (device pointers):
 //   tw[k] = exp(-2 pi i k / H), k < H          (FFT passes)
-//   q[k]  = exp(-2 pi i k / N), k <= H/2       (real-FFT split), N = 2H = w
-//   pt[k] = exp(-i pi k / (2N)), k <= H        (DCT phase)
+//   pt[k] = exp(-i pi k / (2N)), k <= H        (DCT phase), N = 2H = w; the real-FFT
+//           split factor exp(-2 pi i k / N) is pt[k]^4, pt[H-k] = e^{-i pi/4} conj(pt[k])
 template <typename T>
 struct FftTables {
-    const typename Cplx<T>::type *tw, *q, *pt;
+    const typename Cplx<T>::type *tw, *pt;
     int h;   // log2(H)
 };
+
+// Shared-memory slot of complex element i.  The XOR swizzle spreads the last FFT
+// passes (sub-transform sizes 32 and 4, strides 4 and 1) over all banks: without
+// it every 64-bit access of those passes is a 4-way conflict per half-warp.  The
+// host applies the same map when it builds the scatter/gather tables.
+__host__ __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 4) & 3) ^ (((i >> 5) & 3) << 2); }
 
 template <bool INV, typename T2> __device__ __forceinline__ T2 twiddle(const T2 *tw, int idx)
 {
@@ -89,19 +95,19 @@ __device__ __forceinline__ void fft_pass(typename Cplx<T>::type *buf, const type
         const int base = ((q >> logQ) << logS) + j;
         T2 v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = buf[base + m * stride];
+        for (int m = 0; m < R; ++m) v[m] = buf[swz(base + m * stride)];
         const T2 w1 = twiddle<INV>(tw, j * tw_step);
         if (LOGR == 1) {
             bfly(v[0], v[1], w1);
         } else if (LOGR == 2) {
-            const T2 w2 = twiddle<INV>(tw, 2 * j * tw_step);
+            const T2 w2 = cmul(w1, w1);                 // w_S^{2j}
             bfly(v[0], v[2], w1);
             bfly(v[1], v[3], mul_mi<INV>(w1));          // w1 * w_4^1
             bfly(v[0], v[1], w2);
             bfly(v[2], v[3], w2);
         } else {
-            const T2 w2 = twiddle<INV>(tw, 2 * j * tw_step);
-            const T2 w4 = twiddle<INV>(tw, 4 * j * tw_step);
+            const T2 w2 = cmul(w1, w1);                 // w_S^{2j}
+            const T2 w4 = cmul(w2, w2);                 // w_S^{4j}
             const T2 r8 = INV ? T2{kR, kR} : T2{kR, -kR};  // w_8^1
             const T2 w1b = cmul(w1, r8);
             bfly(v[0], v[4], w1);
@@ -119,7 +125,7 @@ __device__ __forceinline__ void fft_pass(typename Cplx<T>::type *buf, const type
             bfly(v[6], v[7], w4);
         }
 #pragma unroll
-        for (int m = 0; m < R; ++m) buf[base + m * stride] = v[m];
+        for (int m = 0; m < R; ++m) buf[swz(base + m * stride)] = v[m];
     }
 }
 
@@ -152,19 +158,24 @@ __device__ void dct2_post(typename Cplx<T>::type *buf, const FftTables<T> &tb, i
             buf[0] = T2{z.x + z.y, (z.x - z.y) * (T)0.70710678118654752440};
             continue;
         }
-        const int pa = bitrev(k, h), pb = bitrev(H - k, h);
+        const int pa = swz(bitrev(k, h)), pb = swz(bitrev(H - k, h));
         const T2 za = buf[pa], zb = buf[pb];
+        const T2 ptk = __ldg(tb.pt + k);
+        const T2 pt2 = cmul(ptk, ptk);
+        const T2 qk = cmul(pt2, pt2);                                  // q[k] = pt[k]^4
+        const T kR = (T)0.70710678118654752440;
+        const T2 ptm = cmul(T2{kR, -kR}, cconj(ptk));                  // pt[H-k] = e^{-i pi/4} conj(pt[k])
         // E = (za + conj(zb))/2, O = -i (za - conj(zb))/2
         const T2 E = {(T)0.5 * (za.x + zb.x), (T)0.5 * (za.y - zb.y)};
         const T2 D = {(T)0.5 * (za.x - zb.x), (T)0.5 * (za.y + zb.y)};
         const T2 O = {D.y, -D.x};
-        const T2 qO = cmul(__ldg(tb.q + k), O);
+        const T2 qO = cmul(qk, O);
         const T2 Vk = cadd(E, qO);                 // V[k]
         const T2 Vm = cconj(csub(E, qO));          // V[H-k]
-        const T2 ta = cmul(__ldg(tb.pt + k), Vk);
+        const T2 ta = cmul(ptk, Vk);
         buf[pa] = T2{ta.x, -ta.y};
         if (pb != pa) {
-            const T2 t2 = cmul(__ldg(tb.pt + (H - k)), Vm);
+            const T2 t2 = cmul(ptm, Vm);
             buf[pb] = T2{t2.x, -t2.y};
         }
     }
@@ -187,14 +198,20 @@ __device__ void dct3_pre(typename Cplx<T>::type *buf, const FftTables<T> &tb, in
             continue;
         }
         const int kb = H - k;
-        const T2 ca = buf[k], cb = buf[kb];
+        const int sa = swz(k), sb = swz(kb);
+        const T2 ca = buf[sa], cb = buf[sb];
+        const T2 ptk = __ldg(tb.pt + k);
+        const T2 pt2 = cmul(ptk, ptk);
+        const T2 qk = cmul(pt2, pt2);                                  // q[k] = pt[k]^4
+        const T kR = (T)0.70710678118654752440;
+        const T2 ptm = cmul(T2{kR, -kR}, cconj(ptk));                  // pt[H-k]
         // W[k] = conj(pt[k]) (c[k] - i c[N-k]) / 2
-        const T2 Wa = cmul(cconj(__ldg(tb.pt + k)), T2{(T)0.5 * ca.x, (T)-0.5 * ca.y});
-        const T2 Wb = cmul(cconj(__ldg(tb.pt + kb)), T2{(T)0.5 * cb.x, (T)-0.5 * cb.y});
+        const T2 Wa = cmul(cconj(ptk), T2{(T)0.5 * ca.x, (T)-0.5 * ca.y});
+        const T2 Wb = cmul(cconj(ptm), T2{(T)0.5 * cb.x, (T)-0.5 * cb.y});
         const T2 A = cadd(Wa, cconj(Wb));
-        const T2 B = cmul(csub(Wa, cconj(Wb)), cconj(__ldg(tb.q + k)));
-        buf[k] = T2{A.x - B.y, A.y + B.x};                      // A + iB
-        if (kb != k) buf[kb] = T2{A.x + B.y, -A.y + B.x};      // conj(A) + i conj(B)
+        const T2 B = cmul(csub(Wa, cconj(Wb)), cconj(qk));
+        buf[sa] = T2{A.x - B.y, A.y + B.x};                     // A + iB
+        if (kb != k) buf[sb] = T2{A.x + B.y, -A.y + B.x};      // conj(A) + i conj(B)
     }
     __syncthreads();
 }
