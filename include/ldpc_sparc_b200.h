@@ -198,6 +198,67 @@ int lsb_sparc_amp_dev_f64(lsb_sparc_design *g, const double *y, int64_t n_frames
                           const lsb_sparc_amp_params *p, const int32_t *idx0,
                           const lsb_sparc_amp_out *out, void *stream);
 
+/* ----------------------------- (4) SPARC, dense Gaussian design (sparc_sophie)
+ * Replaces, for batches of frames that share one design matrix A [n x ML]
+ * (sparc_new.py:1284-1294), the NumPy steps of sparc_amp / sparc_amp_single_it
+ * (sparc_new.py:885-912, 975-990) and the pure-Python section <-> bit glue around
+ * the BP decoder (sparc_new.py:1118-1138, 1162-1193, 1260-1279, 824-883).  The
+ * host side (ldpc_sparc_b200/sparc_new.py) chains these with lsb_ldpc_decode_dev_*
+ * into sparc_ldpc_decode / naively_integrated_decoder / integrated_decoder.
+ * All pointers are device pointers; per-frame scalars (tau_sqr, beta_sq,
+ * onsager_sum) are double[F]; calls are asynchronous on `stream`.
+ */
+typedef struct lsb_dense_design lsb_dense_design;
+
+int lsb_dense_design_create(const double *A /* host, row-major [n, ML] */, int64_t n, int64_t ML,
+                            int want_f32, int want_f64, lsb_dense_design **out);
+void lsb_dense_design_destroy(lsb_dense_design *g);
+
+/* out[F, n] = x[F, ML] A^T  (np.dot(A, beta), :903)  /  out[F, ML] = z[F, n] A  (np.dot(AT, z), :907) */
+int lsb_dense_ab_dev_f32(const lsb_dense_design *g, const float *x, float *out, int64_t F, void *stream);
+int lsb_dense_ab_dev_f64(const lsb_dense_design *g, const double *x, double *out, int64_t F, void *stream);
+int lsb_dense_az_dev_f32(const lsb_dense_design *g, const float *z, float *out, int64_t F, void *stream);
+int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out, int64_t F, void *stream);
+
+/* z <- y - ab + z*coef, tau_sqr <- |z|^2/n.  first != 0: z <- y.  mode 0: coef =
+ * (P - beta_sq/n)/tau_sqr (:904); mode 1: coef = onsager_sum/n (:492). */
+int lsb_amp_residual_dev_f32(const float *y, const float *ab, float *z, const double *beta_sq,
+                             const double *onsager_sum, double *tau_sqr, int64_t F, int n, double P,
+                             int mode, int first, void *stream);
+int lsb_amp_residual_dev_f64(const double *y, const double *ab, double *z, const double *beta_sq,
+                             const double *onsager_sum, double *tau_sqr, int64_t F, int n, double P,
+                             int mode, int first, void *stream);
+/* s = atz + beta_in (beta_in may be NULL = 0, and may alias beta_out);
+ * beta_out <- sqrt_nPl softmax_section(sqrt_nPl s / tau_sqr) (:1040-1066);
+ * beta_sq <- |beta_out|^2; s_out optional. */
+int lsb_amp_denoise_dev_f32(const float *beta_in, const float *atz, float *beta_out, float *s_out,
+                            const double *tau_sqr, double *beta_sq, int64_t F, int L, int M,
+                            double sqrt_nPl, void *stream);
+int lsb_amp_denoise_dev_f64(const double *beta_in, const double *atz, double *beta_out, double *s_out,
+                            const double *tau_sqr, double *beta_sq, int64_t F, int L, int M,
+                            double sqrt_nPl, void *stream);
+/* beta [n_sections, M] -> probs (P(bit = 0), optional) and llr (optional), each [n_sections, logM] (:1118-1138,1166-1169) */
+int lsb_section_to_bit_dev_f32(const float *beta, float *probs, float *llr, int64_t n_sections, int M,
+                               double sqrt_nPl, void *stream);
+int lsb_section_to_bit_dev_f64(const double *beta, double *probs, double *llr, int64_t n_sections, int M,
+                               double sqrt_nPl, void *stream);
+/* app [F, L, logM] -> probs = sigmoid(app) (optional), beta [F, L, M] (:1190, 1260-1279) and
+ * beta_sq[f] = |beta_f|^2 (optional) */
+int lsb_bit_to_section_dev_f32(const float *app, float *probs, float *beta, double *beta_sq, int64_t F,
+                               int L, int M, double sqrt_nPl, void *stream);
+int lsb_bit_to_section_dev_f64(const double *app, double *probs, double *beta, double *beta_sq, int64_t F,
+                               int L, int M, double sqrt_nPl, void *stream);
+/* bits[blk, k] = app[blk, k] < 0 for the K systematic positions of each N-bit block (:1184-1186) */
+int lsb_hard_info_bits_dev_f32(const float *app, uint8_t *bits, int64_t n_blocks, int N, int K, void *stream);
+int lsb_hard_info_bits_dev_f64(const double *app, uint8_t *bits, int64_t n_blocks, int N, int K, void *stream);
+/* out[f] = sum_i beta_i * main_term_i of differentiated_eta_calc (:824-841, 871-883) */
+int lsb_integrated_onsager_dev_f32(const float *beta, const float *vk, const float *vk0,
+                                   const float *alpha_weighted, const double *tau_sqr, double *out,
+                                   int64_t F, int L, int M, double sqrt_nPl, void *stream);
+int lsb_integrated_onsager_dev_f64(const double *beta, const double *vk, const double *vk0,
+                                   const double *alpha_weighted, const double *tau_sqr, double *out,
+                                   int64_t F, int L, int M, double sqrt_nPl, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,20 @@ SIGNATURES = {
     "lsb_sparc_az_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_sparc_amp_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
     "lsb_sparc_amp_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
+    # SPARC (dense Gaussian design) + section <-> bit glue
+    "lsb_dense_design_create": (ct.c_int, [c_f64p, ct.c_int64, ct.c_int64, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p)]),
+    "lsb_dense_design_destroy": (None, [ct.c_void_p]),
 }
+_VP = ct.c_void_p
+for _suf in ("f32", "f64"):
+    SIGNATURES["lsb_dense_ab_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, ct.c_int64, _VP])
+    SIGNATURES["lsb_dense_az_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, ct.c_int64, _VP])
+    SIGNATURES["lsb_amp_residual_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ct.c_int64, ct.c_int, ct.c_double, ct.c_int, ct.c_int, _VP])
+    SIGNATURES["lsb_amp_denoise_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, _VP])
+    SIGNATURES["lsb_section_to_bit_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, ct.c_int64, ct.c_int, ct.c_double, _VP])
+    SIGNATURES["lsb_bit_to_section_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, _VP, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, _VP])
+    SIGNATURES["lsb_hard_info_bits_dev_" + _suf] = (ct.c_int, [_VP, _VP, ct.c_int64, ct.c_int, ct.c_int, _VP])
+    SIGNATURES["lsb_integrated_onsager_dev_" + _suf] = (ct.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, _VP])
 
 
 def lib():

@@ -1,0 +1,488 @@
+// Dense Gaussian design SPARC (sparc_sophie/sparc_new.py): frame-batched A*beta and
+// A^T*z, the AMP residual / denoiser steps and the section <-> bit glue around the BP
+// decoder.  First (round 1) version of this row: FP32 / FP64 SIMT kernels, correct and
+// coalesced, not yet the tcgen05 path.
+//
+// Reference per AMP iteration (sparc_new.py:885-912, 975-990):
+//   z   = y - A beta + (z / tau^2)(P - |beta|^2 / n)        (integrated: + (z / n) sum d_eta, :492)
+//   s   = beta + A^T z ;  tau^2 = |z|^2 / n
+//   beta = sqrt(nP_l) softmax_section(sqrt(nP_l) s / tau^2)                   (:1040-1066)
+// Glue (sparc_new.py:1118-1138, 1162-1193, 1260-1279, 824-883): section posterior ->
+// P(bit = 0) -> LLR -> [BP] -> APP -> P(bit = 0) -> product-form section prior.
+#include "common.cuh"
+
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------ tiled GEMM
+// C[F, N] = X[F, K] * op(A):  TRANS_A = true : A is [N, K] row-major (C = X A^T, the A*beta product)
+//                             TRANS_A = false: A is [K, N] row-major (C = X A,   the A^T*z product)
+template <typename T, int BM, int BN, bool TRANS_A>
+__global__ void __launch_bounds__(kThreads)
+gemm_kernel(const T *__restrict__ X, const T *__restrict__ A, T *__restrict__ C, int F, int N, int K)
+{
+    constexpr int BK = 16, TM = 4, TN = BM * BN / (kThreads * TM);
+    __shared__ T Xs[BK][BM + 4];
+    __shared__ T As[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int f0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);   // thread tile: rows ty*TM.., cols tx*TN..
+    T acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = (T)0;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // X tile [BM x BK], k contiguous in memory
+        for (int e = tid; e < BM * BK; e += kThreads) {
+            const int m = e / BK, k = e % BK;
+            const int f = f0 + m, kk = k0 + k;
+            Xs[k][m] = (f < F && kk < K) ? X[(size_t)f * K + kk] : (T)0;
+        }
+        if (TRANS_A) {   // A[n, k]: k contiguous
+            for (int e = tid; e < BN * BK; e += kThreads) {
+                const int nn = e / BK, k = e % BK;
+                const int n = n0 + nn, kk = k0 + k;
+                As[k][nn] = (n < N && kk < K) ? A[(size_t)n * K + kk] : (T)0;
+            }
+        } else {         // A[k, n]: n contiguous
+            for (int e = tid; e < BN * BK; e += kThreads) {
+                const int k = e / BN, nn = e % BN;
+                const int n = n0 + nn, kk = k0 + k;
+                As[k][nn] = (n < N && kk < K) ? A[(size_t)kk * N + n] : (T)0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            T xr[TM], ar[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) xr[i] = Xs[k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) ar[j] = As[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] += xr[i] * ar[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int f = f0 + ty * TM + i;
+        if (f >= F) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n < N) C[(size_t)f * N + n] = acc[i][j];
+        }
+    }
+}
+
+// deterministic block sum (fixed tree), result valid in thread 0
+template <typename T>
+__device__ T block_sum(T v, T *red /* [kThreads/32] shared */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T tot = (T)0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kThreads / 32; ++w) tot += red[w];
+    __syncthreads();
+    return tot;
+}
+
+// z <- y - Ab + z * coef, tau_sqr <- |z|^2 / n.   One CTA per frame.
+//   mode 0: coef = (P - beta_sq / n) / tau_sqr_in      (sparc_new.py:904,981)
+//   mode 1: coef = onsager_sum / n                     (sparc_new.py:492)
+//   first != 0: z = y (t = 0 of sparc_amp, :898) -- Ab and coef ignored
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+residual_kernel(const T *__restrict__ y, const T *__restrict__ ab, T *__restrict__ z, const double *beta_sq,
+                const double *onsager_sum, double *tau_sqr, int n, double P, int mode, int first)
+{
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    double coef = 0.0;
+    if (!first) coef = mode == 0 ? (P - beta_sq[f] / n) / tau_sqr[f] : onsager_sum[f] / n;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const size_t p = f * n + i;
+        const T v = first ? y[p] : (T)((y[p] - ab[p]) + z[p] * (T)coef);
+        z[p] = v;
+        part += (double)v * (double)v;
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) tau_sqr[f] = tot / n;
+}
+
+// s = beta + atz ; beta <- sqrt_nPl * softmax_section(sqrt_nPl * s / tau_sqr) ; beta_sq = |beta|^2.
+// One CTA per frame, one warp per section (any power-of-two M).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+denoise_kernel(const T *beta_in, const T *__restrict__ atz, T *beta, T *__restrict__ s_out,
+               const double *tau_sqr, double *beta_sq, int L, int M, double sqrt_nPl)
+{
+    const bool add_beta = beta_in != nullptr;   // beta_in may alias beta (each entry is read before it is written)
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T scale = (T)(sqrt_nPl / tau_sqr[f]);
+    const T amp = (T)sqrt_nPl;
+    double part = 0.0;
+    const int spw = M >= 32 ? 1 : 32 / M;      // sections per warp pass
+    const int per_lane = M >= 32 ? M / 32 : 1;
+    for (int sec0 = warp * spw; sec0 < L; sec0 += (kThreads / 32) * spw) {
+        const int sec = M >= 32 ? sec0 : sec0 + lane / M;
+        const bool live = sec < L;
+        const size_t base = f * (size_t)L * M + (size_t)sec * M;
+        T mx = -INFINITY;
+        T sv[8];   // M <= 256
+        for (int k = 0; k < per_lane; ++k) {
+            const int j = M >= 32 ? lane + 32 * k : lane % M;
+            T v = (T)0;
+            if (live) {
+                v = atz[base + j];
+                if (add_beta) v += beta_in[base + j];
+                if (s_out) s_out[base + j] = v;
+            }
+            sv[k] = v;
+            mx = fmax(mx, v);
+        }
+        const int width = M >= 32 ? 32 : M;
+        for (int o = width >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        T sum = (T)0;
+        for (int k = 0; k < per_lane; ++k) {
+            sv[k] = exp((sv[k] - mx) * scale);
+            sum += sv[k];
+        }
+        for (int o = width >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (live) {
+            for (int k = 0; k < per_lane; ++k) {
+                const int j = M >= 32 ? lane + 32 * k : lane % M;
+                const T b = amp * (sv[k] / sum);
+                beta[base + j] = b;
+                part += (double)b * (double)b;
+            }
+        }
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) beta_sq[f] = tot;
+}
+
+// P(bit b of the section index = 0) = sum_{j: bit b of j == 0} beta_j / sqrt_nPl, summed in
+// increasing j as the reference (sparc_new.py:1118-1138; b = 0 is the MSB); LLR = log p -
+// log(1-p) with p clipped to [1e-15, 1-1e-15] (:1166-1169).  One thread per (frame, section, bit).
+template <typename T>
+__global__ void section_to_bit_kernel(const T *__restrict__ beta, T *__restrict__ probs, T *__restrict__ llr,
+                                      long long total, int M, int logM, double sqrt_nPl)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long sec = i / logM;
+    const int b = (int)(i % logM);
+    const int shift = logM - 1 - b;
+    const T *bs = beta + sec * M;
+    T p = (T)0;
+    for (int j = 0; j < M; ++j)
+        if (((j >> shift) & 1) == 0) p += bs[j] / (T)sqrt_nPl;
+    if (probs) probs[i] = p;
+    if (llr) {   // clip and logs in fp64: 1 - 1e-15 is not representable in fp32
+        const double pc = fmin(fmax((double)p, 1e-15), 1.0 - 1e-15);
+        llr[i] = (T)(log(pc) - log(1.0 - pc));
+    }
+}
+
+// p_b = e^app / (1 + e^app) (:1190); beta_i = sqrt_nPl * prod_b (p_b or 1 - p_b) (:1260-1279).
+// One CTA per frame; beta_sq[f] = |beta_f|^2 (optional) for the next Onsager term.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bit_to_section_kernel(const T *__restrict__ app, T *__restrict__ probs, T *__restrict__ beta, double *beta_sq,
+                      int L, int M, int logM, double sqrt_nPl)
+{
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    double part = 0.0;
+    for (int e = threadIdx.x; e < L * M; e += kThreads) {
+    const long long i = (long long)f * L * M + e;
+    const long long sec = i / M;
+    const int idx = (int)(i % M);
+    T prod = (T)1;
+    for (int j = 0; j < logM; ++j) {
+        const T a = app[sec * logM + j];
+        T p;
+        if (sizeof(T) == 8) {            // the reference's expression (overflows to NaN above 709, :1190)
+            const T e = exp(a);
+            p = e / ((T)1 + e);
+        } else {                         // fp32: same value, without the overflow at a > 88
+            p = (T)1 / ((T)1 + exp(-a));
+        }
+        if (idx == 0 && probs) probs[sec * logM + j] = p;
+        prod = ((idx >> (logM - 1 - j)) & 1) ? prod * ((T)1 - p) : prod * p;
+    }
+    const T bv = prod * (T)sqrt_nPl;
+    beta[i] = bv;
+    part += (double)bv * (double)bv;
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0 && beta_sq) beta_sq[f] = tot;
+}
+
+// hard decisions of the K systematic bits of every LDPC block: bits[blk, k] = app[blk, k] < 0 (:1184-1186)
+template <typename T>
+__global__ void hard_bits_kernel(const T *__restrict__ app, uint8_t *__restrict__ bits, long long n_blocks, int N, int K)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks * K) return;
+    bits[i] = app[(i / K) * N + (i % K)] < (T)0;
+}
+
+// sum over the frame of beta_i * main_term_i (sparc_new.py:824-841,871-883), reference
+// operation order inside a section.  One CTA per frame, one thread per (section, i).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+onsager_kernel(const T *__restrict__ beta, const T *__restrict__ vk, const T *__restrict__ vk0,
+               const T *__restrict__ alpha_w /* weighted alpha = sqrt_nPl * alpha */, const double *tau_sqr,
+               double *out, int L, int M, int logM, double sqrt_nPl)
+{
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    const T c = (T)(sqrt_nPl / tau_sqr[f]);
+    const T inv_amp = (T)(1.0 / sqrt_nPl);
+    double part = 0.0;
+    for (int e = threadIdx.x; e < L * M; e += kThreads) {
+        const int l = e / M, i = e % M;
+        const T *a = alpha_w + f * (size_t)L * M + (size_t)l * M;
+        const T ai = a[i] / (T)sqrt_nPl;
+        T main_term = (T)0;
+        for (int k = 0; k < logM; ++k) {
+            const int shift = logM - 1 - k;
+            T sum_term = (T)0;
+            for (int q = 0; q < M; ++q) {
+                if ((q >> shift) & 1) continue;          // q in S_k: bit k of q is 0
+                const T aq = a[q] / (T)sqrt_nPl;
+                sum_term += (q == i) ? aq * c * ((T)1 - aq) : aq * c * (-ai);
+            }
+            const size_t bi = f * (size_t)L * logM + (size_t)l * logM + k;
+            const T v0 = fmin(fmax(vk0[bi], (T)1e-10), (T)1 - (T)1e-10);
+            const T sub = ((T)1 / (v0 * ((T)1 - v0))) * sum_term;
+            const T v = vk[bi];
+            if ((i >> shift) & 1) main_term -= v * sub;
+            else main_term += ((T)1 - v) * sub;
+        }
+        part += (double)(beta[f * (size_t)L * M + e] * main_term);
+        (void)inv_amp;
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) out[f] = tot;
+}
+
+}  // namespace
+
+struct lsb_dense_design {
+    int device = 0;
+    int64_t n = 0, ML = 0;
+    float *d_A32 = nullptr;
+    double *d_A64 = nullptr;
+};
+
+namespace {
+
+int check_device(const lsb_dense_design *g)
+{
+    int dev = -1;
+    LSB_CUDA(cudaGetDevice(&dev));
+    LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);
+    return LSB_OK;
+}
+
+template <typename T> const T *mat(const lsb_dense_design *g);
+template <> const float *mat<float>(const lsb_dense_design *g) { return g->d_A32; }
+template <> const double *mat<double>(const lsb_dense_design *g) { return g->d_A64; }
+
+template <typename T>
+int run_gemm(const lsb_dense_design *g, bool transpose, const T *x, T *out, int64_t F, cudaStream_t st)
+{
+    LSB_REQUIRE(g && x && out, "null pointer");
+    LSB_REQUIRE(mat<T>(g), "the design holds no %s copy of A", sizeof(T) == 4 ? "fp32" : "fp64");
+    LSB_REQUIRE(F >= 0, "negative frame count");
+    if (F == 0) return LSB_OK;
+    int rc = check_device(g);
+    if (rc) return rc;
+    const int n = (int)g->n, ML = (int)g->ML;
+    if (!transpose) {   // out[F, n] = x[F, ML] A^T
+        if (F > 16) {
+            dim3 grid((n + 63) / 64, (unsigned)((F + 63) / 64));
+            gemm_kernel<T, 64, 64, true><<<grid, kThreads, 0, st>>>(x, mat<T>(g), out, (int)F, n, ML);
+        } else {
+            dim3 grid((n + 255) / 256, (unsigned)((F + 15) / 16));
+            gemm_kernel<T, 16, 256, true><<<grid, kThreads, 0, st>>>(x, mat<T>(g), out, (int)F, n, ML);
+        }
+    } else {            // out[F, ML] = x[F, n] A
+        if (F > 16) {
+            dim3 grid((ML + 63) / 64, (unsigned)((F + 63) / 64));
+            gemm_kernel<T, 64, 64, false><<<grid, kThreads, 0, st>>>(x, mat<T>(g), out, (int)F, ML, n);
+        } else {
+            dim3 grid((ML + 255) / 256, (unsigned)((F + 15) / 16));
+            gemm_kernel<T, 16, 256, false><<<grid, kThreads, 0, st>>>(x, mat<T>(g), out, (int)F, ML, n);
+        }
+    }
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+inline unsigned blocks_for(long long total) { return (unsigned)((total + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+extern "C" {
+
+int lsb_dense_design_create(const double *A, int64_t n, int64_t ML, int want_f32, int want_f64,
+                            lsb_dense_design **out)
+{
+    LSB_REQUIRE(A && out, "null pointer");
+    LSB_REQUIRE(n > 0 && ML > 0 && n < (1 << 30) && ML < (1 << 30), "bad design size");
+    LSB_REQUIRE(want_f32 || want_f64, "ask for at least one precision");
+    lsb_dense_design *g = new (std::nothrow) lsb_dense_design();
+    if (!g) return LSB_ERR_NOMEM;
+    g->n = n;
+    g->ML = ML;
+    if (cudaGetDevice(&g->device) != cudaSuccess) {
+        lsb::set_error("no CUDA device");
+        delete g;
+        return LSB_ERR_NO_DEVICE;
+    }
+    const size_t count = (size_t)n * (size_t)ML;
+    cudaError_t e = cudaSuccess;
+    if (want_f64) {
+        e = cudaMalloc((void **)&g->d_A64, count * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(g->d_A64, A, count * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && want_f32) {
+        std::vector<float> tmp;
+        try { tmp.resize(count); } catch (...) { e = cudaErrorMemoryAllocation; }
+        if (e == cudaSuccess) {
+            for (size_t i = 0; i < count; ++i) tmp[i] = (float)A[i];
+            e = cudaMalloc((void **)&g->d_A32, count * sizeof(float));
+            if (e == cudaSuccess) e = cudaMemcpy(g->d_A32, tmp.data(), count * sizeof(float), cudaMemcpyHostToDevice);
+        }
+    }
+    if (e != cudaSuccess) {
+        lsb::set_error("uploading the design matrix: %s", cudaGetErrorString(e));
+        lsb_dense_design_destroy(g);
+        return LSB_ERR_CUDA;
+    }
+    *out = g;
+    return LSB_OK;
+}
+
+void lsb_dense_design_destroy(lsb_dense_design *g)
+{
+    if (!g) return;
+    cudaFree(g->d_A32);
+    cudaFree(g->d_A64);
+    delete g;
+}
+
+int lsb_dense_ab_dev_f32(const lsb_dense_design *g, const float *x, float *out, int64_t F, void *stream)
+{ return run_gemm<float>(g, false, x, out, F, (cudaStream_t)stream); }
+int lsb_dense_ab_dev_f64(const lsb_dense_design *g, const double *x, double *out, int64_t F, void *stream)
+{ return run_gemm<double>(g, false, x, out, F, (cudaStream_t)stream); }
+int lsb_dense_az_dev_f32(const lsb_dense_design *g, const float *z, float *out, int64_t F, void *stream)
+{ return run_gemm<float>(g, true, z, out, F, (cudaStream_t)stream); }
+int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out, int64_t F, void *stream)
+{ return run_gemm<double>(g, true, z, out, F, (cudaStream_t)stream); }
+
+#define LSB_DENSE_ELEMWISE(SUF, T)                                                                              \
+    int lsb_amp_residual_dev_##SUF(const T *y, const T *ab, T *z, const double *beta_sq,                         \
+                                   const double *onsager_sum, double *tau_sqr, int64_t F, int n, double P,       \
+                                   int mode, int first, void *stream)                                            \
+    {                                                                                                            \
+        LSB_REQUIRE(y && z && tau_sqr && (first || ab), "null pointer");                                         \
+        LSB_REQUIRE(first || (mode == 0 ? beta_sq != nullptr : onsager_sum != nullptr), "missing coefficient");  \
+        if (F <= 0) return LSB_OK;                                                                               \
+        residual_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(y, ab, z, beta_sq, onsager_sum,   \
+                                                                               tau_sqr, n, P, mode, first);     \
+        lsb::count_launch();                                                                                     \
+        LSB_CUDA(cudaGetLastError());                                                                            \
+        return LSB_OK;                                                                                           \
+    }                                                                                                            \
+    int lsb_amp_denoise_dev_##SUF(const T *beta_in, const T *atz, T *beta_out, T *s_out,                         \
+                                  const double *tau_sqr, double *beta_sq, int64_t F, int L, int M,               \
+                                  double sqrt_nPl, void *stream)                                                 \
+    {                                                                                                            \
+        LSB_REQUIRE(beta_out && atz && tau_sqr && beta_sq, "null pointer");                                      \
+        LSB_REQUIRE(M >= 2 && M <= 256 && (M & (M - 1)) == 0, "M must be a power of two in [2, 256]");            \
+        if (F <= 0) return LSB_OK;                                                                               \
+        denoise_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out,     \
+                                                                              tau_sqr, beta_sq, L, M, sqrt_nPl); \
+        lsb::count_launch();                                                                                     \
+        LSB_CUDA(cudaGetLastError());                                                                            \
+        return LSB_OK;                                                                                           \
+    }                                                                                                            \
+    int lsb_section_to_bit_dev_##SUF(const T *beta, T *probs, T *llr, int64_t n_sections, int M,                 \
+                                     double sqrt_nPl, void *stream)                                              \
+    {                                                                                                            \
+        LSB_REQUIRE(beta && (probs || llr), "null pointer");                                                     \
+        int logM = 0;                                                                                            \
+        while ((1 << logM) < M) ++logM;                                                                          \
+        const long long total = (long long)n_sections * logM;                                                    \
+        if (total <= 0) return LSB_OK;                                                                           \
+        section_to_bit_kernel<T><<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>(beta, probs, llr,     \
+                                                                                          total, M, logM,       \
+                                                                                          sqrt_nPl);            \
+        lsb::count_launch();                                                                                     \
+        LSB_CUDA(cudaGetLastError());                                                                            \
+        return LSB_OK;                                                                                           \
+    }                                                                                                            \
+    int lsb_bit_to_section_dev_##SUF(const T *app, T *probs, T *beta, double *beta_sq, int64_t F, int L, int M,  \
+                                     double sqrt_nPl, void *stream)                                              \
+    {                                                                                                            \
+        LSB_REQUIRE(app && beta, "null pointer");                                                                \
+        int logM = 0;                                                                                            \
+        while ((1 << logM) < M) ++logM;                                                                          \
+        if (F <= 0) return LSB_OK;                                                                               \
+        bit_to_section_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(app, probs, beta, beta_sq,  \
+                                                                                    L, M, logM, sqrt_nPl);      \
+        lsb::count_launch();                                                                                     \
+        LSB_CUDA(cudaGetLastError());                                                                            \
+        return LSB_OK;                                                                                           \
+    }                                                                                                            \
+    int lsb_hard_info_bits_dev_##SUF(const T *app, uint8_t *bits, int64_t n_blocks, int N, int K, void *stream)  \
+    {                                                                                                            \
+        LSB_REQUIRE(app && bits, "null pointer");                                                                \
+        if (n_blocks <= 0) return LSB_OK;                                                                        \
+        hard_bits_kernel<T><<<blocks_for((long long)n_blocks * K), kThreads, 0, (cudaStream_t)stream>>>(         \
+            app, bits, (long long)n_blocks, N, K);                                                               \
+        lsb::count_launch();                                                                                     \
+        LSB_CUDA(cudaGetLastError());                                                                            \
+        return LSB_OK;                                                                                           \
+    }                                                                                                            \
+    int lsb_integrated_onsager_dev_##SUF(const T *beta, const T *vk, const T *vk0, const T *alpha_weighted,      \
+                                         const double *tau_sqr, double *out, int64_t F, int L, int M,            \
+                                         double sqrt_nPl, void *stream)                                          \
+    {                                                                                                            \
+        LSB_REQUIRE(beta && vk && vk0 && alpha_weighted && tau_sqr && out, "null pointer");                      \
+        int logM = 0;                                                                                            \
+        while ((1 << logM) < M) ++logM;                                                                          \
+        if (F <= 0) return LSB_OK;                                                                               \
+        onsager_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta, vk, vk0, alpha_weighted,     \
+                                                                              tau_sqr, out, L, M, logM,         \
+                                                                              sqrt_nPl);                        \
+        lsb::count_launch();                                                                                     \
+        LSB_CUDA(cudaGetLastError());                                                                            \
+        return LSB_OK;                                                                                           \
+    }
+
+LSB_DENSE_ELEMWISE(f32, float)
+LSB_DENSE_ELEMWISE(f64, double)
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""GPU parity tests of the dense-design LDPC-SPARC path (sparc_sophie): AMP, the
+section<->bit glue and the three AMP+BP decoders against the reference's goldens and
+the numpy oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sophie_oracle as sph
+from conftest import GOLDEN
+from ldpc_sparc_b200 import ldpc, sparc_new
+from test_oracle_sophie import setup_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(os.path.join(GOLDEN, "sophie_reference.npz"))
+    return g, json.loads(str(g["meta_json"]))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def test_dense_amp_matches_golden(gold):
+    g, meta = gold
+    for name, m in meta.items():
+        pre, c, sp, dp, y, A = setup_case(g, m, name, 0)
+        beta, s, tau = sparc_new.sparc_amp(y, sp, dp, A, precision="fp64", return_trace=True)
+        assert rel(tau, g[pre + "amp_tau_sqr"]) < 1e-10
+        assert rel(beta, g[pre + "amp_beta"]) < 1e-8 and rel(s, g[pre + "amp_s"]) < 1e-10
+        beta32, s32, tau32 = sparc_new.sparc_amp(y, sp, dp, A, precision="fp32", return_trace=True)
+        assert np.max(np.abs(tau32 - g[pre + "amp_tau_sqr"]) / g[pre + "amp_tau_sqr"]) < 1e-4      # north_star tolerance
+        assert rel(beta32, g[pre + "amp_beta"]) < 1e-4
+        assert np.array_equal(beta32.reshape(-1, sp["M"]).argmax(1), g[pre + "amp_beta"].reshape(-1, sp["M"]).argmax(1))
+
+
+def test_glue_kernels_vs_oracle():
+    rng = np.random.RandomState(0)
+    for M in (2, 4, 8, 64):
+        L, sq = 40, 1.7
+        logM = int(np.log2(M))
+        beta = rng.dirichlet(np.ones(M) * 0.3, size=L).ravel() * sq
+        p_ref = sph.beta_estimate_to_bp_probs(beta, L, M, sq)
+        p = sparc_new.beta_estimate_to_bp_probs(beta, L, M, sq)
+        assert np.max(np.abs(p - p_ref)) < 1e-14
+        probs = rng.uniform(0.01, 0.99, L * logM)
+        b_ref = sph.bp_output_to_beta_estimate(probs, L, M, sq)
+        b = sparc_new.bp_output_to_beta_estimate(probs, L, M, sq)
+        assert np.max(np.abs(b - b_ref)) < 1e-13 * sq
+        s = rng.randn(L * M)
+        e_ref = sph.mmse_estimator(s, 0.37, 50, sq * sq / 50, M)
+        e = sparc_new.msg_vector_mmse_estimator(s, 0.37, 50, sq * sq / 50, M)
+        assert np.max(np.abs(e - e_ref)) < 1e-13
+        e32 = sparc_new.msg_vector_mmse_estimator(s, 0.37, 50, sq * sq / 50, M, precision="fp32")
+        assert np.max(np.abs(e32 - e_ref)) < 1e-5
+
+
+def test_ldpc_bp_wrapper_vs_oracle():
+    c = ldpc.code("802.16", "1/2", 27)
+    rng = np.random.RandomState(2)
+    x = np.concatenate([c.encode(rng.randint(0, 2, c.K)) for _ in range(2)])
+    probs = np.clip(np.where(x == 0, 0.8, 0.2) + 0.25 * rng.randn(x.size), 0.0, 1.0)
+    p_ref, _ = sph.ldpc_bp(probs, sph.Code(c), 6, False)
+    p, _ = sparc_new.ldpc_bp(probs, c, 6, False)
+    assert np.allclose(p, p_ref, rtol=1e-9, atol=1e-12)
+    _, b_ref = sph.ldpc_bp(probs, sph.Code(c), 200, True)
+    _, b = sparc_new.ldpc_bp(probs, c, 200, True)
+    assert np.array_equal(b, b_ref) and b.shape == (2 * c.K,)
+
+
+@pytest.mark.parametrize("name", ["z27_m2", "z27_m4", "n11_m8", "z54_m2_hi"])
+def test_decoders_fp64_match_reference_golden(gold, name):
+    g, meta = gold
+    m = meta[name]
+    for si in range(len(m["seeds"])):
+        pre, c, sp, dp, y, A = setup_case(g, m, name, si)
+        lp = dict(standard=m["standard"], rate=m["rate"], z=m["z"])
+        lengths = dict(k_ldpc=c.K * m["mults"], mults=m["mults"], L_unprotected=0)
+        bits = sparc_new.sparc_ldpc_decode(y, sp, lp, dp, True, lengths, A, precision="fp64")
+        assert np.array_equal(bits, g[pre + "bits_separate"])
+        bits, tau = sparc_new.naively_integrated_decoder(y, sp, lp, dp, A, precision="fp64", return_trace=True)
+        assert rel(tau, g[pre + "naive_tau_sqr"]) < 1e-8
+        assert np.array_equal(bits, g[pre + "bits_naive"])
+        bits, tau, ons = sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="fp64", return_trace=True)
+        assert rel(tau, g[pre + "int_tau_sqr"]) < 1e-8
+        assert rel(ons, g[pre + "int_onsager_sum"]) < 1e-8
+        assert np.array_equal(bits, g[pre + "bits_integrated"])
+
+
+def test_decoders_fp32_converging_case(gold):
+    """fp32 mode on the operating point where the decoders converge (BER 0 in the
+    reference): identical bits, tau^2 within 1e-4."""
+    g, meta = gold
+    m = meta["z54_m2_hi"]
+    for si in range(2):
+        pre, c, sp, dp, y, A = setup_case(g, m, "z54_m2_hi", si)
+        lp = dict(standard=m["standard"], rate=m["rate"], z=m["z"])
+        lengths = dict(k_ldpc=c.K * m["mults"], mults=m["mults"], L_unprotected=0)
+        assert np.array_equal(sparc_new.sparc_ldpc_decode(y, sp, lp, dp, True, lengths, A, precision="fp32"),
+                              g[pre + "bits_separate"])
+        bits, tau = sparc_new.naively_integrated_decoder(y, sp, lp, dp, A, precision="fp32", return_trace=True)
+        assert np.array_equal(bits, g[pre + "bits_naive"])
+        assert np.max(np.abs(tau - g[pre + "naive_tau_sqr"]) / g[pre + "naive_tau_sqr"]) < 1e-4
+        bits, tau, ons = sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="fp32", return_trace=True)
+        assert np.array_equal(bits, g[pre + "bits_integrated"])
+        assert np.max(np.abs(tau - g[pre + "int_tau_sqr"]) / g[pre + "int_tau_sqr"]) < 1e-4
+
+
+def test_encode_and_batched_decode(gold):
+    """sparc_ldpc_encode reproduces the reference's codeword; a batch of frames sharing A
+    decodes to the same bits as frame-by-frame calls."""
+    g, meta = gold
+    m = meta["z54_m2_hi"]
+    pre, c, sp, dp, y, A = setup_case(g, m, "z54_m2_hi", 0)
+    lp = dict(standard=m["standard"], rate=m["rate"], z=m["z"])
+    lengths = dict(k_ldpc=c.K * m["mults"], mults=m["mults"], L_unprotected=0)
+    ub, tb, beta0, x, A2 = sparc_new.sparc_ldpc_encode(sp, lp, lengths, True, m["seeds"][0])
+    assert np.array_equal(ub, g[pre + "user_bits"]) and np.array_equal(tb, g[pre + "total_bits"].astype(bool))
+    assert rel(x, g[pre + "x"]) < 1e-12 and np.array_equal(A2, A)
+    rng = np.random.RandomState(1)
+    ys = np.stack([g[pre + "x"] + np.sqrt(sp["P"] / 5.0) * rng.randn(len(y)) for _ in range(20)])
+    for dec in (lambda yy, pr: sparc_new.sparc_ldpc_decode(yy, sp, lp, dp, True, lengths, A, precision=pr),
+                lambda yy, pr: sparc_new.naively_integrated_decoder(yy, sp, lp, dp, A, precision=pr),
+                lambda yy, pr: sparc_new.integrated_decoder(yy, sp, lp, dp, A, precision=pr)):
+        batch = dec(ys, "fp64")
+        assert batch.shape == (20, c.K * m["mults"])
+        for f in (0, 7, 19):
+            assert np.array_equal(batch[f], dec(ys[f], "fp64"))
+        assert (batch != g[pre + "user_bits"]).mean() < 0.05
+        assert (dec(ys, "fp32") != batch).mean() < 0.01
