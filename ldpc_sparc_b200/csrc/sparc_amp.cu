@@ -427,9 +427,17 @@ int make_tables(lsb_sparc_design *g, FftTables<T> *tb, int h)
     std::vector<T2> tw(H), pt(H + 1);
     for (int k = 0; k < H; ++k) tw[k] = T2{(T)cos(2 * PI * k / H), (T)-sin(2 * PI * k / H)};
     for (int k = 0; k <= H; ++k) pt[k] = T2{(T)cos(PI * k / (2 * N)), (T)-sin(PI * k / (2 * N))};
+    std::vector<T2> ptr(H / 2 + 1);
+    for (int t = 0; t < H / 2; ++t) {
+        int k = 0;
+        for (int i = 0; i < h - 1; ++i) k |= ((t >> i) & 1) << (h - 2 - i);   // brev over h-1 bits
+        ptr[t] = pt[k];
+    }
+    ptr[H / 2] = pt[H / 2];
     int rc;
     if ((rc = dev_upload(g, &tb->tw, tw))) return rc;
     if ((rc = dev_upload(g, &tb->pt, pt))) return rc;
+    if ((rc = dev_upload(g, &tb->ptr, ptr))) return rc;
     tb->h = h;
     return LSB_OK;
 }

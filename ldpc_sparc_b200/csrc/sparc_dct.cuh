@@ -49,6 +49,7 @@ template <bool INV, typename T2> __device__ __forceinline__ T2 mul_mi(T2 a)
 template <typename T>
 struct FftTables {
     const typename Cplx<T>::type *tw, *pt;
+    const typename Cplx<T>::type *ptr;   // ptr[t] = pt[brev_{h-1}(t)], t < H/2; ptr[H/2] = pt[H/2]
     int h;   // log2(H)
 };
 
@@ -152,7 +153,13 @@ __device__ void dct2_post(typename Cplx<T>::type *buf, const FftTables<T> &tb, i
 {
     typedef typename Cplx<T>::type T2;
     const int h = tb.h, H = 1 << h;
-    for (int k = tid; k <= (H >> 1); k += nthreads) {
+    // Pair index k is visited in bit-reversed order (k = brev_{h-1}(t)): the FFT left
+    // Z[k] at slot brev_h(k) = 2t and Z[H-k] at a slot that runs backwards with t, so
+    // consecutive lanes touch consecutive slots (in natural k order every lane of a
+    // warp hits the same bank).  ptr is pt in that same order, so it loads coalesced.
+    const int Hh = H >> 1;
+    for (int t = tid; t <= Hh; t += nthreads) {
+        const int k = (t == Hh) ? Hh : (h > 1 ? bitrev(t, h - 1) : 0);
         if (k == 0) {
             const T2 z = buf[0];
             buf[0] = T2{z.x + z.y, (z.x - z.y) * (T)0.70710678118654752440};
@@ -160,7 +167,7 @@ __device__ void dct2_post(typename Cplx<T>::type *buf, const FftTables<T> &tb, i
         }
         const int pa = swz(bitrev(k, h)), pb = swz(bitrev(H - k, h));
         const T2 za = buf[pa], zb = buf[pb];
-        const T2 ptk = __ldg(tb.pt + k);
+        const T2 ptk = __ldg(tb.ptr + t);
         const T2 pt2 = cmul(ptk, ptk);
         const T2 qk = cmul(pt2, pt2);                                  // q[k] = pt[k]^4
         const T kR = (T)0.70710678118654752440;
