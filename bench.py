@@ -43,7 +43,7 @@ METRIC = "decoded info bits/s (LDPC 802.11n r1/2 n=1944 sum-product BP, <=50 its
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=N_FRAMES, help="frames per GPU per step")
@@ -168,7 +168,7 @@ class ClockSampler:
                 self.rows.append([t.strip() for t in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.thread = threading.Thread(target=self._loop, daemon=True)

@@ -259,6 +259,20 @@ int lsb_integrated_onsager_dev_f64(const double *beta, const double *vk, const d
                                    const double *alpha_weighted, const double *tau_sqr, double *out,
                                    int64_t F, int L, int M, double sqrt_nPl, void *stream);
 
+/* Tensor-core variant of the two dense products (tcgen05 + TMEM + TMA, csrc/dense_tc.cu):
+ * operands split into two bf16 terms, three MMAs per tile into one fp32 accumulator, so
+ * results carry ~16 mantissa bits (about 2e-5 relative), enough for the 1e-4 bound on
+ * tau^2 / beta.  fp32 in / fp32 out; n and ML must be multiples of 8.  The handle holds
+ * bf16 hi/lo copies of A and of A^T (8 bytes per entry in total). */
+typedef struct lsb_tc_design lsb_tc_design;
+int lsb_tc_design_create(const double *A /* host, row-major [n, ML] */, int64_t n, int64_t ML,
+                         lsb_tc_design **out);
+void lsb_tc_design_destroy(lsb_tc_design *g);
+int lsb_tc_ab_dev_f32(lsb_tc_design *g, const float *x /* [F, ML] */, float *out /* [F, n] */, int64_t F,
+                      void *stream);
+int lsb_tc_az_dev_f32(lsb_tc_design *g, const float *z /* [F, n] */, float *out /* [F, ML] */, int64_t F,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -440,7 +440,11 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     tau_tr = torch.zeros((F, t_max, Lc), dtype=torch.float64, device=dev) if return_trace else None
     psi_tr = torch.zeros((F, t_max, Lc), dtype=torch.float64, device=dev) if return_trace else None
 
-    params = _lib.AmpParams(float(awgn_var), float(rtol), 2 * np.finfo(float).resolution, int(t_max), int(phi_est_method))
+    # atol of the early-stop test: the reference hard-codes 2*finfo(float).resolution = 2e-15
+    # (sparc.py:916).  decode_params['atol'] (an extension, not validated by
+    # check_decode_params) lets an fp32 run stop at its own noise floor, e.g. 1e-7.
+    atol = float(decode_params.get('atol', 2 * np.finfo(float).resolution))
+    params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method))
     ptr = lambda t: t.data_ptr() if t is not None else None
     out = _lib.AmpOut(ptr(idx), ptr(t_final), ptr(psi), ptr(nmse), ptr(beta_soft), ptr(s_last), ptr(tau_tr), ptr(psi_tr))
     fn = _lib.lib().lsb_sparc_amp_dev_f64 if precision == "fp64" else _lib.lib().lsb_sparc_amp_dev_f32

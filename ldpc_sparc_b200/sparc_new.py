@@ -9,8 +9,10 @@ decoders (sparc_new.py:15-82, 257-282, 472-502, 709-735, 885-912, 975-990,
 All decoding arithmetic runs on the GPU (csrc/sparc_dense.cu + the BP kernels).
 ``y`` may be ``[n]`` (the reference's call) or ``[F, n]`` (F frames sharing the
 design ``A``); ``A`` is a NumPy array -- uploaded once and cached -- exactly what
-``sparc_ldpc_encode`` returns.  ``precision`` is 'fp64' (parity mode, default for
-single frames like the reference's float64) or 'fp32' (throughput mode).
+``sparc_ldpc_encode`` returns.  ``precision`` is 'fp64' (parity mode, default, the
+reference's float64), 'fp32' (SIMT fp32) or 'tc' (throughput mode: the two products
+A beta and A^T z run on the tensor cores -- tcgen05, split-bf16 operands with fp32
+accumulation, about 2e-5 relative -- and everything else in fp32).
 """
 import ctypes as ct
 
@@ -117,20 +119,26 @@ class _Engine:
         _lib.require_device()
         self.torch = torch
         self.precision = precision
+        self.tc = precision == "tc"          # tensor-core products (tcgen05, split bf16), fp32 everywhere else
+        self.bp_precision = "fp64" if precision == "fp64" else "fp32"
         self.dt = torch.float64 if precision == "fp64" else torch.float32
         self.suf = "f64" if precision == "fp64" else "f32"
         A = np.ascontiguousarray(A, dtype=np.float64)
         self.n, self.ML = A.shape
         h = ct.c_void_p()
-        _lib.check(_lib.lib().lsb_dense_design_create(A.ctypes.data_as(_lib.c_f64p), self.n, self.ML,
-                                                      int(precision == "fp32"), int(precision == "fp64"), ct.byref(h)),
-                   "lsb_dense_design_create")
+        if self.tc:
+            _lib.check(_lib.lib().lsb_tc_design_create(A.ctypes.data_as(_lib.c_f64p), self.n, self.ML, ct.byref(h)),
+                       "lsb_tc_design_create")
+        else:
+            _lib.check(_lib.lib().lsb_dense_design_create(A.ctypes.data_as(_lib.c_f64p), self.n, self.ML,
+                                                          int(precision == "fp32"), int(precision == "fp64"),
+                                                          ct.byref(h)), "lsb_dense_design_create")
         self.h = h
         self.dev = torch.device("cuda", torch.cuda.current_device())
 
     def __del__(self):
         try:
-            _lib.lib().lsb_dense_design_destroy(self.h)
+            (_lib.lib().lsb_tc_design_destroy if self.tc else _lib.lib().lsb_dense_design_destroy)(self.h)
         except Exception:
             pass
 
@@ -152,12 +160,14 @@ class _Engine:
 
     def ab(self, beta):
         out = self.empty(beta.shape[0], self.n)
-        _lib.check(self.fn("dense_ab")(self.h, beta.data_ptr(), out.data_ptr(), beta.shape[0], self.stream()), "dense_ab")
+        fn = _lib.lib().lsb_tc_ab_dev_f32 if self.tc else self.fn("dense_ab")
+        _lib.check(fn(self.h, beta.data_ptr(), out.data_ptr(), beta.shape[0], self.stream()), "dense_ab")
         return out
 
     def az(self, z):
         out = self.empty(z.shape[0], self.ML)
-        _lib.check(self.fn("dense_az")(self.h, z.data_ptr(), out.data_ptr(), z.shape[0], self.stream()), "dense_az")
+        fn = _lib.lib().lsb_tc_az_dev_f32 if self.tc else self.fn("dense_az")
+        _lib.check(fn(self.h, z.data_ptr(), out.data_ptr(), z.shape[0], self.stream()), "dense_az")
         return out
 
     def residual(self, y, ab, z, beta_sq, onsager, tau, P, mode, first):
@@ -193,7 +203,7 @@ class _Engine:
     def bp(self, llr, c, num_its):
         """LLRs [F, blocks*N] -> APP, fresh messages per block (sparc_new.py:1172-1179)."""
         F = llr.shape[0]
-        app, _ = c.decode(llr.reshape(-1, c.N), num_its, precision=self.precision)
+        app, _ = c.decode(llr.reshape(-1, c.N), num_its, precision=self.bp_precision)
         return app.reshape(F, -1)
 
     def hard_bits(self, app, c):
@@ -214,8 +224,8 @@ class _Engine:
 
 def _engine(A, precision):
     precision = precision or DEFAULT_PRECISION
-    if precision not in ("fp32", "fp64"):
-        raise ValueError("precision must be 'fp32' or 'fp64'")
+    if precision not in ("fp32", "fp64", "tc"):
+        raise ValueError("precision must be 'fp32', 'fp64' or 'tc'")
     if isinstance(A, _Engine):
         return A
     key = (id(A), A.shape, precision)

@@ -133,3 +133,40 @@ def test_encode_and_batched_decode(gold):
             assert np.array_equal(batch[f], dec(ys[f], "fp64"))
         assert (batch != g[pre + "user_bits"]).mean() < 0.05
         assert (dec(ys, "fp32") != batch).mean() < 0.01
+
+
+def test_tensor_core_products_vs_fp64():
+    """tcgen05 split-bf16 products against float64 numpy: ~16 mantissa bits."""
+    import ctypes as ct
+    import torch
+    from ldpc_sparc_b200 import _lib
+    rng = np.random.RandomState(3)
+    for n, ML, F in ((256, 512, 128), (384, 1160, 200), (1000, 2408, 37)):
+        A = rng.randn(n, ML) / np.sqrt(n)
+        eng = sparc_new._Engine(A, "tc")
+        x = rng.randn(F, ML) * np.array([1.0, 1e-3, 30.0])[rng.randint(0, 3, (F, 1))]
+        z = rng.randn(F, n)
+        ab = eng.ab(eng.to_dev(x)).cpu().numpy().astype(np.float64)
+        az = eng.az(eng.to_dev(z)).cpu().numpy().astype(np.float64)
+        ref_ab, ref_az = x @ A.T, z @ A
+        err_ab = np.max(np.abs(ab - ref_ab)) / np.max(np.abs(ref_ab))
+        err_az = np.max(np.abs(az - ref_az)) / np.max(np.abs(ref_az))
+        assert err_ab < 5e-5 and err_az < 5e-5, (n, ML, F, err_ab, err_az)
+        # row-wise: every frame within 1e-4 of its own scale
+        assert np.all(np.max(np.abs(ab - ref_ab), 1) < 1e-4 * np.max(np.abs(ref_ab), 1))
+
+
+def test_tensor_core_mode_decoders(gold):
+    """precision='tc' (tensor-core products, fp32 elsewhere) on the converging case: same
+    bits as the reference, tau^2 within 1e-4."""
+    g, meta = gold
+    m = meta["z54_m2_hi"]
+    pre, c, sp, dp, y, A = setup_case(g, m, "z54_m2_hi", 0)
+    lp = dict(standard=m["standard"], rate=m["rate"], z=m["z"])
+    lengths = dict(k_ldpc=c.K * m["mults"], mults=m["mults"], L_unprotected=0)
+    beta, s, tau = sparc_new.sparc_amp(y, sp, dp, A, precision="tc", return_trace=True)
+    assert np.max(np.abs(tau - g[pre + "amp_tau_sqr"]) / g[pre + "amp_tau_sqr"]) < 1e-4
+    assert rel(beta, g[pre + "amp_beta"]) < 1e-4
+    assert np.array_equal(sparc_new.sparc_ldpc_decode(y, sp, lp, dp, True, lengths, A, precision="tc"), g[pre + "bits_separate"])
+    assert np.array_equal(sparc_new.naively_integrated_decoder(y, sp, lp, dp, A, precision="tc"), g[pre + "bits_naive"])
+    assert np.array_equal(sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="tc"), g[pre + "bits_integrated"])

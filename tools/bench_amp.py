@@ -25,12 +25,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--atol", type=float, default=None, help="early-stop atol (default: the reference's 2e-15)")
     args = ap.parse_args()
     import torch
     from ldpc_sparc_b200 import sparc
 
     cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
     dp = dict(t_max=25)
+    if args.atol is not None:
+        dp["atol"] = args.atol
     sparc.check_code_params(cp)
     sparc.check_decode_params(dp)
     W = sparc.create_base_matrix(**dict(cp, awgn_var=1.0))
@@ -69,7 +72,7 @@ def main():
     achieved = BYTES_PER_FRAME_ITER * frame_iters / (ms * 1e-3) / 1e9
     print(json.dumps({
         "workload": "sparc_public AMP decode, PA L=1024 M=32 R=1.5 (n=%d), t_max=25, %d frames sharing one design" % (n, F),
-        "precision": args.precision, "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
+        "precision": args.precision, "atol": dp.get("atol", 2e-15), "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
         "info_bits_per_s": F * 5120 / (ms * 1e-3), "mean_iterations": its,
         "section_error_rate": float((idx != idx0).float().mean().item()),
         "roofline": {"bound": "hbm (state-streaming model; really shared-memory/FFT bound, DESIGN.md)",
