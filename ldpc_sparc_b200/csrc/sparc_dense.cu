@@ -271,8 +271,9 @@ onsager_kernel(const T *__restrict__ beta, const T *__restrict__ vk, const T *__
                 sum_term += (q == i) ? aq * c * ((T)1 - aq) : aq * c * (-ai);
             }
             const size_t bi = f * (size_t)L * logM + (size_t)l * logM + k;
-            const T v0 = fmin(fmax(vk0[bi], (T)1e-10), (T)1 - (T)1e-10);
-            const T sub = ((T)1 / (v0 * ((T)1 - v0))) * sum_term;
+            // clip in fp64: 1 - 1e-10 is not representable in fp32 (v0 = 1 would divide by zero)
+            const double v0 = fmin(fmax((double)vk0[bi], 1e-10), 1.0 - 1e-10);
+            const T sub = (T)(1.0 / (v0 * (1.0 - v0))) * sum_term;
             const T v = vk[bi];
             if ((i >> shift) & 1) main_term -= v * sub;
             else main_term += ((T)1 - v) * sub;

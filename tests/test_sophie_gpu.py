@@ -170,3 +170,30 @@ def test_tensor_core_mode_decoders(gold):
     assert np.array_equal(sparc_new.sparc_ldpc_decode(y, sp, lp, dp, True, lengths, A, precision="tc"), g[pre + "bits_separate"])
     assert np.array_equal(sparc_new.naively_integrated_decoder(y, sp, lp, dp, A, precision="tc"), g[pre + "bits_naive"])
     assert np.array_equal(sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="tc"), g[pre + "bits_integrated"])
+
+
+def test_config5_small_variant_vs_oracle():
+    """BASELINE config 5, parity variant of SURVEY section 8: 802.16 r1/2 z=150, mults=1,
+    logM=1 (M=2), R=1 -> L = n = 3600, A = 3600 x 7200, P = 19.44, t_max = 25, at the two
+    ends of the reference's SNR sweep (performance_plots_general.py:21-47,96-98)."""
+    c = ldpc.code("802.16", "1/2", 150)
+    oc = sph.Code(c)
+    L, M, n = 3600, 2, 3600
+    sp = dict(P=19.44, R=1.0, L=L, M=M)
+    lp = dict(standard="802.16", rate="1/2", z=150)
+    lengths = dict(k_ldpc=c.K, mults=1, L_unprotected=0)
+    dp = dict(t_max=25)
+    ub, tb, beta0, x, A = sph.encode(sp, oc, 1, 11, c.encode)
+    rng = np.random.RandomState(11)
+    for snr in (6.0, 3.0):
+        y = x + np.sqrt(sp["P"] / snr) * rng.randn(n)
+        ref_sep = sph.sparc_ldpc_decode(y, sp, oc, dp, True, lengths, A)
+        ref_int = sph.integrated_decoder(y, sp, oc, dp, A)
+        got_sep = sparc_new.sparc_ldpc_decode(y, sp, lp, dp, True, lengths, A, precision="fp64")
+        got_int = sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="fp64")
+        assert np.array_equal(got_sep, ref_sep) and np.array_equal(got_int, ref_int), snr
+        if snr == 6.0:
+            assert np.array_equal(ref_int, ub)                       # decodes cleanly at the top of the sweep
+            assert np.array_equal(sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="tc"), ub)
+            assert np.array_equal(sparc_new.naively_integrated_decoder(y, sp, lp, dp, A, precision="tc"),
+                                  sph.naively_integrated_decoder(y, sp, oc, dp, A))
