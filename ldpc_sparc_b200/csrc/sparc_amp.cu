@@ -106,15 +106,17 @@ template <> struct Scale<double> { static __device__ __forceinline__ double get(
 
 // ------------------------------------------------------------ operator kernels
 // out[f, n] = A x[f, LM]   (reference Ab, sparc.py:786-789,811-819,851-862)
-template <typename T>
+// GBUF: the FFT buffer does not fit shared memory (w > 32768, e.g. BASELINE config 4
+// with w = 65536) and lives in a per-CTA global scratch (L2 resident) instead.
+template <typename T, bool GBUF>
 __global__ void __launch_bounds__(kThreads)
-ab_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ x, T *__restrict__ out, long long n_frames)
+ab_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ x, T *__restrict__ out, long long n_frames, T *gbuf)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     typedef typename Cplx<T>::type T2;
     const int H = 1 << d.h;
-    T2 *buf = reinterpret_cast<T2 *>(smem);
-    T *acc = reinterpret_cast<T *>(buf + H);   // [n]
+    T2 *buf = GBUF ? reinterpret_cast<T2 *>(gbuf + (size_t)blockIdx.x * d.w) : reinterpret_cast<T2 *>(smem);
+    T *acc = GBUF ? reinterpret_cast<T *>(smem) : reinterpret_cast<T *>(buf + H);   // [n]
     const int tid = threadIdx.x;
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         for (int i = tid; i < d.n; i += kThreads) acc[i] = (T)0;
@@ -132,14 +134,14 @@ ab_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ x, T *__restrict__
 }
 
 // out[f, LM] = A^T y[f, n]   (reference Az, sparc.py:791-794,821-829,864-875)
-template <typename T>
+template <typename T, bool GBUF>
 __global__ void __launch_bounds__(kThreads)
-az_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ y, T *__restrict__ out, long long n_frames)
+az_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ y, T *__restrict__ out, long long n_frames, T *gbuf)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     typedef typename Cplx<T>::type T2;
     const int H = 1 << d.h;
-    T2 *buf = reinterpret_cast<T2 *>(smem);
+    T2 *buf = GBUF ? reinterpret_cast<T2 *>(gbuf + (size_t)blockIdx.x * d.w) : reinterpret_cast<T2 *>(smem);
     const int tid = threadIdx.x;
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         T *o = out + f * (long long)d.L * d.M;
@@ -164,7 +166,7 @@ az_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ y, T *__restrict__
 }
 
 // ------------------------------------------------------------------ AMP kernel
-template <typename T>
+template <typename T, bool GBUF>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
 amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_all,
            const int32_t *__restrict__ idx0, AmpOut o, T *__restrict__ scratch, long long n_frames,
@@ -174,8 +176,10 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     typedef typename Cplx<T>::type T2;
     const int H = 1 << d.h;
     const int LM = d.L * d.M;
-    T2 *buf = reinterpret_cast<T2 *>(smem);
-    T *z = reinterpret_cast<T *>(buf + H);     // [n]
+    // per-CTA global scratch: [beta LM][s LM] (+ [FFT buffer w] when it does not fit shared memory)
+    T *cta_scratch = scratch + (size_t)blockIdx.x * (2 * (size_t)LM + (GBUF ? (size_t)d.w : 0));
+    T2 *buf = GBUF ? reinterpret_cast<T2 *>(cta_scratch + 2 * (size_t)LM) : reinterpret_cast<T2 *>(smem);
+    T *z = GBUF ? reinterpret_cast<T *>(smem) : reinterpret_cast<T *>(buf + H);     // [n]
     T *acc = z + d.n;                          // [n]
     __shared__ double psi[kMaxLc], psi_prev[kMaxLc], tau[kMaxLc], nm[kMaxLc];
     __shared__ double phi[kMaxLr], phi_prev[kMaxLr], gam[kMaxLr], zsq[kMaxLr];
@@ -183,7 +187,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     __shared__ int s_stop;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    T *beta = scratch + (size_t)blockIdx.x * 2 * (size_t)LM;   // per-CTA scratch
+    T *beta = cta_scratch;
     T *s = beta + LM;
     const int secs_per_col = d.Mc / d.M;                       // sections per column block
     const double sec_norm = (double)d.L / d.Lc;
@@ -457,37 +461,71 @@ int check_device(const lsb_sparc_design *g)
     return LSB_OK;
 }
 
-size_t amp_smem(const DesignDev &d, size_t elem) { return ((size_t)d.w + 2 * (size_t)d.n) * elem; }
-size_t ab_smem(const DesignDev &d, size_t elem) { return ((size_t)d.w + (size_t)d.n) * elem; }
-size_t az_smem(const DesignDev &d, size_t elem) { return (size_t)d.w * elem; }
+// shared memory per CTA; gbuf = FFT buffer kept in global memory instead
+size_t amp_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + 2 * (size_t)d.n) * elem; }
+size_t ab_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + (size_t)d.n) * elem; }
+size_t az_smem(const DesignDev &d, size_t elem, bool gbuf) { return (gbuf ? 16 : (size_t)d.w * elem); }
+bool needs_gbuf(const DesignDev &d, size_t elem) { return amp_smem(d, elem, false) + 8192 > (size_t)lsb::max_smem_optin(); }
+
+// (re)allocate the per-handle scratch and chain this launch behind the previous user
+int ensure_scratch(lsb_sparc_design *g, size_t need, cudaStream_t st)
+{
+    if (g->scratch_bytes < need) {
+        LSB_CUDA(cudaDeviceSynchronize());
+        if (g->d_scratch) cudaFree(g->d_scratch);
+        g->d_scratch = nullptr;
+        g->scratch_bytes = 0;
+        LSB_CUDA(cudaMalloc(&g->d_scratch, need));
+        g->scratch_bytes = need;
+    }
+    if (!g->scratch_event) LSB_CUDA(cudaEventCreateWithFlags(&g->scratch_event, cudaEventDisableTiming));
+    else LSB_CUDA(cudaStreamWaitEvent(st, g->scratch_event, 0));
+    return LSB_OK;
+}
 
 template <typename T> const FftTables<T> &tables(const lsb_sparc_design *g);
 template <> const FftTables<float> &tables<float>(const lsb_sparc_design *g) { return g->tb32; }
 template <> const FftTables<double> &tables<double>(const lsb_sparc_design *g) { return g->tb64; }
 
-template <typename T>
-int run_op(const lsb_sparc_design *g, bool transpose, const T *in, T *out, int64_t n_frames, cudaStream_t st)
+template <typename T, bool GBUF>
+int launch_op(lsb_sparc_design *g, bool transpose, const T *in, T *out, int64_t n_frames, long long grid,
+              cudaStream_t st)
 {
+    const size_t smem = transpose ? az_smem(g->dev, sizeof(T), GBUF) : ab_smem(g->dev, sizeof(T), GBUF);
+    LSB_REQUIRE(smem <= (size_t)lsb::max_smem_optin(), "design needs %zu B of shared memory (max %d)", smem,
+                lsb::max_smem_optin());
+    T *gbuf = GBUF ? (T *)g->d_scratch : nullptr;
+    if (transpose) {
+        LSB_CUDA(cudaFuncSetAttribute(az_kernel<T, GBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        az_kernel<T, GBUF><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out,
+                                                                  (long long)n_frames, gbuf);
+    } else {
+        LSB_CUDA(cudaFuncSetAttribute(ab_kernel<T, GBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ab_kernel<T, GBUF><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out,
+                                                                  (long long)n_frames, gbuf);
+    }
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+template <typename T>
+int run_op(const lsb_sparc_design *cg, bool transpose, const T *in, T *out, int64_t n_frames, cudaStream_t st)
+{
+    lsb_sparc_design *g = const_cast<lsb_sparc_design *>(cg);
     LSB_REQUIRE(g && in && out, "null pointer");
     LSB_REQUIRE(n_frames >= 0, "negative frame count");
     if (n_frames == 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
-    const size_t smem = transpose ? az_smem(g->dev, sizeof(T)) : ab_smem(g->dev, sizeof(T));
-    LSB_REQUIRE(smem <= (size_t)lsb::max_smem_optin(), "transform size %d needs %zu B of shared memory (max %d)",
-                g->dev.w, smem, lsb::max_smem_optin());
     long long grid = (long long)lsb::sm_count() * 4;
     if (grid > n_frames) grid = n_frames;
-    if (transpose) {
-        LSB_CUDA(cudaFuncSetAttribute(az_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        az_kernel<T><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out, (long long)n_frames);
-    } else {
-        LSB_CUDA(cudaFuncSetAttribute(ab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ab_kernel<T><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out, (long long)n_frames);
-    }
-    lsb::count_launch();
-    LSB_CUDA(cudaGetLastError());
-    return LSB_OK;
+    if (!needs_gbuf(g->dev, sizeof(T))) return launch_op<T, false>(g, transpose, in, out, n_frames, grid, st);
+    std::lock_guard<std::mutex> lock(g->mu);
+    if ((rc = ensure_scratch(g, (size_t)grid * g->dev.w * sizeof(T), st))) return rc;
+    rc = launch_op<T, true>(g, transpose, in, out, n_frames, grid, st);
+    if (!rc) LSB_CUDA(cudaEventRecord(g->scratch_event, st));
+    return rc;
 }
 
 template <typename T>
@@ -502,38 +540,37 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     if (n_frames == 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
-    const size_t smem = amp_smem(g->dev, sizeof(T));
-    LSB_REQUIRE(smem + 4096 <= (size_t)lsb::max_smem_optin(),
-                "design needs %zu B of shared memory per CTA (transform size %d, n %d): unsupported", smem,
-                g->dev.w, g->dev.n);
-    auto kern = amp_kernel<T>;
+    const bool gbuf = needs_gbuf(g->dev, sizeof(T));
+    const size_t smem = amp_smem(g->dev, sizeof(T), gbuf);
+    LSB_REQUIRE(smem + 8192 <= (size_t)lsb::max_smem_optin(),
+                "design needs %zu B of shared memory per CTA (n = %d): unsupported", smem, g->dev.n);
     int &cached = g->amp_grid[sizeof(T) == 8];
     if (cached == 0) {
-        LSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+        if (gbuf) {
+            LSB_CUDA(cudaFuncSetAttribute(amp_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amp_kernel<T, true>, kThreads, smem));
+        } else {
+            LSB_CUDA(cudaFuncSetAttribute(amp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amp_kernel<T, false>, kThreads, smem));
+        }
         if (per_sm < 1) per_sm = 1;
         cached = per_sm * lsb::sm_count();
     }
     long long grid = cached < n_frames ? cached : n_frames;
-    const size_t need = (size_t)cached * 2 * (size_t)g->dev.L * g->dev.M * sizeof(double);
+    const size_t need = (size_t)cached * (2 * (size_t)g->dev.L * g->dev.M + (gbuf ? (size_t)g->dev.w : 0)) * sizeof(double);
     std::lock_guard<std::mutex> lock(g->mu);
-    if (g->scratch_bytes < need) {
-        LSB_CUDA(cudaDeviceSynchronize());
-        if (g->d_scratch) cudaFree(g->d_scratch);
-        g->d_scratch = nullptr;
-        g->scratch_bytes = 0;
-        LSB_CUDA(cudaMalloc(&g->d_scratch, need));
-        g->scratch_bytes = need;
-    }
-    if (!g->scratch_event) LSB_CUDA(cudaEventCreateWithFlags(&g->scratch_event, cudaEventDisableTiming));
-    else LSB_CUDA(cudaStreamWaitEvent(st, g->scratch_event, 0));
+    if ((rc = ensure_scratch(g, need, st))) return rc;
     unsigned long long *queue = g->d_queue + (g->next_queue.fetch_add(1) % kCounters);
     LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method};
     AmpOut o{po->idx, po->t_final, po->psi, po->nmse, po->beta_soft, po->s_last, po->tau_trace, po->psi_trace};
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o, (T *)g->d_scratch,
-                                                (long long)n_frames, queue);
+    if (gbuf)
+        amp_kernel<T, true><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o,
+                                                                   (T *)g->d_scratch, (long long)n_frames, queue);
+    else
+        amp_kernel<T, false><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o,
+                                                                    (T *)g->d_scratch, (long long)n_frames, queue);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     LSB_CUDA(cudaEventRecord(g->scratch_event, st));
@@ -556,7 +593,7 @@ int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n
     LSB_REQUIRE(Mc % M == 0, "column blocks must hold whole sections");
     int w = 1;
     while (w < (Mr > Mc ? Mr : Mc) + 1) w <<= 1;
-    LSB_REQUIRE(w >= 4 && w <= 32768, "transform size %d outside [4, 32768] (larger designs not built yet)", w);
+    LSB_REQUIRE(w >= 4 && w <= 65536, "transform size %d outside [4, 65536] (index tables are 16-bit)", w);
     int h = 0;
     while ((2 << h) < w) ++h;   // H = w/2 = 2^h
     const int H = w / 2, N = w;
@@ -656,7 +693,7 @@ int lsb_sparc_design_info(const lsb_sparc_design *g, int64_t info[8])
     LSB_REQUIRE(g && info, "null pointer");
     const DesignDev &d = g->dev;
     info[0] = d.L; info[1] = d.M; info[2] = d.n; info[3] = d.Lr; info[4] = d.Lc; info[5] = d.w;
-    info[6] = d.n_blocks; info[7] = (int64_t)amp_smem(d, 4);
+    info[6] = d.n_blocks; info[7] = (int64_t)amp_smem(d, 4, needs_gbuf(d, 4));
     return LSB_OK;
 }
 

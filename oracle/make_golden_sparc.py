@@ -26,7 +26,13 @@ SPARC_CASES = {
                        B=2, R_PA_ratio=0.5), dict(t_max=20, phi_est_method=2), 1.0),
     # M=64 (> warp), tighter rtol
     "reg_m64": (dict(P=7.0, R=1.0, L=128, M=64), dict(t_max=30, rtol=1e-4), 1.0),
+    # transform size 65536 (does not fit shared memory): regular, one block of 384 x 32768
+    "big_reg": (dict(P=15.0, R=1.5, L=64, M=512), dict(t_max=20), 1.0),
+    # BASELINE config 4: spatially coupled "wave" decoding, sparc_demo_sc_decode_wave.ipynb:60-68
+    # (Lr=37, Lc=32, n=12284, w=65536, 192 blocks); one seed, no soft-state arrays (4 MB each)
+    "c4_sc_wave": (dict(P=15.0, R=1.5, L=2048, M=512, spatially_coupled=True, omega=6, Lambda=32), dict(t_max=40), 1.0),
 }
+BIG = {"c4_sc_wave"}
 SEEDS = ([1, 2], [5, 6])
 
 
@@ -66,13 +72,20 @@ def make_sparc(ref):
     meta = {}
     for name, (cp, dp, var) in SPARC_CASES.items():
         meta[name] = dict(code_params=cp, decode_params=dp, awgn_var=var, seeds=[list(s) for s in SEEDS])
-        for si, seed in enumerate(SEEDS):
+        seeds = SEEDS[:1] if name in BIG else SEEDS
+        meta[name]["seeds"] = [list(s) for s in seeds]
+        for si, seed in enumerate(seeds):
             r = run_reference(ref, cp, dp, var, seed)
+            logM = int(np.log2(cp["M"]))
+            truth = r["bits_in"].reshape(-1, logM).astype(int).dot(1 << np.arange(logM)[::-1])
+            print(name, seed, "t_final", int(r["t_final"]), "section errors", int((r["idx"] != truth).sum()), "n", int(r["n"]))
+            if name in BIG:
+                for k in ("s_last", "beta_soft", "x"):
+                    r.pop(k)
+                r["bits_in"] = np.packbits(r["bits_in"])
+                r["bits_out"] = np.packbits(r["bits_out"])
             for k, v in r.items():
                 out["%s_s%d_%s" % (name, si, k)] = v
-            print(name, seed, "t_final", int(r["t_final"]), "section errors",
-                  int((r["idx"] != (r["bits_in"].reshape(-1, int(np.log2(cp["M"]))).astype(int)
-                                    .dot(1 << np.arange(int(np.log2(cp["M"])))[::-1]))).sum()), "n", int(r["n"]))
     out["meta_json"] = np.array(json.dumps(meta))
     np.savez_compressed(os.path.join(GOLD, "sparc_reference.npz"), **out)
     print("sparc_reference.npz: %.1f kB" % (os.path.getsize(os.path.join(GOLD, "sparc_reference.npz")) / 1e3))

@@ -25,9 +25,27 @@ def _run_oracle(cp, dp, var, seed):
     return bits_i, beta0, x, y, design, out, trace
 
 
+def test_oracle_matches_reference_golden_config4(gold):
+    """BASELINE config 4 (SC wave, w = 65536, 192 blocks, n = 12284): ~20 s of numpy."""
+    g, meta = gold
+    m = meta["c4_sc_wave"]
+    pre = "c4_sc_wave_s0_"
+    bits_i, beta0, x, y, design, (bits_o, beta, T, nmse, expect), trace = _run_oracle(
+        m["code_params"], m["decode_params"], m["awgn_var"], m["seeds"][0])
+    assert (design.Lr, design.Lc, design.w, design.n) == (37, 32, 65536, 12284)
+    assert np.array_equal(np.packbits(bits_i), g[pre + "bits_in"]) and np.array_equal(y, g[pre + "y"])
+    assert T == int(g[pre + "t_final"]) and np.array_equal(np.packbits(bits_o), g[pre + "bits_out"])
+    assert np.array_equal(beta.reshape(-1, 512).argmax(1), g[pre + "idx"])
+    assert np.array_equal(nmse, g[pre + "nmse"])
+    assert np.array_equal(np.array([t["tau"] for t in trace]), g[pre + "tau_it"])
+    assert np.array_equal(np.array([t["psi"] for t in trace]), g[pre + "psi_it"])
+
+
 def test_oracle_matches_reference_golden(gold):
     g, meta = gold
     for name, m in meta.items():
+        if name == "c4_sc_wave":
+            continue
         for si, seed in enumerate(m["seeds"]):
             pre = "%s_s%d_" % (name, si)
             bits_i, beta0, x, y, design, (bits_o, beta, T, nmse, expect), trace = _run_oracle(

@@ -85,7 +85,7 @@ def _decode_case(g, meta, name, si, precision, **kw):
     return pre, cp, dp, out
 
 
-@pytest.mark.parametrize("name", ["c1_pa", "reg", "sc", "sc_pa_m16", "reg_m64"])
+@pytest.mark.parametrize("name", ["c1_pa", "reg", "sc", "sc_pa_m16", "reg_m64", "big_reg"])
 def test_amp_fp64_matches_reference_golden(gold, name):
     g, meta = gold
     for si in range(2):
@@ -100,7 +100,7 @@ def test_amp_fp64_matches_reference_golden(gold, name):
         assert np.allclose(nmse, g[pre + "nmse"], rtol=1e-5, atol=1e-7)                                      # nmse out is fp32
 
 
-@pytest.mark.parametrize("name", ["c1_pa", "reg", "sc", "sc_pa_m16", "reg_m64"])
+@pytest.mark.parametrize("name", ["c1_pa", "reg", "sc", "sc_pa_m16", "reg_m64", "big_reg"])
 def test_amp_fp32_matches_reference_golden(gold, name):
     g, meta = gold
     for si in range(2):
@@ -180,3 +180,33 @@ def test_batched_decode_vs_oracle():
     bits_t, idx_t, T_t, _, _ = sparc.sparc_decode(yt, cp, dp, 1.0, [1, 2], None, Ab, Az)
     assert np.array_equal(idx_t.cpu().numpy(), idx)
     assert np.array_equal(bits_t.cpu().numpy(), bits)
+
+
+def test_config4_sc_wave_matches_reference_golden(gold):
+    """BASELINE config 4 (sparc_demo_sc_decode_wave.ipynb: L=2048, M=512, R=1.5, omega=6,
+    Lambda=32, t_max=40 -> Lr=37, Lc=32, n=12284, transform size 65536, 192 blocks).  The FFT
+    buffer does not fit shared memory, so this runs the global-buffer variant of the kernels."""
+    g, meta = gold
+    m = meta["c4_sc_wave"]
+    pre = "c4_sc_wave_s0_"
+    cp, dp = dict(m["code_params"]), dict(m["decode_params"])
+    seed = m["seeds"][0]
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], seed)
+    assert cp["n"] == 12284 and Ab.design.w == 65536
+    assert np.array_equal(np.packbits(bits_in), g[pre + "bits_in"])
+    y = so.awgn_channel(x, m["awgn_var"], seed)
+    assert np.max(np.abs(y - g[pre + "y"])) < 1e-9 * np.max(np.abs(y))      # encode x = A beta0 on the GPU (fp64)
+    sparc.check_decode_params(dp)
+    T = int(g[pre + "t_final"])
+    for prec in ("fp64", "fp32"):
+        beta, t_final, nmse, psi, ex = sparc.sparc_amp(g[pre + "y"], cp, dp, m["awgn_var"], seed, beta0, Ab, Az,
+                                                       precision=prec, return_trace=True)
+        assert np.array_equal(beta.reshape(-1, 512).argmax(1), g[pre + "idx"]), prec
+        if prec == "fp64":
+            assert t_final == T
+            assert rel_err(ex["tau"][:T], g[pre + "tau_it"]) < 1e-9
+            assert np.allclose(nmse, g[pre + "nmse"], rtol=1e-5, atol=1e-7)
+        else:
+            assert T - 1 <= t_final <= dp["t_max"] - 1
+            Tc = min(T, t_final)
+            assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < 1e-4
