@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary workloads (SPARC AMP config 1, dense-design AMP config 3)")
     return ap.parse_args()
 
 
@@ -343,6 +345,18 @@ def main():
     out["clocks"] = clocks.summary()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(code, args, args.cpu_seconds)
+    if rank == 0 and world == 1 and not args.no_extras:
+        # secondary workloads of BASELINE.json (parity-test configs, reported for context; not the headline)
+        out["extra_workloads"] = {}
+        for key, cmd in (("sparc_amp_config1", ["tools/bench_amp.py", "--frames", "4096", "--steps", "2", "--warmup", "1"]),
+                         ("dense_amp_config3_tcgen05", ["tools/bench_dense.py", "--precision", "tc", "--frames", "1024",
+                                                        "--steps", "2", "--warmup", "1"])):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], capture_output=True,
+                                   text=True, timeout=240, cwd=ROOT)
+                out["extra_workloads"][key] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:   # the headline line must still be printed
+                out["extra_workloads"][key] = {"error": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -26,28 +26,41 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--atol", type=float, default=None, help="early-stop atol (default: the reference's 2e-15)")
+    ap.add_argument("--config", default="c1", choices=["c1", "c4"],
+                    help="c1: PA L=1024 M=32 R=1.5; c4: SC wave L=2048 M=512 R=1.5 omega=6 Lambda=32 t_max=40")
     args = ap.parse_args()
     import torch
     from ldpc_sparc_b200 import sparc
 
-    cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
-    dp = dict(t_max=25)
+    global BYTES_PER_FRAME_ITER
+    if args.config == "c1":
+        cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
+        dp = dict(t_max=25)
+    else:
+        cp = dict(P=15.0, R=1.5, L=2048, M=512, spatially_coupled=True, omega=6, Lambda=32)
+        dp = dict(t_max=40)
     if args.atol is not None:
         dp["atol"] = args.atol
     sparc.check_code_params(cp)
     sparc.check_decode_params(dp)
+    L_, M_ = cp["L"], cp["M"]
+    logM = int(np.log2(M_))
     W = sparc.create_base_matrix(**dict(cp, awgn_var=1.0))
-    n = int(round(1024 * 5 / 1.5))
+    n = int(round(L_ * logM / cp["R"]))
+    if W.ndim == 2:
+        n = int(round(n / W.shape[0])) * W.shape[0]
     cp["n"] = n
-    Ab, Az = sparc.sparc_transforms(W, 1024, 32, n, [1, 2])
+    BYTES_PER_FRAME_ITER = (2 * L_ * M_ + 3 * n) * 4          # beta r+w, z r+w, y r in fp32
+    Ab, Az = sparc.sparc_transforms(W, L_, M_, n, [1, 2])
     F = args.frames
+    chunk = max(1, min(1024, (256 << 20) // (L_ * M_ * 4)))
     gen = torch.Generator(device="cuda").manual_seed(0)
-    idx0 = torch.randint(0, 32, (F, 1024), device="cuda", generator=gen, dtype=torch.int32)
+    idx0 = torch.randint(0, M_, (F, L_), device="cuda", generator=gen, dtype=torch.int32)
     y = torch.empty((F, n), device="cuda", dtype=torch.float32)
-    for f0 in range(0, F, 1024):     # x = A beta0 in chunks (beta0 is 128 KB per frame)
-        f1 = min(F, f0 + 1024)
-        beta0 = torch.zeros((f1 - f0, 1024 * 32), device="cuda", dtype=torch.float32)
-        beta0.view(f1 - f0, 1024, 32).scatter_(2, idx0[f0:f1].long().unsqueeze(-1), 1.0)
+    for f0 in range(0, F, chunk):     # x = A beta0 in chunks (beta0 is L*M*4 bytes per frame)
+        f1 = min(F, f0 + chunk)
+        beta0 = torch.zeros((f1 - f0, L_ * M_), device="cuda", dtype=torch.float32)
+        beta0.view(f1 - f0, L_, M_).scatter_(2, idx0[f0:f1].long().unsqueeze(-1), 1.0)
         y[f0:f1] = Ab(beta0, precision="fp32") + torch.randn((f1 - f0, n), device="cuda", generator=gen)
     del beta0
 
@@ -71,9 +84,10 @@ def main():
     peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
     achieved = BYTES_PER_FRAME_ITER * frame_iters / (ms * 1e-3) / 1e9
     print(json.dumps({
-        "workload": "sparc_public AMP decode, PA L=1024 M=32 R=1.5 (n=%d), t_max=25, %d frames sharing one design" % (n, F),
+        "workload": "sparc_public AMP decode, config %s L=%d M=%d R=1.5 (n=%d), t_max=%d, %d frames sharing one design"
+                    % (args.config, L_, M_, n, dp["t_max"], F),
         "precision": args.precision, "atol": dp.get("atol", 2e-15), "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
-        "info_bits_per_s": F * 5120 / (ms * 1e-3), "mean_iterations": its,
+        "info_bits_per_s": F * L_ * logM / (ms * 1e-3), "mean_iterations": its,
         "section_error_rate": float((idx != idx0).float().mean().item()),
         "roofline": {"bound": "hbm (state-streaming model; really shared-memory/FFT bound, DESIGN.md)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
