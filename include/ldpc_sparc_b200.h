@@ -95,6 +95,12 @@ void lsb_ldpc_graph_destroy(lsb_ldpc_graph *g);
 /* nv, nc, nmsg, is_qc, z */
 int lsb_ldpc_graph_info(const lsb_ldpc_graph *g, int64_t info[5]);
 
+/* Systematic encoder on the device (QC graphs only), replaces code.encode
+ * (ldpc.py:400-460) for Monte-Carlo frame generation: info [n_frames, K] bytes
+ * (0/1) -> codewords [n_frames, N] bytes (0/1); asynchronous on `stream`. */
+int lsb_ldpc_encode_dev(const lsb_ldpc_graph *g, const uint8_t *info, uint8_t *codewords,
+                        int64_t n_frames, void *stream);
+
 /* Device-pointer decode, asynchronous on `stream` (a cudaStream_t; NULL = the
  * legacy default stream).  Replaces a loop of `code.decode(ch[f], max_it)`
  * (ldpc.py:463-490) over n_frames independent frames.

@@ -23,6 +23,52 @@ __global__ void convert_kernel(const A *__restrict__ in, B *__restrict__ out, lo
     const long long step = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += step) out[i] = (B)in[i];
 }
+
+// Systematic QC encoder (reference ldpc.py:400-460), one CTA per codeword, x held in
+// shared memory as [cols][z] bytes.  np.roll(v, -s)[i] = v[(i + s) mod z].
+__global__ void qc_encode_kernel(const int *__restrict__ proto, int rows, int cols, int z, int toff,
+                                 const uint8_t *__restrict__ info, uint8_t *__restrict__ cw, long long n_frames)
+{
+    extern __shared__ unsigned char enc_smem[];
+    const int Kp = cols - rows;
+    uint8_t *x = enc_smem;                 // [cols][z]
+    uint8_t *p = x + cols * z;             // [rows][z]
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        for (int i = threadIdx.x; i < Kp * z; i += blockDim.x) x[i] = info[f * (long long)Kp * z + i] & 1;
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * z; e += blockDim.x) {       // p_j = sum_k roll(x_k, -proto[j,k])
+            const int j = e / z, i = e - j * z;
+            unsigned acc = 0;
+            for (int k = 0; k < Kp; ++k) {
+                const int s = proto[j * cols + k];
+                if (s != -1) acc ^= x[k * z + (i + s) % z];
+            }
+            p[e] = (uint8_t)acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < z; i += blockDim.x) {              // first parity block: roll(sum_j p_j, toff)
+            const int src = (i - toff + z) % z;
+            unsigned acc = 0;
+            for (int j = 0; j < rows; ++j) acc ^= p[j * z + src];
+            x[Kp * z + i] = (uint8_t)acc;
+        }
+        __syncthreads();
+        for (int j = 0; j + 1 < rows; ++j) {                            // remaining parity blocks, one row at a time
+            const int myk = Kp + j + 1;
+            for (int i = threadIdx.x; i < z; i += blockDim.x) {
+                unsigned acc = p[j * z + i];
+                for (int k = Kp; k < myk; ++k) {
+                    const int s = proto[j * cols + k];
+                    if (s != -1) acc ^= x[k * z + (i + s) % z];
+                }
+                x[myk * z + i] = (uint8_t)acc;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < cols * z; i += blockDim.x) cw[f * (long long)cols * z + i] = x[i];
+        __syncthreads();
+    }
+}
 }  // namespace
 
 // ------------------------------------------------------------------ host side
@@ -36,6 +82,9 @@ struct lsb_ldpc_graph {
     // QC tables
     QcTables *d_tabs = nullptr;
     int qc_edges = 0;
+    // systematic encoder (QC graphs): protograph on the device, inverse offset of the first parity block
+    int *d_proto = nullptr;
+    int rows = 0, cols = 0, enc_toff = -1;
     // frame-queue counters (ring, one per launch in flight)
     unsigned long long *d_queue = nullptr;
     std::atomic<unsigned> next_queue{0};
@@ -414,6 +463,18 @@ int lsb_ldpc_graph_create_qc(const int32_t *proto, int rows, int cols, int z,
     g->is_qc = true;
     g->z = z;
     g->qc_edges = ne;
+    g->rows = rows;
+    g->cols = cols;
+    {   // encoder: the offsets in column Kp must add to a single offset (ldpc.py:435-446)
+        const int Kp = cols - rows;
+        std::vector<int> cnt(z, 0);
+        for (int r = 0; r < rows; ++r)
+            if (proto[r * cols + Kp] != -1) cnt[proto[r * cols + Kp] % z] ^= 1;
+        int n_odd = 0, off = -1;
+        for (int i = 0; i < z; ++i)
+            if (cnt[i]) { ++n_odd; off = i; }
+        g->enc_toff = n_odd == 1 ? off : -1;
+    }
     g->max_dc = max_dc;
     if (cudaGetDevice(&g->device) != cudaSuccess) {
         lsb::set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
@@ -425,6 +486,8 @@ int lsb_ldpc_graph_create_qc(const int32_t *proto, int rows, int cols, int z,
         cudaError_t e = cudaMalloc((void **)&g->d_tabs, sizeof(QcTables));
         if (e == cudaSuccess)
             e = cudaMemcpy(g->d_tabs, &t, sizeof(QcTables), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&g->d_proto, sizeof(int) * rows * cols);
+        if (e == cudaSuccess) e = cudaMemcpy(g->d_proto, proto, sizeof(int) * rows * cols, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             lsb::set_error("uploading QC tables: %s", cudaGetErrorString(e));
             rc = LSB_ERR_CUDA;
@@ -452,10 +515,32 @@ void lsb_ldpc_graph_destroy(lsb_ldpc_graph *g)
     cudaFree(g->d_coff);
     cudaFree(g->d_intrlv);
     cudaFree(g->d_tabs);
+    cudaFree(g->d_proto);
     cudaFree(g->d_queue);
     cudaFree(g->d_ws);
     if (g->ws_event) cudaEventDestroy(g->ws_event);
     delete g;
+}
+
+int lsb_ldpc_encode_dev(const lsb_ldpc_graph *g, const uint8_t *info, uint8_t *codewords, int64_t n_frames,
+                        void *stream)
+{
+    LSB_REQUIRE(g && info && codewords, "null pointer");
+    LSB_REQUIRE(g->is_qc && g->d_proto, "encoding needs a QC graph (lsb_ldpc_graph_create_qc)");
+    LSB_REQUIRE(g->enc_toff >= 0, "The offsets in colum Kp+1 of proto do not add to a single offset");
+    if (n_frames <= 0) return LSB_OK;
+    int rc = check_device(g);
+    if (rc) return rc;
+    const size_t smem = (size_t)(g->cols + g->rows) * g->z;
+    LSB_REQUIRE(smem <= 48 * 1024, "code too large for the encoder kernel");
+    long long grid = (long long)lsb::sm_count() * 8;
+    if (grid > n_frames) grid = n_frames;
+    qc_encode_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(g->d_proto, g->rows, g->cols, g->z,
+                                                                        g->enc_toff, info, codewords,
+                                                                        (long long)n_frames);
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
 }
 
 int lsb_ldpc_graph_info(const lsb_ldpc_graph *g, int64_t info[5])

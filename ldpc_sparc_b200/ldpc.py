@@ -281,6 +281,22 @@ class code:
             _lib.check(rc, "lsb_ldpc_decode_dev")
         return hard, iters
 
+    def encode_device(self, info):
+        """Systematic encoding on the GPU: CUDA tensor ``info [F, K]`` (any integer / bool
+        dtype, values 0/1) -> ``uint8 [F, N]`` codewords (same map as ``encode``)."""
+        import torch
+        if not info.is_cuda:
+            raise TypeError("encode_device takes a CUDA tensor (numpy arrays: use encode)")
+        if info.shape[-1] != self.K:
+            raise NameError('information word length not compatible with proto and z')
+        u = info.reshape(-1, self.K).to(torch.uint8).contiguous()
+        with torch.cuda.device(u.device):
+            g = self._handle()
+            x = torch.empty((u.shape[0], self.N), dtype=torch.uint8, device=u.device)
+            _lib.check(_lib.lib().lsb_ldpc_encode_dev(g, u.data_ptr(), x.data_ptr(), u.shape[0],
+                                                      torch.cuda.current_stream().cuda_stream), "lsb_ldpc_encode_dev")
+        return x
+
     # -------------------------------------------------------- scalar helpers
     def Lxor(self, L1, L2, corrflag=1):
         """LLR of the XOR of two bits (reference ldpc.py:492-495, c_ldpc.c:234)."""

@@ -94,3 +94,74 @@ def ldpc_awgn_sweep(code, snr_db_points, frames_per_point, max_itcount=200, seed
     out = {name: counters[:, i].cpu().numpy() for i, name in enumerate(COUNTER_FIELDS)}
     out["snr_db"] = np.asarray(snr_db_points, dtype=float)
     return out
+
+
+RATE_VALUE = {"1/2": .5, "2/3": 0.6667, "3/4": 0.75, "5/6": 0.83333}   # ldpc_awgn.py:63-72
+
+
+def sim(standard, rate, z, ptype='A', N_MEASUREMENTS=24, C_AWGN_OFFSET=1.0, P_STEP=100.0, MIN_ERRORS=100,
+        MAX_BLOCKS=400000, results_path=None, max_itcount=200, seed=0, batch=16384, device=None, decode_fn=None,
+        encode_fn=None):
+    """Batched equivalent of the reference campaign driver ``ldpc_awgn.sim``
+    (ldpc_jossy/py/ldpc_awgn.py:60-123): for every measurement point random information
+    words are encoded, sent over BPSK/AWGN and decoded until MIN_ERRORS block errors are
+    seen (or MAX_BLOCKS blocks), one result tuple
+    ``(standard, rate, z, SNR, nblocks, nblockerrors, nblocks*K, nbiterrors, nit_total)``
+    is appended to ``results_path`` (the reference's data/results.txt line format, :109-114)
+    and the SNR is stepped by ``sqrt(P_STEP / nblocks)`` (:116).
+
+    Frames are generated, decoded and counted on the GPU in batches; the counters are cut
+    at exactly the frame that brings the MIN_ERRORS-th block error, as the serial loop
+    does.  With a process group every rank contributes ``batch`` frames per round (rank r
+    takes the r-th slice of the round, so the global frame order is defined) and the
+    per-frame statistics of a round are all-gathered.  Returns the list of tuples."""
+    import torch
+    import torch.distributed as dist
+    from .ldpc import code as _code
+    if rate not in RATE_VALUE:
+        raise NameError("Rate unsupported")
+    rank, world = _rank_world()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    mycode = _code(standard, rate, z, ptype)
+    K, N = mycode.K, mycode.N
+    if decode_fn is None:
+        decode_fn = lambda llr, it: mycode.decode_hard(llr, it)
+    if encode_fn is None:
+        encode_fn = lambda u: mycode.encode_device(u)
+    SNR = 10.0 * np.log10(np.power(2, RATE_VALUE[rate]) - 1.0) + C_AWGN_OFFSET    # :76
+    res = []
+    for datapoint in range(N_MEASUREMENTS):
+        sigma2 = 1.0 / np.power(10, SNR / 10.0)
+        nblocks = nblockerrors = nbiterrors = nit_total = 0
+        rnd = 0
+        while nblockerrors < MIN_ERRORS and nblocks < MAX_BLOCKS:
+            gen = torch.Generator(device=device).manual_seed(chunk_seed(seed, datapoint, rnd * world + rank))
+            u = torch.randint(0, 2, (batch, K), device=device, generator=gen, dtype=torch.uint8)
+            x = encode_fn(u)
+            y = (1.0 - 2.0 * x.float()) + (sigma2 ** 0.5) * torch.randn((batch, N), device=device, generator=gen)
+            hard, iters = decode_fn((2.0 / sigma2) * y, max_itcount)
+            biterr = (hard.to(torch.uint8) != x).sum(dim=1).to(torch.int32)          # over all N code bits (:99)
+            stats = torch.stack([biterr, iters.to(torch.int32)])                      # [2, batch]
+            if world > 1:
+                allst = torch.empty((world,) + tuple(stats.shape), dtype=stats.dtype, device=device)
+                dist.all_gather_into_tensor(allst, stats)
+                stats = allst.permute(1, 0, 2).reshape(2, world * batch)             # global frame order of the round
+            be, it = stats[0].cpu().numpy().astype(np.int64), stats[1].cpu().numpy().astype(np.int64)
+            room = MAX_BLOCKS - nblocks
+            cum = np.cumsum(be > 0) + nblockerrors
+            hit = np.flatnonzero(cum >= MIN_ERRORS)
+            take = min(len(be), room, (hit[0] + 1) if len(hit) else len(be))
+            nblocks += take
+            nblockerrors += int((be[:take] > 0).sum())
+            nbiterrors += int(be[:take].sum())
+            nit_total += int(it[:take].sum())
+            rnd += 1
+        output = (standard, rate, z, float(SNR), nblocks, nblockerrors, nblocks * K, nbiterrors, nit_total)
+        res.append(output)
+        if results_path is not None and rank == 0:
+            with open(results_path, 'a') as f:
+                f.write(str(output))
+                f.write("\n")
+        SNR += np.sqrt(P_STEP / nblocks)
+    return res

@@ -296,3 +296,32 @@ def test_full_size_statistics_match_recorded_campaign():
     bler = hard.any(1).double().mean().item()
     assert abs(mean_it - 2122217 / 125625) < 0.15, mean_it      # sigma of the mean ~ 0.03
     assert 2e-4 < bler < 2.4e-3, bler                            # 8e-4 +- Poisson noise of both samples
+
+
+def test_device_encoder_equals_host_encoder():
+    import torch
+    for fam in (("802.11n", "1/2", 81, "A"), ("802.16", "5/6", 54, "A"), ("802.16", "2/3", 27, "B"),
+                ("802.16", "3/4", 150, "A"), ("802.11n", "3/4", 27, "A")):
+        c = ldpc.code(*fam)
+        rng = np.random.RandomState(1)
+        u = rng.randint(0, 2, (33, c.K))
+        x = c.encode_device(torch.from_numpy(u).cuda()).cpu().numpy()
+        assert np.array_equal(x, c.encode(u)), fam
+
+
+def test_campaign_driver_matches_reference_semantics(tmp_path):
+    """montecarlo.sim: the reference's stopping rule, tuple format and SNR stepping
+    (ldpc_awgn.py:60-123), statistics consistent with the recorded campaign."""
+    from ldpc_sparc_b200 import montecarlo
+    path = tmp_path / "results.txt"
+    res = montecarlo.sim("802.11n", "1/2", 81, N_MEASUREMENTS=3, MIN_ERRORS=100, MAX_BLOCKS=40000,
+                         results_path=str(path), batch=4096)
+    lines = path.read_text().strip().splitlines()
+    assert len(lines) == 3 and eval(lines[0]) == res[0]
+    std, rate, z, snr0, nblocks, nerr, nbits, nbiterr, nit = res[0]
+    assert (std, rate, z) == ("802.11n", "1/2", 81) and nbits == nblocks * 972
+    assert abs(snr0 - (10 * np.log10(2 ** 0.5 - 1) + 1.0)) < 1e-12           # -2.8278 dB, results.txt:115
+    assert nerr == 100 and nblocks == 100 and nit == 200 * 100               # hopeless SNR: every block fails at 200 its
+    assert abs(res[1][3] - (snr0 + 1.0)) < 1e-12                             # step sqrt(100/100) = 1 dB
+    # third point (-0.83 dB) is still below threshold in the recorded campaign (results.txt:252: 100/100)
+    assert res[2][5] >= 100 and res[2][4] <= 110

@@ -62,3 +62,40 @@ def test_two_rank_gloo_sweep_equals_single_process():
     # uncoded BPSK bit error rate Q(sqrt(1/sigma2)) at 0 dB ~ 0.1587, at 3 dB ~ 0.0789
     ber = single["bit_errors"] / (single["frames"] * code.N)
     assert abs(ber[0] - 0.1587) < 0.003 and abs(ber[1] - 0.0789) < 0.003
+
+
+def _sim_worker(rank, world, port, q, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    code = ldpc.code("802.11n", "1/2", 27)
+    enc = lambda u: torch.from_numpy(code.encode(u.numpy()).astype(np.uint8))
+    res = montecarlo.sim("802.11n", "1/2", 27, N_MEASUREMENTS=2, MIN_ERRORS=50, MAX_BLOCKS=2000, results_path=path,
+                         batch=256, device=torch.device("cpu"), decode_fn=_stub_decode, encode_fn=enc)
+    if rank == 0:
+        q.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_campaign_driver_two_ranks_gloo(tmp_path):
+    """montecarlo.sim over 2 gloo ranks with stubbed encode/decode: the per-round all-gather
+    gives every rank the same global frame order, rank 0 writes the reference's tuple lines."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    path = str(tmp_path / "results.txt")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sim_worker, args=(r, 2, port, q, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lines = open(path).read().strip().splitlines()
+    assert len(lines) == 2 and eval(lines[1]) == res[1]
+    for std, rate, z, snr, nblocks, nerr, nbits, nbiterr, nit in res:
+        assert nerr == 50 and nbits == nblocks * 324 and nit == 3 * nblocks      # uncoded stub: every block errs
+        assert nblocks == 50
+    assert abs(res[1][3] - res[0][3] - np.sqrt(100.0 / 50)) < 1e-12
