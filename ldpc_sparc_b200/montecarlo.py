@@ -144,9 +144,9 @@ def sim(standard, rate, z, ptype='A', N_MEASUREMENTS=24, C_AWGN_OFFSET=1.0, P_ST
             biterr = (hard.to(torch.uint8) != x).sum(dim=1).to(torch.int32)          # over all N code bits (:99)
             stats = torch.stack([biterr, iters.to(torch.int32)])                      # [2, batch]
             if world > 1:
-                allst = torch.empty((world,) + tuple(stats.shape), dtype=stats.dtype, device=device)
-                dist.all_gather_into_tensor(allst, stats)
-                stats = allst.permute(1, 0, 2).reshape(2, world * batch)             # global frame order of the round
+                parts = [torch.empty_like(stats) for _ in range(world)]
+                dist.all_gather(parts, stats.contiguous())
+                stats = torch.cat(parts, dim=1)                                       # global frame order of the round
             be, it = stats[0].cpu().numpy().astype(np.int64), stats[1].cpu().numpy().astype(np.int64)
             room = MAX_BLOCKS - nblocks
             cum = np.cumsum(be > 0) + nblockerrors
