@@ -69,6 +69,48 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v)
     return v;
 }
 
+// Gather / scatter loops: the U index-table entries of a batch are loaded before any
+// dependent shared-memory access, so U global loads are in flight per thread instead of
+// one (ncu: the table load -> address -> shared access chain was the top stall site).
+constexpr int kBatch = 4;
+
+template <typename T>
+__device__ __forceinline__ void gather_add(T *dst, const T *bf, const uint16_t *__restrict__ tab, T sc, int n, int tid)
+{
+    for (int i0 = tid; i0 < n; i0 += kThreads * kBatch) {
+        int id[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int i = i0 + u * kThreads;
+            id[u] = i < n ? (int)__ldg(tab + i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < n) dst[i] += sc * bf[id[u]];
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void scatter_scaled(T *bf, const uint16_t *__restrict__ tab, const T *src, T scale, int n,
+                                               int tid)
+{
+    for (int i0 = tid; i0 < n; i0 += kThreads * kBatch) {
+        int id[kBatch];
+        T v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int i = i0 + u * kThreads;
+            id[u] = i < n ? (int)__ldg(tab + i) : -1;
+            v[u] = i < n ? src[i] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+            if (id[u] >= 0) bf[id[u]] = v[u] * scale;
+    }
+}
+
 // ---- A_rc x : scatter a column block into the FFT buffer, DCT-II, leave Y in buf
 template <typename T>
 __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
@@ -79,7 +121,7 @@ __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &t
     for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
     __syncthreads();
     if (x) {
-        for (int j = tid; j < Mc; j += kThreads) bf[b.ab_scatter[j]] = x[j];
+        scatter_scaled<T>(bf, b.ab_scatter, x, (T)1, Mc, tid);
     }
     __syncthreads();
     fft_inplace<T, false>(buf, tb, tid, kThreads);
@@ -94,7 +136,7 @@ __device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> 
     T *bf = reinterpret_cast<T *>(buf);
     for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
     __syncthreads();
-    for (int i = tid; i < Mr; i += kThreads) bf[b.az_scatter[i]] = y[i] * yscale;
+    scatter_scaled<T>(bf, b.az_scatter, y, yscale, Mr, tid);
     __syncthreads();
     dct3_pre<T>(buf, tb, tid, kThreads);
     fft_inplace<T, true>(buf, tb, tid, kThreads);
@@ -125,7 +167,7 @@ ab_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ x, T *__restrict__
             block_forward<T>(buf, tb, b, x + f * (long long)d.L * d.M + (long long)b.c * d.Mc, -1, d.Mc, H, tid);
             const T *bf = reinterpret_cast<const T *>(buf);
             const T sc = Scale<T>::get(b);
-            for (int i = tid; i < d.Mr; i += kThreads) acc[b.r * d.Mr + i] += sc * bf[b.ab_gather[i]];
+            gather_add<T>(acc + b.r * d.Mr, bf, b.ab_gather, sc, d.Mr, tid);
             __syncthreads();
         }
         for (int i = tid; i < d.n; i += kThreads) out[f * d.n + i] = acc[i];
@@ -223,7 +265,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                     block_forward<T>(buf, tb, b, beta + (size_t)b.c * d.Mc, -1, d.Mc, H, tid);
                     const T *bf = reinterpret_cast<const T *>(buf);
                     const T sc = Scale<T>::get(b);
-                    for (int i = tid; i < d.Mr; i += kThreads) acc[b.r * d.Mr + i] += sc * bf[b.ab_gather[i]];
+                    gather_add<T>(acc + b.r * d.Mr, bf, b.ab_gather, sc, d.Mr, tid);
                     __syncthreads();
                 }
                 for (int i = tid; i < d.n; i += kThreads) {                 // z = y - A beta + b z  (:944-946)
@@ -272,10 +314,23 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                     block_transpose<T>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid);
                     const T *bf = reinterpret_cast<const T *>(buf);
                     const T sc = Scale<T>::get(b) * tau_c;
-                    for (int j = tid; j < d.Mc; j += kThreads) {
-                        const T v = sc * bf[b.az_gather[j]];
-                        if (bi == b0) s_c[j] = (t > 0 ? beta_c[j] : (T)0) + v;
-                        else s_c[j] += v;
+                    {
+                        const T *prev = bi == b0 ? (t > 0 ? beta_c : nullptr) : s_c;
+                        for (int j0 = tid; j0 < d.Mc; j0 += kThreads * kBatch) {
+                            int id[kBatch];
+                            T pv[kBatch];
+#pragma unroll
+                            for (int u = 0; u < kBatch; ++u) {
+                                const int j = j0 + u * kThreads;
+                                id[u] = j < d.Mc ? (int)__ldg(b.az_gather + j) : 0;
+                                pv[u] = (prev && j < d.Mc) ? prev[j] : (T)0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < kBatch; ++u) {
+                                const int j = j0 + u * kThreads;
+                                if (j < d.Mc) s_c[j] = pv[u] + sc * bf[id[u]];
+                            }
+                        }
                     }
                     __syncthreads();
                 }
