@@ -43,6 +43,10 @@
 #ifndef LSB_BP_CHEAP_SYNDROME
 #define LSB_BP_CHEAP_SYNDROME 1
 #endif
+// resident CTAs per SM the fp32 degree<=8 kernel's register budget is tuned for
+#ifndef LSB_BP_OCC8
+#define LSB_BP_OCC8 5
+#endif
 
 namespace lsb_bp {
 
@@ -305,16 +309,21 @@ __device__ __forceinline__ T variable_node_any(T *msg, const int2 *entry, int dv
 }
 
 // ------------------------------------------------------------------ QC kernel
-template <int MAXDC, int ELEM>
+template <int MAXDC, int ELEM, bool APG>
 struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
-    static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? 5 : (MAXDC <= 16 ? 4 : 3));
+    static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? (APG ? 6 : LSB_BP_OCC8) : (MAXDC <= 16 ? 4 : 3));
 };
 
-template <typename T, int ALGO, int MAXDC>
-__global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T)>::value)
+// APG: the APP vector is not kept in shared memory but written straight to its
+// output row (or, when the caller wants hard decisions only, to a per-CTA scratch row)
+// at every variable-node pass.  The stores cost the same instructions, stay in L2 and
+// free 4*nv bytes of shared memory per CTA: 6 instead of 5 resident CTAs per SM for the
+// n = 1944 code (40 registers, no spills).
+template <typename T, int ALGO, int MAXDC, bool APG>
+__global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T), APG>::value)
 bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *__restrict__ app,
              uint8_t *__restrict__ hard, int32_t *__restrict__ iters, long long n_frames,
-             int max_it, T scale, unsigned long long *__restrict__ queue)
+             int max_it, T scale, unsigned long long *__restrict__ queue, T *__restrict__ ap_scratch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QcTables tabs;
@@ -330,13 +339,14 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
     const unsigned magic = tabs.magic;
     T *msg = reinterpret_cast<T *>(smem_raw);   // [n_edges][z]
     T *ch = msg + n_msg;                        // [nv]
-    T *ap = ch + nv;                            // [nv]
+    T *ap = ch + nv;                            // [nv] (shared-memory variant)
 
     for (;;) {
         if (tid == 0) s_frame = (long long)atomicAdd(queue, 1ull);
         __syncthreads();
         const long long f = s_frame;
         if (f >= n_frames) break;
+        if (APG) ap = app ? app + f * nv : ap_scratch + (size_t)blockIdx.x * nv;
 
         const T *frame_llr = llr + f * nv;
         for (int v = tid; v < nv; v += kThreads) {
@@ -353,8 +363,8 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
                 const int c = (int)__umulhi((unsigned)v, magic);
                 const int j = v - c * z;
                 const int t0 = tabs.col_ptr[c];
-                ap[v] = variable_node_any<T>(msg, tabs.col_entry + t0, tabs.col_ptr[c + 1] - t0, j, z,
-                                             ch[v]);
+                const T total = variable_node_any<T>(msg, tabs.col_entry + t0, tabs.col_ptr[c + 1] - t0, j, z, ch[v]);
+                ap[v] = APG ? Domain<T, ALGO>::out(total) : total;
             }
             __syncthreads();
             // ---- check nodes: lane = consecutive checks of a (degree-sorted) row
@@ -372,11 +382,11 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
         }
 
         if (tid == 0) iters[f] = it;
-        if (app) {
+        if (!APG && app) {
             T *o = app + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = Domain<T, ALGO>::out(ap[v]);
         }
-        if (hard) {
+        if (hard) {   // (APG: every thread reads back only what it wrote itself)
             uint8_t *o = hard + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
         }
@@ -445,22 +455,22 @@ bp_generic_kernel(const int *__restrict__ voff, const int *__restrict__ coff,
 }
 
 // ------------------------------------------------------------------ launchers
-template <typename T, int ALGO, int MAXDC>
+template <typename T, int ALGO, int MAXDC, bool APG>
 int launch_qc_bucket(const QcLaunch<T> &a)
 {
-    auto kern = bp_qc_kernel<T, ALGO, MAXDC>;
+    auto kern = bp_qc_kernel<T, ALGO, MAXDC, APG>;
+    const size_t smem = APG ? a.smem_apg : a.smem;
     if (*a.cached_grid == 0) {
-        LSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)a.smem));
+        LSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, a.smem));
+        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
         if (per_sm < 1) per_sm = 1;
         *a.cached_grid = per_sm * lsb::sm_count();
     }
     long long grid = *a.cached_grid;
     if (grid > a.n_frames) grid = a.n_frames;
-    kern<<<(unsigned)grid, kThreads, a.smem, a.stream>>>(a.tabs, a.llr, a.app, a.hard, a.iters,
-                                                        a.n_frames, a.max_it, a.scale, a.queue);
+    kern<<<(unsigned)grid, kThreads, smem, a.stream>>>(a.tabs, a.llr, a.app, a.hard, a.iters, a.n_frames,
+                                                      a.max_it, a.scale, a.queue, a.ap_scratch);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     return LSB_OK;
@@ -469,9 +479,13 @@ int launch_qc_bucket(const QcLaunch<T> &a)
 template <typename T, int ALGO>
 int launch_qc_algo(const QcLaunch<T> &a)
 {
-    if (a.max_dc <= 8) return launch_qc_bucket<T, ALGO, 8>(a);
-    if (a.max_dc <= 16) return launch_qc_bucket<T, ALGO, 16>(a);
-    return launch_qc_bucket<T, ALGO, 24>(a);
+    // APP-in-global variant: fp32 sumprod2 on degree <= 8 codes (the throughput path)
+    if (a.max_dc <= 8) {
+        if (qc_uses_global_app<T>(a.max_dc, ALGO)) return launch_qc_bucket<T, ALGO, 8, true>(a);
+        return launch_qc_bucket<T, ALGO, 8, false>(a);
+    }
+    if (a.max_dc <= 16) return launch_qc_bucket<T, ALGO, 16, false>(a);
+    return launch_qc_bucket<T, ALGO, 24, false>(a);
 }
 
 template <typename T>
