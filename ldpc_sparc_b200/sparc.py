@@ -33,72 +33,71 @@ def is_power_of_2(x):
 
 
 # ------------------------------------------------------------ parameter checks
+_FLAGS = ('complex', 'modulated', 'power_allocated', 'spatially_coupled')
+_FLOAT = (float, np.float64)
+
+
+def _need(code_params, keys, kept):
+    """Copies the required keys into `kept`; same exception text as the reference."""
+    if any(k not in code_params for k in keys):
+        raise Exception('Need code parameters {}.'.format(list(keys)))
+    for k in keys:
+        kept[k] = copy(code_params[k])
+
+
 def check_code_params(code_params):
-    """Validates and normalises ``code_params`` in place (reference sparc.py:77-149)."""
-    code_params_copy = {}
+    """Validates ``code_params`` and normalises it IN PLACE: flags default to False, only
+    the keys the selected SPARC type needs survive (semantics of reference sparc.py:77-149:
+    exact Python types, AssertionError / Exception on violation, clear() + update())."""
+    kept = {}
+    for flag in _FLAGS:
+        value = code_params.setdefault(flag, False)
+        assert type(value) == bool, "'{}' must be boolean".format(flag)
+        kept[flag] = copy(value)
 
-    def in_code_param_list(code_param_list):
-        if all([(item in code_params) for item in code_param_list]):
-            for item in code_param_list:
-                code_params_copy[item] = copy(code_params[item])
-        else:
-            raise Exception('Need code parameters {}.'.format(code_param_list))
-
-    for item in ['complex', 'modulated', 'power_allocated', 'spatially_coupled']:
-        if item not in code_params:
-            code_params[item] = False
-        else:
-            assert type(code_params[item]) == bool, "'{}' must be boolean".format(item)
-        code_params_copy[item] = copy(code_params[item])
-
-    code_param_list = ['P', 'R', 'L', 'M']
-    in_code_param_list(code_param_list)
-    P, R, L, M = map(code_params.get, code_param_list)
-    assert (type(P) == float or type(P) == np.float64) and P > 0
-    assert (type(R) == float or type(R) == np.float64) and R > 0
+    _need(code_params, ('P', 'R', 'L', 'M'), kept)
+    P, R, L, M = (code_params[k] for k in ('P', 'R', 'L', 'M'))
+    assert type(P) in _FLOAT and P > 0
+    assert type(R) in _FLOAT and R > 0
     assert type(L) == int and L > 0
     assert type(M) == int and M > 0 and is_power_of_2(M)
 
-    if code_params['modulated']:
-        in_code_param_list(['K'])
+    if kept['modulated']:                       # K-PSK modulation of the non-zero values
+        _need(code_params, ('K',), kept)
         K = code_params['K']
         assert type(K) == int and K > 1 and is_power_of_2(K)
-        if not code_params['complex']:
-            assert K == 2, 'Real-modulated SPARCs requires K=2'
-
-    if code_params['power_allocated']:
-        in_code_param_list(['B', 'R_PA_ratio'])
-        B, R_PA_ratio = map(code_params.get, ['B', 'R_PA_ratio'])
+        assert kept['complex'] or K == 2, 'Real-modulated SPARCs requires K=2'
+    if kept['power_allocated']:                 # iterative power allocation over B blocks
+        _need(code_params, ('B', 'R_PA_ratio'), kept)
+        B, ratio = code_params['B'], code_params['R_PA_ratio']
         assert type(B) == int and B > 1
         assert L % B == 0, 'B must divide L'
-        assert type(R_PA_ratio) == float or type(R_PA_ratio) == np.float64
-        assert R_PA_ratio >= 0
-
-    if code_params['spatially_coupled']:
-        in_code_param_list(['omega', 'Lambda'])
-        omega, Lambda = map(code_params.get, ['omega', 'Lambda'])
+        assert type(ratio) in _FLOAT
+        assert ratio >= 0
+    if kept['spatially_coupled']:               # (omega, Lambda) band base matrix
+        _need(code_params, ('omega', 'Lambda'), kept)
+        omega, Lambda = code_params['omega'], code_params['Lambda']
         assert type(omega) == int and omega > 1
         assert type(Lambda) == int and Lambda >= (2 * omega - 1)
         assert L % Lambda == 0, 'Lambda must divide L'
-
-    if code_params['power_allocated'] and code_params['spatially_coupled']:
-        assert L % (Lambda * B) == 0, 'Lambda*B must divide L'
+        if kept['power_allocated']:
+            assert L % (Lambda * B) == 0, 'Lambda*B must divide L'
 
     code_params.clear()
-    code_params.update(dict(code_params_copy))
+    code_params.update(kept)
 
 
 def check_decode_params(decode_params):
-    """Reference sparc.py:151-170."""
-    if not all([(item in decode_params) for item in ['t_max']]):
+    """``t_max`` is required; ``rtol`` (1e-6) and ``phi_est_method`` (1) get their defaults
+    in place (reference sparc.py:151-170)."""
+    if 't_max' not in decode_params:
         raise Exception('Need decode parameters {}.'.format(['t_max']))
-    for key, val in {'rtol': 1e-6, 'phi_est_method': 1}.items():
-        if key not in decode_params:
-            decode_params[key] = val
-    t_max, rtol, phi_est_method = map(decode_params.get, ['t_max', 'rtol', 'phi_est_method'])
+    decode_params.setdefault('rtol', 1e-6)
+    decode_params.setdefault('phi_est_method', 1)
+    t_max, rtol = decode_params['t_max'], decode_params['rtol']
     assert type(t_max) == int and t_max > 1
     assert type(rtol) == float and 0 < rtol < 1
-    assert phi_est_method == 1 or phi_est_method == 2
+    assert decode_params['phi_est_method'] in (1, 2)
 
 
 def _require_real_unmodulated(code_params):
@@ -196,52 +195,42 @@ def msg_vector_map_estimator(s, M, K=1):
 
 # ------------------------------------------------------------- base matrix W
 def pa_iterative(P, sigmaSqr, B, R_PA):
-    """Iterative power allocation (reference sparc.py:516-533)."""
+    """Iterative power allocation over B blocks (reference sparc.py:516-533): block b gets
+    2 ln2 R_PA (sigma^2 + P - mean(Q)) while that exceeds an even split of the remaining
+    power, after which the remainder is spread evenly; the result is renormalised to mean P."""
     Q = np.zeros(B)
-    for b in range(B):
-        phi = sigmaSqr + P - Q.mean()
-        Pblock = 2 * np.log(2) * R_PA * phi
-        Pspread = (B * P - Q.sum()) / (B - b)
-        if Pblock > Pspread:
-            Q[b:b + 1] = Pblock
-        else:
-            Q[b:] = Pspread
+    b = 0
+    while b < B:
+        greedy = 2 * np.log(2) * R_PA * (sigmaSqr + P - Q.mean())
+        even = (B * P - Q.sum()) / (B - b)
+        if greedy <= even:
+            Q[b:] = even
             break
-    Q /= Q.mean() / P
-    return Q
+        Q[b] = greedy
+        b += 1
+    return Q / (Q.mean() / P)
 
 
 def sc_basic(Q, omega, Lambda):
-    """(omega, Lambda) spatially coupled base matrix (reference sparc.py:535-568)."""
+    """(omega, Lambda) spatially coupled base matrix with uncoupled entry / vector Q
+    (reference sparc.py:535-568): column block c carries Q * Lr / omega in rows c..c+omega-1."""
     assert type(Q) == np.ndarray
-    Lr = Lambda + omega - 1
-    if Q.ndim == 0:
-        W = np.zeros((Lr, Lambda))
-        for c in range(Lambda):
-            W[c:c + omega, c] = Q * Lr / omega
-    elif Q.ndim == 1:
-        B = Q.size
-        W = np.zeros((Lr, Lambda * B))
-        for c in range(Lambda):
-            for r in range(c, c + omega):
-                W[r, c * B:(c + 1) * B] = Q * Lr / omega
-    else:
+    if Q.ndim > 1:
         raise Exception('Something wrong with Q')
+    Lr = Lambda + omega - 1
+    r, c = np.arange(Lr)[:, None], np.arange(Lambda)[None, :]
+    band = ((r >= c) & (r < c + omega)).astype(float)              # [Lr, Lambda]
+    W = band * (Q * Lr / omega) if Q.ndim == 0 else np.kron(band, (Q * Lr / omega)[None, :])
     assert np.isclose(W.mean(), np.mean(Q)), "Average base matrix values must equal P"
     return W
 
 
 def create_base_matrix(P, power_allocated=False, spatially_coupled=False, **kwargs):
-    """Reference sparc.py:570-589."""
-    if not power_allocated:
-        Q = np.array(P)
-    else:
-        awgn_var, B, R, R_PA_ratio = map(kwargs.get, ['awgn_var', 'B', 'R', 'R_PA_ratio'])
-        Q = pa_iterative(P, awgn_var, B, R * R_PA_ratio)
-    if not spatially_coupled:
-        return Q
-    omega, Lambda = map(kwargs.get, ['omega', 'Lambda'])
-    return sc_basic(Q, omega, Lambda)
+    """Base entry / vector / matrix W of the design (reference sparc.py:570-589)."""
+    Q = np.array(P)
+    if power_allocated:
+        Q = pa_iterative(P, kwargs['awgn_var'], kwargs['B'], kwargs['R'] * kwargs['R_PA_ratio'])
+    return sc_basic(Q, kwargs['omega'], kwargs['Lambda']) if spatially_coupled else Q
 
 
 # ----------------------------------------------------------- design + operators
