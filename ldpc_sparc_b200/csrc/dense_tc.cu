@@ -8,14 +8,17 @@
 // (x = hi + lo, 16 mantissa bits) and three MMAs accumulate into the same fp32 TMEM
 // tile:  W_hi X_hi + W_lo X_hi + W_hi X_lo  (the lo*lo term is below 2^-16 relative).
 //
-// Kernel anatomy (one 128 x 128 output tile per CTA, K streamed in 64-element blocks):
+// Kernel anatomy (persistent, one CTA per SM; a work item is one 128 x 128 output tile over
+// one K range, K streamed in 64-element blocks; K is split when the tile count alone would
+// leave the last wave mostly idle, partials summed in fixed order by reduce_splits_kernel):
 //   warp 0, one lane : TMA producer  - 4 tiles (W_hi, W_lo, X_hi, X_lo; 128 rows x 128 B,
 //                      SWIZZLE_128B) per stage, 3-stage ring, mbarrier expect_tx
 //   warp 1, one lane : MMA issuer    - 4 k-steps x 3 tcgen05.mma.cta_group::1.kind::f16
 //                      (M = 128, N = 128, K = 16) per stage, tcgen05.commit frees the stage
-//   warp 2           : TMEM allocator (128 fp32 columns)
+//   warp 2           : TMEM allocator (2 accumulators x 128 fp32 columns)
 //   warps 4..7       : epilogue      - tcgen05.ld 32x32b.x32, transposed store C[f, r]
-//                      (lanes = consecutive r: coalesced)
+//                      (lanes = consecutive r: coalesced); drains accumulator j & 1 while
+//                      the MMAs of the CTA's next item fill the other one
 #include "common.cuh"
 
 #include <cuda.h>
@@ -89,22 +92,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: CTA b works on items b, b + gridDim.x, ...; an item is one 128 x 128 output
+// tile restricted to one of `splits` contiguous K ranges (partial s goes to C + s * split_stride;
+// the caller sums the partials in a fixed order, so results do not depend on scheduling).
+// Two TMEM accumulators: the epilogue of item j overlaps the MMAs of item j + 1.
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
                const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
-               float *__restrict__ C, int rows_total, int F, int K)
+               float *__restrict__ C, int rows_total, int F, int K, int n_row_tiles, int n_f_tiles, int splits,
+               long long split_stride)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full_bar[2], acc_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // W row tiles vary fastest: co-resident CTAs stream different W panels against the same
-    // X tile (measured 1.7x faster than the opposite order, which makes 8 CTAs hit one W
-    // panel at the same time)
-    const int row0 = blockIdx.x * kTileRows, f0 = blockIdx.y * kTileN;
     const int num_kb = (K + kBlockK - 1) / kBlockK;
+    const int n_tiles = n_row_tiles * n_f_tiles;
+    const int n_items = n_tiles * splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW_hi) : "memory");
@@ -117,32 +128,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constan
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full_bar[a], 1);
+            mbar_init(&acc_empty_bar[a], 4);     // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "n"(kTileN)
+                     "n"(2 * kTileN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_slot;
+    const uint32_t tmem_base = tmem_base_slot;
+
+    // item -> (W row tile, frame tile, K range).  Frame tiles vary fastest: the CTAs running
+    // at the same time share a few W panels (one DRAM read each, the rest L2 hits) and the
+    // frame operand stays L2-resident.  With W row tiles fastest, A^T z (W = 403 MB of bf16
+    // hi/lo, 8 frame tiles) re-read W from DRAM once per frame tile: 578 us vs 467 us.
+#define LSB_TC_DECODE_ITEM(item)                                               \
+    const int split = (item) / n_tiles, tile = (item) - split * n_tiles;      \
+    const int row0 = (tile / n_f_tiles) * kTileRows;                           \
+    const int f0 = (tile % n_f_tiles) * kTileN;                                \
+    const int kb0 = (int)(((long long)split * num_kb) / splits);               \
+    const int kb1 = (int)(((long long)(split + 1) * num_kb) / splits);
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t phase = (kb / kStages) & 1;
-                mbar_wait(&empty_bar[s], phase ^ 1);
-                uint8_t *st = tiles + s * kStageBytes;
-                mbar_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_2d(st, &mapW_hi, &full_bar[s], kb * kBlockK, row0);
-                tma_load_2d(st + kTileBytes, &mapW_lo, &full_bar[s], kb * kBlockK, row0);
-                tma_load_2d(st + 2 * kTileBytes, &mapX_hi, &full_bar[s], kb * kBlockK, f0);
-                tma_load_2d(st + 3 * kTileBytes, &mapX_lo, &full_bar[s], kb * kBlockK, f0);
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                LSB_TC_DECODE_ITEM(item)
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&empty_bar[s], phase ^ 1);
+                    uint8_t *st = tiles + s * kStageBytes;
+                    mbar_expect_tx(&full_bar[s], kStageBytes);
+                    tma_load_2d(st, &mapW_hi, &full_bar[s], kb * kBlockK, row0);
+                    tma_load_2d(st + kTileBytes, &mapW_lo, &full_bar[s], kb * kBlockK, row0);
+                    tma_load_2d(st + 2 * kTileBytes, &mapX_hi, &full_bar[s], kb * kBlockK, f0);
+                    tma_load_2d(st + 3 * kTileBytes, &mapX_lo, &full_bar[s], kb * kBlockK, f0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -150,59 +179,99 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constan
             // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                                    ((uint32_t)(kTileRows >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t phase = (kb / kStages) & 1;
-                mbar_wait(&full_bar[s], phase);
+            uint32_t it = 0, j = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+                LSB_TC_DECODE_ITEM(item)
+                (void)row0;
+                (void)f0;
+                const uint32_t a = j & 1;
+                mbar_wait(&acc_empty_bar[a], ((j >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t base = smem_u32(tiles + s * kStageBytes);
-                const uint64_t dW_hi = umma_desc(base), dW_lo = umma_desc(base + kTileBytes);
-                const uint64_t dX_hi = umma_desc(base + 2 * kTileBytes), dX_lo = umma_desc(base + 3 * kTileBytes);
+                const uint32_t tmem_d = tmem_base + a * kTileN;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&full_bar[s], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(tiles + s * kStageBytes);
+                    const uint64_t dW_hi = umma_desc(base), dW_lo = umma_desc(base + kTileBytes);
+                    const uint64_t dX_hi = umma_desc(base + 2 * kTileBytes), dX_lo = umma_desc(base + 3 * kTileBytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K step inside the swizzle row
-                    umma_bf16(tmem_d, dW_hi + adv, dX_hi + adv, idesc, (kb | k) != 0);
-                    umma_bf16(tmem_d, dW_lo + adv, dX_hi + adv, idesc, 1);
-                    umma_bf16(tmem_d, dW_hi + adv, dX_lo + adv, idesc, 1);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K step inside the swizzle row
+                        umma_bf16(tmem_d, dW_hi + adv, dX_hi + adv, idesc, (kb != kb0) || (k != 0));
+                        umma_bf16(tmem_d, dW_lo + adv, dX_hi + adv, idesc, 1);
+                        umma_bf16(tmem_d, dW_hi + adv, dX_lo + adv, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
+                umma_commit(&acc_full_bar[a]);       // accumulator complete
             }
-            umma_commit(&tmem_full_bar);         // accumulator complete
         }
     } else if (warp >= 4) {
-        mbar_wait(&tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                   // TMEM lane quarter this warp may read
-        const int r = row0 + q * 32 + lane;
+        uint32_t j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            LSB_TC_DECODE_ITEM(item)
+            (void)kb0;
+            (void)kb1;
+            const uint32_t a = j & 1;
+            float *Cs = C + (size_t)split * (size_t)split_stride;
+            mbar_wait(&acc_full_bar[a], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r = row0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTileN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-                  "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                  "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (r < rows_total) {
+            for (int c0 = 0; c0 < kTileN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + a * kTileN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (r < rows_total) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int f = f0 + c0 + j;
-                    if (f < F) C[(size_t)f * rows_total + r] = __uint_as_float(v[j]);
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int f = f0 + c0 + jj;
+                        if (f < F) Cs[(size_t)f * rows_total + r] = __uint_as_float(v[jj]);
+                    }
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty_bar[a]);
         }
     }
+#undef LSB_TC_DECODE_ITEM
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(kTileN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTileN) : "memory");
+    }
+}
+
+// out = sum of `splits` partial products, added in index order (fixed result)
+__global__ void reduce_splits_kernel(const float4 *__restrict__ part, float4 *__restrict__ out, long long n4, int splits)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n4; i += step) {
+        float4 a = part[i];
+        for (int s = 1; s < splits; ++s) {
+            const float4 b = part[(long long)s * n4 + i];
+            a.x += b.x;
+            a.y += b.y;
+            a.z += b.z;
+            a.w += b.w;
+        }
+        out[i] = a;
     }
 }
 
@@ -294,6 +363,8 @@ struct lsb_tc_design {
     std::mutex mu;
     __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr;   // staging of the split frame operand
     size_t x_cap = 0;
+    float *part = nullptr;                             // partial products of a K-split launch
+    size_t part_cap = 0;
     cudaEvent_t x_event = nullptr;
 };
 
@@ -350,9 +421,47 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
         LSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
-    dim3 grid((unsigned)((W.rows + kTileRows - 1) / kTileRows), (unsigned)((F + kTileN - 1) / kTileN));
-    tc_gemm_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(W.map_hi, W.map_lo, mx_hi, mx_lo, out, (int)W.rows, (int)F,
-                                                        (int)W.K);
+    const int n_row_tiles = (int)((W.rows + kTileRows - 1) / kTileRows), n_f_tiles = (int)((F + kTileN - 1) / kTileN);
+    const int n_tiles = n_row_tiles * n_f_tiles, sms = lsb::sm_count();
+    const int num_kb = (int)((W.K + kBlockK - 1) / kBlockK);
+    // K splits: few tiles (A beta: n/128 x F/128) leave most of the last wave idle; pick the
+    // split count that minimises rounds-per-split, charging 3% per extra partial written
+    int splits = 1;
+    {
+        double best = 1e30;
+        for (int sp = 1; sp <= 8 && sp * 8 <= num_kb; ++sp) {
+            const double cost = (double)((n_tiles * sp + sms - 1) / sms) / sp + 0.03 * (sp - 1);
+            if (cost < best - 1e-9) {
+                best = cost;
+                splits = sp;
+            }
+        }
+    }
+    const size_t out_count = (size_t)F * (size_t)W.rows;
+    if (((uintptr_t)out & 15) != 0) splits = 1;     // the partial sum runs on float4
+    float *dst = out;
+    if (splits > 1) {
+        const size_t need_part = out_count * (size_t)splits;
+        if (g->part_cap < need_part) {
+            LSB_CUDA(cudaDeviceSynchronize());
+            cudaFree(g->part);
+            g->part = nullptr;
+            g->part_cap = 0;
+            LSB_CUDA(cudaMalloc((void **)&g->part, need_part * sizeof(float)));
+            g->part_cap = need_part;
+        }
+        dst = g->part;
+    }
+    const int n_items = n_tiles * splits;
+    tc_gemm_kernel<<<n_items < sms ? n_items : sms, kThreadsTc, kSmemBytes, st>>>(
+        W.map_hi, W.map_lo, mx_hi, mx_lo, dst, (int)W.rows, (int)F, (int)W.K, n_row_tiles, n_f_tiles, splits,
+        (long long)out_count);
+    if (splits > 1) {
+        lsb::count_launch();
+        LSB_CUDA(cudaGetLastError());
+        reduce_splits_kernel<<<sms * 8, 256, 0, st>>>((const float4 *)g->part, (float4 *)out, (long long)(out_count / 4),
+                                                     splits);
+    }
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     LSB_CUDA(cudaEventRecord(g->x_event, st));
@@ -418,6 +527,7 @@ void lsb_tc_design_destroy(lsb_tc_design *g)
     cudaFree(g->At.lo);
     cudaFree(g->x_hi);
     cudaFree(g->x_lo);
+    cudaFree(g->part);
     if (g->x_event) cudaEventDestroy(g->x_event);
     delete g;
 }

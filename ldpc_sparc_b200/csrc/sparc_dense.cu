@@ -123,52 +123,92 @@ residual_kernel(const T *__restrict__ y, const T *__restrict__ ab, T *__restrict
     if (threadIdx.x == 0) tau_sqr[f] = tot / n;
 }
 
-// s = beta + atz ; beta <- sqrt_nPl * softmax_section(sqrt_nPl * s / tau_sqr) ; beta_sq = |beta|^2.
-// One CTA per frame, one warp per section (any power-of-two M).
-template <typename T>
+// s = beta_in + atz ; beta <- sqrt_nPl * softmax_section(sqrt_nPl * s / tau_sqr) ; beta_sq = |beta|^2.
+// One CTA per frame, one warp per section.  PL = entries per lane (M = 32*PL) or 0 for
+// M < 32 (32/M sections per warp pass).  The loads of the warp's next section are issued
+// before the current one is reduced (the kernel was bound by the exposed load latency of
+// one section at a time).
+template <typename T, int PL>
 __global__ void __launch_bounds__(kThreads)
 denoise_kernel(const T *beta_in, const T *__restrict__ atz, T *beta, T *__restrict__ s_out,
                const double *tau_sqr, double *beta_sq, int L, int M, double sqrt_nPl)
 {
-    const bool add_beta = beta_in != nullptr;   // beta_in may alias beta (each entry is read before it is written)
     __shared__ double red[kThreads / 32];
+    const bool add_beta = beta_in != nullptr;   // beta_in may alias beta (each entry is read before it is written)
     const size_t f = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T scale = (T)(sqrt_nPl / tau_sqr[f]);
     const T amp = (T)sqrt_nPl;
+    const size_t frame_base = f * (size_t)L * M;
     double part = 0.0;
-    const int spw = M >= 32 ? 1 : 32 / M;      // sections per warp pass
-    const int per_lane = M >= 32 ? M / 32 : 1;
-    for (int sec0 = warp * spw; sec0 < L; sec0 += (kThreads / 32) * spw) {
-        const int sec = M >= 32 ? sec0 : sec0 + lane / M;
-        const bool live = sec < L;
-        const size_t base = f * (size_t)L * M + (size_t)sec * M;
-        T mx = -INFINITY;
-        T sv[8];   // M <= 256
-        for (int k = 0; k < per_lane; ++k) {
-            const int j = M >= 32 ? lane + 32 * k : lane % M;
+    if (PL > 0) {
+        constexpr int P = PL > 0 ? PL : 1;
+        constexpr int WARPS = kThreads / 32;
+        T nx[P];
+        int sec = warp;
+        if (sec < L) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const size_t a = frame_base + (size_t)sec * M + lane + 32 * k;
+                nx[k] = atz[a] + (add_beta ? beta_in[a] : (T)0);
+            }
+        }
+        for (; sec < L; sec += WARPS) {
+            T sv[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) sv[k] = nx[k];
+            const int nsec = sec + WARPS;
+            if (nsec < L) {                      // prefetch the next section of this warp
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    const size_t a = frame_base + (size_t)nsec * M + lane + 32 * k;
+                    nx[k] = atz[a] + (add_beta ? beta_in[a] : (T)0);
+                }
+            }
+            const size_t base = frame_base + (size_t)sec * M;
+            T mx = sv[0];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                if (s_out) s_out[base + lane + 32 * k] = sv[k];
+                mx = fmax(mx, sv[k]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            T sum = (T)0;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                sv[k] = exp((sv[k] - mx) * scale);
+                sum += sv[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const T inv = amp / sum;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const T b = sv[k] * inv;
+                beta[base + lane + 32 * k] = b;
+                part += (double)b * (double)b;
+            }
+        }
+    } else {
+        const int spw = 32 / M;      // sections per warp pass
+        for (int sec0 = warp * spw; sec0 < L; sec0 += (kThreads / 32) * spw) {
+            const int sec = sec0 + lane / M, j = lane % M;
+            const bool live = sec < L;
+            const size_t a = frame_base + (size_t)sec * M + j;
             T v = (T)0;
             if (live) {
-                v = atz[base + j];
-                if (add_beta) v += beta_in[base + j];
-                if (s_out) s_out[base + j] = v;
+                v = atz[a] + (add_beta ? beta_in[a] : (T)0);
+                if (s_out) s_out[a] = v;
             }
-            sv[k] = v;
-            mx = fmax(mx, v);
-        }
-        const int width = M >= 32 ? 32 : M;
-        for (int o = width >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        T sum = (T)0;
-        for (int k = 0; k < per_lane; ++k) {
-            sv[k] = exp((sv[k] - mx) * scale);
-            sum += sv[k];
-        }
-        for (int o = width >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (live) {
-            for (int k = 0; k < per_lane; ++k) {
-                const int j = M >= 32 ? lane + 32 * k : lane % M;
-                const T b = amp * (sv[k] / sum);
-                beta[base + j] = b;
+            T mx = v;
+            for (int o = M >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const T e = exp((v - mx) * scale);
+            T sum = e;
+            for (int o = M >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (live) {
+                const T b = amp * (e / sum);
+                beta[a] = b;
                 part += (double)b * (double)b;
             }
         }
@@ -423,8 +463,13 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
         LSB_REQUIRE(beta_out && atz && tau_sqr && beta_sq, "null pointer");                                      \
         LSB_REQUIRE(M >= 2 && M <= 256 && (M & (M - 1)) == 0, "M must be a power of two in [2, 256]");            \
         if (F <= 0) return LSB_OK;                                                                               \
-        denoise_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out,     \
-                                                                              tau_sqr, beta_sq, L, M, sqrt_nPl); \
+        switch (M >= 32 ? M / 32 : 0) {                                                                          \
+            case 0: denoise_kernel<T, 0><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
+            case 1: denoise_kernel<T, 1><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
+            case 2: denoise_kernel<T, 2><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
+            case 4: denoise_kernel<T, 4><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
+            default: denoise_kernel<T, 8><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
+        }                                                                                                        \
         lsb::count_launch();                                                                                     \
         LSB_CUDA(cudaGetLastError());                                                                            \
         return LSB_OK;                                                                                           \
