@@ -412,13 +412,15 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     Lc = design.Lc
 
     idx0 = None
-    if beta0 is not None:
+    if isinstance(beta0, torch.Tensor) and beta0.is_cuda and tuple(beta0.shape) == (F, L) and M != 1:
+        idx0 = beta0.to(dev, torch.int32).contiguous()        # section indices already on the device
+    elif beta0 is not None:
         b0 = beta0.cpu().numpy() if isinstance(beta0, torch.Tensor) else np.asarray(beta0)
         if b0.shape[-1] == L * M:                       # dense message vector(s), as the reference passes
             b0 = b0.reshape(-1, L, M).argmax(axis=2)
         b0 = np.broadcast_to(b0.reshape(-1, L), (F, L)) if b0.reshape(-1, L).shape[0] in (1, F) else None
         if b0 is not None:
-            idx0 = torch.from_numpy(np.ascontiguousarray(b0, dtype=np.int32)).to(dev)
+            idx0 = torch.from_numpy(np.array(b0, dtype=np.int32)).to(dev)
 
     idx = torch.empty((F, L), dtype=torch.int32, device=dev)
     t_final = torch.empty(F, dtype=torch.int32, device=dev)

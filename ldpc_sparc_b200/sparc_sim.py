@@ -1,0 +1,130 @@
+"""End-to-end SPARC simulations: host mirror of sparc_public/sparc_sim.py plus the
+batched Monte-Carlo form that keeps frame generation, decoding and error counting on
+the GPU.
+
+``sparc_sim`` / ``calc_ber`` / ``calc_ser`` / ``awgn_channel`` keep the reference's names,
+arguments and return values (sparc_sim.py:8-98,179-204).  ``sparc_sim_batch`` runs the same
+experiment for ``n_frames`` frames that share one design: messages are drawn on the device,
+``x = A beta0`` goes through the same DCT operator kernel the decoder uses, noise is added
+on the device, the AMP kernel decodes, and only a handful of int64 counters leave the GPU
+(all-reduced when a process group is up -- frames are sharded by chunk, no other exchange).
+"""
+import numpy as np
+
+from . import montecarlo, sparc
+
+
+# ------------------------------------------------------------------ reference API
+def awgn_channel(input_array, awgn_var, rand_seed):
+    """x + N(0, awgn_var) (sparc_sim.py:179-204; real inputs)."""
+    assert input_array.ndim == 1, 'input array must be one-dimensional'
+    assert awgn_var >= 0
+    rng = np.random.RandomState(rand_seed)
+    n = input_array.size
+    if input_array.dtype == float:
+        return input_array + np.sqrt(awgn_var) * rng.randn(n)
+    if input_array.dtype == complex:
+        raise NotImplementedError("complex SPARCs (sub-sampled FFT design) are not built")
+    raise Exception("Unknown input type '{}'".format(input_array.dtype))
+
+
+def calc_ber(true_bin_array, est_bin_array):
+    """Bit error rate of two bool arrays (sparc_sim.py:62-70)."""
+    assert true_bin_array.dtype == 'bool'
+    assert est_bin_array.dtype == 'bool'
+    k = true_bin_array.size
+    assert k == est_bin_array.size
+    return np.count_nonzero(np.bitwise_xor(true_bin_array, est_bin_array)) / k
+
+
+def calc_ser(beta0, beta, L):
+    """Section error rate, locations and count (sparc_sim.py:72-98)."""
+    assert beta.size == beta0.size, 'beta and beta0 are of different size'
+    assert beta.dtype == beta0.dtype, 'beta and beta0 are of different type'
+    assert type(L) == int and L > 0
+    assert beta.size % L == 0
+    wrong = (beta.reshape(L, -1) != beta0.reshape(L, -1)).any(axis=1)
+    num_of_sec_errs = int(np.count_nonzero(wrong))
+    return num_of_sec_errs / L, np.flatnonzero(wrong), num_of_sec_errs
+
+
+def sparc_sim(code_params, decode_params, awgn_var, rand_seed=None, precision=None):
+    """Encode, transmit and decode one frame (sparc_sim.py:8-58).  Returns the results dict
+    ``ber, cer, t_final, nmse, detect, ser, loc_of_sec_errs, num_of_sec_errs``.
+    ``precision`` ('fp32' default / 'fp64') selects the decoder kernel, as in sparc_decode."""
+    bits_i, beta0, x, Ab, Az = sparc.sparc_encode(code_params, awgn_var, rand_seed)
+    y = awgn_channel(x, awgn_var, rand_seed)
+    bits_o, beta, T, nmse, expect = sparc.sparc_decode(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab, Az,
+                                                       precision=precision)
+    ber = calc_ber(bits_i, bits_o)
+    results = {'ber': ber, 'cer': 1.0 * (ber > 0), 't_final': T, 'nmse': nmse,
+               'detect': 1.0 * (not (ber > 0) ^ bool(expect))}
+    ser, loc_of_sec_errs, num_of_sec_errs = calc_ser(beta0, beta, code_params['L'])
+    results.update({'ser': ser, 'loc_of_sec_errs': loc_of_sec_errs, 'num_of_sec_errs': num_of_sec_errs})
+    return results
+
+
+# ------------------------------------------------------------------ batched Monte-Carlo
+BATCH_FIELDS = ("bit_errors", "frame_errors", "section_errors", "frames", "iterations", "detected")
+
+
+def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1, 2), seed=0, chunk=2048,
+                    precision="fp32", device=None):
+    """``n_frames`` independent frames over one design drawn from ``rand_seed``.
+
+    Every rank handles its share of the ``chunk``-frame blocks (montecarlo.shard_chunks);
+    the message and noise streams of a block are seeded by (seed, block index), so the totals
+    do not depend on the number of ranks.  Returns a dict with the rates ``ber, cer, ser,
+    detect``, the mean ``t_final`` and the raw int64 counters (BATCH_FIELDS)."""
+    import torch
+    sparc.check_decode_params(decode_params)
+    code_params = dict(code_params)
+    sparc.check_code_params(code_params)
+    sparc._require_real_unmodulated(code_params)
+    R, L, M = map(code_params.get, ['R', 'L', 'M'])
+    logM = int(round(np.log2(M)))
+    bit_len = L * logM
+    tmp = code_params.copy()
+    tmp.update({'awgn_var': awgn_var})
+    W = sparc.create_base_matrix(**tmp)
+    n = int(round(bit_len / R))                                    # sparc.py:37-45
+    if W.ndim == 2:
+        n = int(round(n / W.shape[0])) * W.shape[0]
+    code_params.update({'n': n, 'R_actual': bit_len / n})
+    Ab, Az = sparc.sparc_transforms(W, L, M, n, list(rand_seed), code_params['complex'])
+
+    rank, world = montecarlo._rank_world()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    dt = torch.float64 if precision == "fp64" else torch.float32
+    counters = torch.zeros(len(BATCH_FIELDS), dtype=torch.int64, device=device)
+    ranges = montecarlo.chunk_ranges(n_frames, chunk)
+    shifts = torch.arange(logM, device=device, dtype=torch.int32)
+    for c in montecarlo.shard_chunks(len(ranges), rank, world):
+        _, nf = ranges[c]
+        gen = torch.Generator(device=device).manual_seed(montecarlo.chunk_seed(seed, 0, c))
+        idx0 = torch.randint(0, M, (nf, L), device=device, generator=gen, dtype=torch.int32)
+        beta0 = torch.zeros((nf, L * M), dtype=dt, device=device)
+        beta0.view(nf, L, M).scatter_(2, idx0.long().unsqueeze(-1), 1.0)
+        x = Ab(beta0, precision)
+        del beta0
+        y = x + float(np.sqrt(awgn_var)) * torch.randn((nf, n), device=device, generator=gen, dtype=dt)
+        _, idx, t_final, _, expect = sparc.sparc_decode(y, code_params, decode_params, awgn_var, list(rand_seed),
+                                                        idx0, Ab, Az, precision=precision)
+        diff = idx ^ idx0
+        bit_err = ((diff.unsqueeze(-1) >> shifts) & 1).sum(dim=(1, 2))
+        frame_err = bit_err > 0
+        counters[0] += bit_err.sum()
+        counters[1] += frame_err.sum()
+        counters[2] += (diff != 0).sum()
+        counters[3] += nf
+        counters[4] += t_final.long().sum()
+        counters[5] += (frame_err == expect).sum()                  # detect = not (err xor expect)
+    montecarlo.all_reduce_counters(counters)
+    cnt = {k: int(v) for k, v in zip(BATCH_FIELDS, counters.cpu().numpy())}
+    frames = max(cnt["frames"], 1)
+    out = {'ber': cnt["bit_errors"] / (frames * bit_len), 'cer': cnt["frame_errors"] / frames,
+           'ser': cnt["section_errors"] / (frames * L), 't_final': cnt["iterations"] / frames,
+           'detect': cnt["detected"] / frames, 'n': n, 'R_actual': bit_len / n}
+    out.update(cnt)
+    return out

@@ -1,0 +1,105 @@
+"""Simulation drivers on the GPU: the single-frame mirrors reproduce the reference's own
+end-to-end runs (golden vectors made by oracle/make_golden_sparc.py from the unmodified
+reference), the batched Monte-Carlo forms are deterministic, count what they should and
+land on the error rates of the per-frame path."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(os.path.join(GOLDEN, "sparc_reference.npz"))
+    return g, json.loads(str(g["meta_json"]))
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", ["reg", "sc_pa_m16", "reg_m64"])
+def test_sparc_sim_reproduces_reference_run(gold, name, precision):
+    from ldpc_sparc_b200 import sparc_sim
+    g, meta = gold
+    m = meta[name]
+    for si, seed in enumerate(m["seeds"]):
+        pre = "%s_s%d_" % (name, si)
+        res = sparc_sim.sparc_sim(dict(m["code_params"]), dict(m["decode_params"]), m["awgn_var"], seed,
+                                  precision=precision)
+        bits_in, bits_out = g[pre + "bits_in"], g[pre + "bits_out"]
+        assert res['ber'] == np.count_nonzero(bits_in ^ bits_out) / bits_in.size        # bit-exact decisions
+        assert res['t_final'] == int(g[pre + "t_final"])
+        logM = int(np.log2(m["code_params"]["M"]))
+        truth = bits_in.reshape(-1, logM).astype(int).dot(1 << np.arange(logM)[::-1])
+        assert res['num_of_sec_errs'] == int((truth != g[pre + "idx"]).sum())
+        assert res['cer'] == float(res['ber'] > 0)
+        assert res['detect'] == float(not ((res['ber'] > 0) ^ bool(g[pre + "expect_err"])))
+        if precision == "fp64":
+            assert np.allclose(res["nmse"], g[pre + "nmse"], rtol=1e-5, atol=1e-7)     # nmse out is fp32
+        else:                                                                          # fp32 state: 1e-4 relative
+            assert np.allclose(res["nmse"], g[pre + "nmse"], rtol=1e-4, atol=1e-6)
+
+
+def test_sparc_sim_batch_counts_and_determinism():
+    from ldpc_sparc_b200 import sparc_sim
+    cp = dict(P=15.0, R=1.3, L=256, M=32)
+    dp = dict(t_max=25)
+    a = sparc_sim.sparc_sim_batch(cp, dp, 1.0, 640, rand_seed=(1, 2), seed=3, chunk=256)
+    b = sparc_sim.sparc_sim_batch(cp, dp, 1.0, 640, rand_seed=(1, 2), seed=3, chunk=256)
+    assert a == b                                             # same seeds -> same counters
+    assert a['frames'] == 640 and a['n'] == int(round(256 * 5 / 1.3))
+    assert a['section_errors'] <= a['bit_errors'] <= 5 * a['section_errors']
+    assert a['frame_errors'] <= a['section_errors']
+    assert 3 <= a['t_final'] <= 24
+    # this operating point decodes essentially error-free in the reference (golden 'reg': no errors)
+    assert a['ser'] < 2e-3 and a['detect'] > 0.95
+    # low SNR: errors appear and the fp64 kernel agrees with the fp32 one on the error rate
+    lo32 = sparc_sim.sparc_sim_batch(cp, dp, 2.2, 256, seed=1, chunk=256)
+    lo64 = sparc_sim.sparc_sim_batch(cp, dp, 2.2, 256, seed=1, chunk=256, precision="fp64")
+    assert lo64['ser'] > 0.01
+    assert abs(lo32['ser'] - lo64['ser']) <= 0.02 * lo64['ser'] + 1e-4
+
+
+def _config5_small():
+    from ldpc_sparc_b200.param_calc import param_calc
+    mults, logM, standard, rate, int_rate, z = 1, 1, '802.16', '1/2', 1 / 2, 150
+    overall, L_sparc, L_sl, lengths = param_calc(mults, logM, standard, rate, int_rate, z, 1)
+    sp = {'P': 19.44, 'R': overall, 'L': L_sparc, 'M': 2}
+    spl = {'P': 19.44, 'R': 1, 'L': L_sl, 'M': 2}
+    lp = {'standard': standard, 'rate': rate, 'z': z, 'int_rate': int_rate, 'mults': mults}
+    return sp, spl, lp, lengths
+
+
+def test_single_frame_sims_run():
+    from ldpc_sparc_b200 import sparc_sim_new
+    sp, spl, lp, lengths = _config5_small()
+    dp = {'t_max': 25}
+    for fn, params, ldpc_bool in ((sparc_sim_new.sparc_ldpc_sim, sp, False), (sparc_sim_new.sparc_ldpc_sim, spl, True),
+                                  (sparc_sim_new.sparc_ldpc_naive_sim, spl, True),
+                                  (sparc_sim_new.sparc_ldpc_integrated_sim, spl, True)):
+        bits_i, bits_o, ber = fn(params, lp, lengths, ldpc_bool, dp, 19.44 / 6.0, [11, 12])
+        assert bits_i.shape == bits_o.shape == (1800,)
+        assert ber == np.count_nonzero(np.asarray(bits_i) != np.asarray(bits_o)) / 1800
+        assert ber < 0.02
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp64"])
+def test_performance_sweep_small(tmp_path, precision):
+    from ldpc_sparc_b200 import sparc_sim_new
+    sp, spl, lp, lengths = _config5_small()
+    path = str(tmp_path / "Test_0.npz")
+    out = sparc_sim_new.performance_sweep(sp, spl, lp, lengths, {'t_max': 25}, [2.0, 6.0], 48, chunk=32, seed=5,
+                                          precision=precision, save_path=path)
+    avg = out['ber_store_averages']
+    assert avg.shape == (4, 2) and np.all(avg >= 0) and np.all(avg < 0.5)
+    assert np.all(out['bits'] == 48 * 1800)
+    assert np.all(out['ber_store_min'] <= avg + 1e-12) and np.all(avg <= out['ber_store_max'] + 1e-12)
+    assert avg[0, 0] > 1e-3                       # uncoded-rate SPARC at snr = 2 makes errors
+    assert np.all(avg[:, 1] <= avg[:, 0] + 1e-12)  # every scheme improves with SNR
+    assert np.all(avg[1:, 1] == 0)                # LDPC-protected schemes are clean at snr = 6
+    saved = np.load(path)
+    assert set(saved.files) == {'ber_store_averages', 'ber_store_max', 'ber_store_min', 'snr_store'}
+    assert np.array_equal(saved['ber_store_averages'], avg)
