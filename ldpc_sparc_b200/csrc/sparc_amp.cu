@@ -4,11 +4,11 @@
 // :703-880, msg_vector_mmse_estimator :402-465 (K = 1), msg_vector_map_estimator
 // :467-512 (K = 1).  One CTA decodes one frame at a time out of a device-side
 // frame queue (frames stop early, at different iterations).  Per frame the
-// residual z and the A*beta accumulator live in shared memory next to the FFT
-// buffer; beta / s stream through a per-CTA global scratch (L2 resident).  Per
-// AMP iteration (t >= 1 for the first half):
-//   acc_r = sum_c A_rc beta_c            (one DCT-II per non-zero block)
-//   z     = y - acc + (gamma_r / phi_prev_r) z
+// residual z lives in shared memory next to the FFT buffer; beta / s stream
+// through a per-CTA global scratch (L2 resident).  Per AMP iteration (t >= 1
+// for the first half):
+//   z_r   = y_r + (gamma_r / phi_prev_r) z_r - sum_c A_rc beta_c
+//           (one DCT-II per non-zero block, subtracted from z in place)
 //   phi_r = awgn_var + gamma_r   |   mean(z_r^2)                    (phi_est_method)
 //   tau_c = (L phi / n) / W_c    |   (L / Mr) / sum_r W_rc / phi_r
 //   s_c   = beta_c + tau_c sum_r A_rc^T (z_r / phi_r)   (one DCT-III per block)
@@ -26,6 +26,11 @@
 #include <vector>
 
 using namespace lsb_sparc;
+
+// resident CTAs per SM the fp32 AMP kernel's register budget is tuned for
+#ifndef LSB_AMP_OCC
+#define LSB_AMP_OCC 5
+#endif
 
 namespace {
 
@@ -112,7 +117,7 @@ __device__ __forceinline__ void scatter_scaled(T *bf, const uint16_t *__restrict
 }
 
 // ---- A_rc x : scatter a column block into the FFT buffer, DCT-II, leave Y in buf
-template <typename T>
+template <typename T, int LOGH = 0>
 __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
                               const T *x /* Mc entries of the column block, or null */, int one_hot_pos,
                               int Mc, int H, int tid)
@@ -124,12 +129,13 @@ __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &t
         scatter_scaled<T>(bf, b.ab_scatter, x, (T)1, Mc, tid);
     }
     __syncthreads();
-    fft_inplace<T, false>(buf, tb, tid, kThreads);
+    if constexpr (LOGH > 0) fft_fixed<T, LOGH, false, kThreads>(buf, tb, tid);
+    else fft_inplace<T, false>(buf, tb, tid, kThreads);
     dct2_post<T>(buf, tb, tid, kThreads);
 }
 
 // ---- A_rc^T y : scatter a row block into the FFT buffer, DCT-III, leave X in buf
-template <typename T>
+template <typename T, int LOGH = 0>
 __device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
                                 const T *y /* Mr entries of the row block */, T yscale, int Mr, int H, int tid)
 {
@@ -139,7 +145,8 @@ __device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> 
     scatter_scaled<T>(bf, b.az_scatter, y, yscale, Mr, tid);
     __syncthreads();
     dct3_pre<T>(buf, tb, tid, kThreads);
-    fft_inplace<T, true>(buf, tb, tid, kThreads);
+    if constexpr (LOGH > 0) fft_fixed<T, LOGH, true, kThreads>(buf, tb, tid);
+    else fft_inplace<T, true>(buf, tb, tid, kThreads);
 }
 
 template <typename T> struct Scale;
@@ -208,8 +215,9 @@ az_kernel(DesignDev d, FftTables<T> tb, const T *__restrict__ y, T *__restrict__
 }
 
 // ------------------------------------------------------------------ AMP kernel
-template <typename T, bool GBUF>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
+// LOGH > 0: log2 of the FFT size fixed at compile time (fft_fixed), 0: any size.
+template <typename T, bool GBUF, int LOGH = 0>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? LSB_AMP_OCC : 2)
 amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_all,
            const int32_t *__restrict__ idx0, AmpOut o, T *__restrict__ scratch, long long n_frames,
            unsigned long long *__restrict__ queue)
@@ -222,7 +230,6 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     T *cta_scratch = scratch + (size_t)blockIdx.x * (2 * (size_t)LM + (GBUF ? (size_t)d.w : 0));
     T2 *buf = GBUF ? reinterpret_cast<T2 *>(cta_scratch + 2 * (size_t)LM) : reinterpret_cast<T2 *>(smem);
     T *z = GBUF ? reinterpret_cast<T *>(smem) : reinterpret_cast<T *>(buf + H);     // [n]
-    T *acc = z + d.n;                          // [n]
     __shared__ double psi[kMaxLc], psi_prev[kMaxLc], tau[kMaxLc], nm[kMaxLc];
     __shared__ double phi[kMaxLr], phi_prev[kMaxLr], gam[kMaxLr], zsq[kMaxLr];
     __shared__ long long s_frame;
@@ -259,21 +266,20 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
             if (tid < d.Lc) psi_prev[tid] = psi[tid];
             __syncthreads();
             if (t > 0) {
-                for (int i = tid; i < d.n; i += kThreads) acc[i] = (T)0;
-                for (int bi = 0; bi < d.n_blocks; ++bi) {
-                    const BlockDev b = d.blocks[bi];
-                    block_forward<T>(buf, tb, b, beta + (size_t)b.c * d.Mc, -1, d.Mc, H, tid);
-                    const T *bf = reinterpret_cast<const T *>(buf);
-                    const T sc = Scale<T>::get(b);
-                    gather_add<T>(acc + b.r * d.Mr, bf, b.ab_gather, sc, d.Mr, tid);
-                    __syncthreads();
-                }
-                for (int i = tid; i < d.n; i += kThreads) {                 // z = y - A beta + b z  (:944-946)
+                // z = y - A beta + b z (:944-946), accumulated in place: z <- y + b z, then every
+                // non-zero block subtracts its A_rc beta_c (no separate A*beta vector)
+                for (int i = tid; i < d.n; i += kThreads) {
                     const int r = i / d.Mr;
                     const T coef = (T)(gam[r] / phi_prev[r]);
-                    z[i] = (y[i] - acc[i]) + coef * z[i];
+                    z[i] = y[i] + coef * z[i];
                 }
-                __syncthreads();
+                for (int bi = 0; bi < d.n_blocks; ++bi) {
+                    const BlockDev b = d.blocks[bi];
+                    block_forward<T, LOGH>(buf, tb, b, beta + (size_t)b.c * d.Mc, -1, d.Mc, H, tid);
+                    const T *bf = reinterpret_cast<const T *>(buf);
+                    gather_add<T>(z + b.r * d.Mr, bf, b.ab_gather, -Scale<T>::get(b), d.Mr, tid);
+                    __syncthreads();
+                }
             }
             // ---- phi (:949-955)
             if (p.phi_method == 2) {
@@ -311,7 +317,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                 const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
                 for (int bi = b0; bi < b1; ++bi) {
                     const BlockDev b = d.blocks[bi];
-                    block_transpose<T>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid);
+                    block_transpose<T, LOGH>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid);
                     const T *bf = reinterpret_cast<const T *>(buf);
                     const T sc = Scale<T>::get(b) * tau_c;
                     {
@@ -517,7 +523,7 @@ int check_device(const lsb_sparc_design *g)
 }
 
 // shared memory per CTA; gbuf = FFT buffer kept in global memory instead
-size_t amp_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + 2 * (size_t)d.n) * elem; }
+size_t amp_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + (size_t)d.n) * elem; }
 size_t ab_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + (size_t)d.n) * elem; }
 size_t az_smem(const DesignDev &d, size_t elem, bool gbuf) { return (gbuf ? 16 : (size_t)d.w * elem); }
 bool needs_gbuf(const DesignDev &d, size_t elem) { return amp_smem(d, elem, false) + 8192 > (size_t)lsb::max_smem_optin(); }
@@ -584,6 +590,28 @@ int run_op(const lsb_sparc_design *cg, bool transpose, const T *in, T *out, int6
 }
 
 template <typename T>
+using AmpKernelFn = void (*)(DesignDev, FftTables<T>, AmpParams, const T *, const int32_t *, AmpOut, T *, long long,
+                             unsigned long long *);
+
+// fp32 (the throughput mode) gets the compile-time-size transforms for the sizes the
+// BASELINE configs and the golden cases use (w = 2048, 4096, 8192); anything else, and
+// the fp64 parity mode, runs the size-generic passes.
+template <typename T>
+AmpKernelFn<T> pick_amp_kernel(bool gbuf, int h)
+{
+    if (gbuf) return amp_kernel<T, true, 0>;
+    if constexpr (sizeof(T) == 4) {
+        switch (h) {
+            case 10: return amp_kernel<T, false, 10>;
+            case 11: return amp_kernel<T, false, 11>;
+            case 12: return amp_kernel<T, false, 12>;
+            default: break;
+        }
+    }
+    return amp_kernel<T, false, 0>;
+}
+
+template <typename T>
 int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_amp_params *pp,
             const int32_t *idx0, const lsb_sparc_amp_out *po, cudaStream_t st)
 {
@@ -599,16 +627,12 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     const size_t smem = amp_smem(g->dev, sizeof(T), gbuf);
     LSB_REQUIRE(smem + 8192 <= (size_t)lsb::max_smem_optin(),
                 "design needs %zu B of shared memory per CTA (n = %d): unsupported", smem, g->dev.n);
+    const AmpKernelFn<T> kernel = pick_amp_kernel<T>(gbuf, g->dev.h);
     int &cached = g->amp_grid[sizeof(T) == 8];
     if (cached == 0) {
         int per_sm = 0;
-        if (gbuf) {
-            LSB_CUDA(cudaFuncSetAttribute(amp_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amp_kernel<T, true>, kThreads, smem));
-        } else {
-            LSB_CUDA(cudaFuncSetAttribute(amp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amp_kernel<T, false>, kThreads, smem));
-        }
+        LSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
         if (per_sm < 1) per_sm = 1;
         cached = per_sm * lsb::sm_count();
     }
@@ -620,12 +644,8 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
     AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method};
     AmpOut o{po->idx, po->t_final, po->psi, po->nmse, po->beta_soft, po->s_last, po->tau_trace, po->psi_trace};
-    if (gbuf)
-        amp_kernel<T, true><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o,
-                                                                   (T *)g->d_scratch, (long long)n_frames, queue);
-    else
-        amp_kernel<T, false><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o,
-                                                                    (T *)g->d_scratch, (long long)n_frames, queue);
+    kernel<<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o, (T *)g->d_scratch,
+                                                   (long long)n_frames, queue);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     LSB_CUDA(cudaEventRecord(g->scratch_event, st));

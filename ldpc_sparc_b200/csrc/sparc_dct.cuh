@@ -144,6 +144,117 @@ __device__ void fft_inplace(typename Cplx<T>::type *buf, const FftTables<T> &tb,
     for (int i = 0; i < n2; ++i) { fft_pass<T, 1, INV>(buf, tb.tw, H, logS, tid, nthreads); logS -= 1; __syncthreads(); }
 }
 
+// ---------------------------------------------------------------- fixed-size FFT
+// Same passes with the transform size known at compile time (the AMP kernel is bound by
+// issue slots, ncu: 77 % issue-active, 43 % of its instructions integer): all strides,
+// loop counts and twiddle steps become immediates, and because swz() is linear over GF(2)
+// (shifts, masks and XORs only) the slot of element base + m*stride is
+// swz(base) ^ swz(m*stride) with the second term a constant.  The radix-8 butterfly is a
+// trivial-twiddle DFT-8 followed by one multiply per output (w^k, k = 1..7, from three
+// table entries), the last pass (stride 1) has no twiddles at all.  Bit-reversed output,
+// identical to fft_inplace.
+__host__ __device__ constexpr int swz_c(int i) { return i ^ ((i >> 4) & 3) ^ (((i >> 5) & 3) << 2); }
+__host__ __device__ constexpr int brev3_c(int m) { return ((m & 1) << 2) | (m & 2) | ((m >> 2) & 1); }
+
+template <bool INV, typename T2> __device__ __forceinline__ T2 mul_w8(T2 a)   // a * exp(-+ i pi/4)
+{
+    typedef decltype(a.x) T;
+    const T kR = (T)0.70710678118654752440;
+    return INV ? T2{(a.x - a.y) * kR, (a.x + a.y) * kR} : T2{(a.x + a.y) * kR, (a.y - a.x) * kR};
+}
+
+template <typename T, int LOGH, int LOGS, int LOGR, bool INV, int NT>
+__device__ __forceinline__ void fft_pass_fixed(typename Cplx<T>::type *buf, const typename Cplx<T>::type *tw, int tid)
+{
+    typedef typename Cplx<T>::type T2;
+    constexpr int H = 1 << LOGH, R = 1 << LOGR, LOGQ = LOGS - LOGR, STRIDE = 1 << LOGQ;
+    constexpr int NB = H >> LOGR;                 // butterflies in this pass
+    constexpr int TW_STEP = H >> LOGS;
+#pragma unroll
+    for (int q0 = 0; q0 < NB; q0 += NT) {
+        const int q = q0 + tid;
+        if (NB % NT != 0 && q >= NB) break;
+        const int j = q & (STRIDE - 1);
+        const int sb = swz(((q >> LOGQ) << LOGS) | j);
+        T2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = buf[sb ^ swz_c(m << LOGQ)];
+        if (LOGR == 1) {
+            bfly1(v[0], v[1]);
+        } else if (LOGR == 2) {
+            bfly1(v[0], v[2]);
+            bfly1(v[1], v[3]);
+            v[3] = mul_mi<INV>(v[3]);
+            bfly1(v[0], v[1]);
+            bfly1(v[2], v[3]);
+        } else {
+            bfly1(v[0], v[4]);
+            bfly1(v[1], v[5]);
+            bfly1(v[2], v[6]);
+            bfly1(v[3], v[7]);
+            v[5] = mul_w8<INV>(v[5]);
+            v[6] = mul_mi<INV>(v[6]);
+            v[7] = mul_mi<INV>(mul_w8<INV>(v[7]));
+            bfly1(v[0], v[2]);
+            bfly1(v[1], v[3]);
+            bfly1(v[4], v[6]);
+            bfly1(v[5], v[7]);
+            v[3] = mul_mi<INV>(v[3]);
+            v[7] = mul_mi<INV>(v[7]);
+            bfly1(v[0], v[1]);
+            bfly1(v[2], v[3]);
+            bfly1(v[4], v[5]);
+            bfly1(v[6], v[7]);
+        }
+        if (LOGQ > 0) {     // output m holds frequency k = brev(m) of the radix-R DFT: times w_S^(j k)
+            const T2 w1 = twiddle<INV>(tw, j * TW_STEP);
+            if (LOGR == 1) {
+                v[1] = cmul(v[1], w1);
+            } else if (LOGR == 2) {
+                const T2 w2 = twiddle<INV>(tw, 2 * j * TW_STEP);
+                v[1] = cmul(v[1], w2);
+                v[2] = cmul(v[2], w1);
+                v[3] = cmul(v[3], cmul(w1, w2));
+            } else {
+                const T2 w2 = twiddle<INV>(tw, 2 * j * TW_STEP);
+                const T2 w4 = twiddle<INV>(tw, 4 * j * TW_STEP);
+                const T2 w3 = cmul(w1, w2);
+                v[1] = cmul(v[1], w4);
+                v[2] = cmul(v[2], w2);
+                v[3] = cmul(v[3], cmul(w2, w4));
+                v[4] = cmul(v[4], w1);
+                v[5] = cmul(v[5], cmul(w1, w4));
+                v[6] = cmul(v[6], w3);
+                v[7] = cmul(v[7], cmul(w3, w4));
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) buf[sb ^ swz_c(m << LOGQ)] = v[m];
+    }
+}
+
+// radix of the pass that starts at sub-transform size 2^LOGS: 8 unless that would leave a
+// single radix-2 pass (then two radix-4 passes close the plan), as in fft_inplace
+__host__ __device__ constexpr int pass_logr(int logs) { return (logs >= 3 && logs - 3 != 1) ? 3 : (logs >= 2 ? 2 : 1); }
+
+template <typename T, int LOGH, int LOGS, bool INV, int NT>
+__device__ __forceinline__ void fft_fixed_from(typename Cplx<T>::type *buf, const typename Cplx<T>::type *tw, int tid)
+{
+    if constexpr (LOGS > 0) {
+        constexpr int LOGR = pass_logr(LOGS);
+        fft_pass_fixed<T, LOGH, LOGS, LOGR, INV, NT>(buf, tw, tid);
+        __syncthreads();
+        fft_fixed_from<T, LOGH, LOGS - LOGR, INV, NT>(buf, tw, tid);
+    }
+}
+
+// Complete in-place FFT of 2^LOGH points, NT threads.  Ends with __syncthreads().
+template <typename T, int LOGH, bool INV, int NT>
+__device__ __forceinline__ void fft_fixed(typename Cplx<T>::type *buf, const FftTables<T> &tb, int tid)
+{
+    fft_fixed_from<T, LOGH, LOGH, INV, NT>(buf, tb.tw, tid);
+}
+
 __device__ __forceinline__ int bitrev(int k, int h) { return (int)(__brev((unsigned)k) >> (32 - h)); }
 
 // After the forward FFT of the packed sequence: slot brev(k) <- (Y[k], Y[N-k]),
