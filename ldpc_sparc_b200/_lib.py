@@ -78,6 +78,9 @@ SIGNATURES = {
     "lsb_tc_design_destroy": (None, [ct.c_void_p]),
     "lsb_tc_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_tc_az_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    # state evolution
+    "lsb_sparc_se_expect_f64": (ct.c_int, [ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, c_f64p, ct.c_int, c_f64p, ct.c_void_p]),
+    "lsb_sparc_se_expect_f32": (ct.c_int, [ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, c_f64p, ct.c_int, c_f64p, ct.c_void_p]),
 }
 _VP = ct.c_void_p
 for _suf in ("f32", "f64"):
