@@ -180,12 +180,16 @@ typedef struct lsb_sparc_amp_params {
     double atol;           /* absolute tolerance; the reference uses 2e-15 (:916)   */
     int32_t t_max;         /* the loop runs at most t_max - 1 iterations (:931)     */
     int32_t phi_est_method;/* 1: awgn_var + gamma, 2: mean(z^2)  (:949-955)         */
+    int32_t modulation;    /* K of the reference: 0 or 1 = unmodulated, 2 = real    *
+                            * 2-PSK values +1 / -1 (:433-441, 488-492)              */
+    int32_t reserved;      /* must be 0                                             */
 } lsb_sparc_amp_params;
 
 /* Outputs of one batched AMP decode (device pointers; optional ones may be NULL).
  * beta_soft / s_last have the element type of the entry point. */
 typedef struct lsb_sparc_amp_out {
-    int32_t *idx;      /* [F, L]          MAP decision: argmax of s per section (:997) */
+    int32_t *idx;      /* [F, L]          MAP decision: argmax of s per section (:997);   *
+                        *                  modulation 2: argmax|s| + M if that s < 0   */
     int32_t *t_final;  /* [F]             iterations run, as the reference returns it  */
     double *psi;       /* [F, Lc]         final psi                                    */
     float *nmse;       /* [F, t_max, Lc]  NMSE per iteration; needs idx0   (optional)  */
@@ -196,7 +200,8 @@ typedef struct lsb_sparc_amp_out {
 } lsb_sparc_amp_out;
 
 /* y [F, n] received words; idx0 [F, L] true section indices (NULL unless nmse is
- * wanted -- the reference takes beta0 for the same purpose, sparc.py:889). */
+ * wanted -- the reference takes beta0 for the same purpose, sparc.py:889), coded like
+ * out->idx (location + M for a -1 value when modulation = 2). */
 int lsb_sparc_amp_dev_f32(lsb_sparc_design *g, const float *y, int64_t n_frames,
                           const lsb_sparc_amp_params *p, const int32_t *idx0,
                           const lsb_sparc_amp_out *out, void *stream);

@@ -25,7 +25,8 @@ class LibraryError(RuntimeError):
 
 class AmpParams(ct.Structure):      # lsb_sparc_amp_params
     _fields_ = [("awgn_var", ct.c_double), ("rtol", ct.c_double), ("atol", ct.c_double),
-                ("t_max", ct.c_int32), ("phi_est_method", ct.c_int32)]
+                ("t_max", ct.c_int32), ("phi_est_method", ct.c_int32), ("modulation", ct.c_int32),
+                ("reserved", ct.c_int32)]
 
 
 class AmpOut(ct.Structure):         # lsb_sparc_amp_out

@@ -48,6 +48,7 @@ struct DesignDev {
 struct AmpParams {
     double awgn_var, rtol, atol;
     int t_max, phi_method;
+    int K;   // 1: unmodulated, 2: real 2-PSK values
 };
 
 struct AmpOut {
@@ -345,7 +346,40 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                 const T inv_tau = (T)1 / tau_c;
                 if (d.M >= 32) {
                     const int per_lane = d.M >> 5;
-                    for (int sec = warp; sec < secs_per_col; sec += kThreads / 32) {
+                    for (int sec = warp; p.K == 2 && sec < secs_per_col; sec += kThreads / 32) {
+                        // real 2-PSK (:433-441): beta = (e^x - e^-x) / sum_section (e^x + e^-x), x = s / tau,
+                        // every exponent shifted by the section's max |x|
+                        T *ss = s_c + (size_t)sec * d.M;
+                        T mx = (T)0;
+                        for (int k = 0; k < per_lane; ++k) mx = fmax(mx, fabs(ss[lane + 32 * k]));
+                        mx = warp_max(mx);
+                        T sum = (T)0;
+                        for (int k = 0; k < per_lane; ++k) {
+                            const T v = ss[lane + 32 * k];
+                            sum += exp((v - mx) * inv_tau) + exp((-v - mx) * inv_tau);
+                        }
+                        sum = warp_sum(sum);
+                        const T inv = (T)1 / sum;
+                        const int truth = idx0 ? idx0[f * d.L + c * secs_per_col + sec] : -1;
+                        const int t_loc = truth >= 0 ? (truth & (d.M - 1)) : -1;
+                        const double t_val = truth >= d.M ? -1.0 : 1.0;
+                        double q = 0.0, e2 = 0.0;
+                        for (int k = 0; k < per_lane; ++k) {
+                            const int j = lane + 32 * k;
+                            const T v = ss[j];
+                            const T ep = exp((v - mx) * inv_tau), em = exp((-v - mx) * inv_tau);
+                            const T bta = (ep - em) * inv;
+                            beta[(size_t)c * d.Mc + (size_t)sec * d.M + j] = bta;
+                            // 1 - sum beta^2 = sum p (1 - p) + 4 e+ e- / bot^2,  p = (e+ + e-) / bot: no cancellation
+                            const T pj = (ep + em) * inv;
+                            q += (double)pj * (double)((sum - (ep + em)) * inv) + 4.0 * (double)(ep * inv) * (double)(em * inv);
+                            const double dlt = (double)bta - (j == t_loc ? t_val : 0.0);
+                            e2 += dlt * dlt;
+                        }
+                        psi_part += q;
+                        nm_part += e2;
+                    }
+                    for (int sec = warp; p.K != 2 && sec < secs_per_col; sec += kThreads / 32) {
                         T *ss = s_c + (size_t)sec * d.M;
                         T mx = -INFINITY;
                         for (int k = 0; k < per_lane; ++k) mx = fmax(mx, ss[lane + 32 * k]);
@@ -377,12 +411,23 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                         const int sec = sec0 + sub;
                         const bool live = sec < secs_per_col;
                         const T v = live ? s_c[(size_t)sec * d.M + k] : (T)0;
-                        T mx = v;
+                        T mx = p.K == 2 ? fabs(v) : v;
                         for (int off = d.M >> 1; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
                         const T e = exp((v - mx) * inv_tau);
-                        T sum = e;
+                        const T em = p.K == 2 ? exp((-v - mx) * inv_tau) : (T)0;
+                        T sum = e + em;
                         for (int off = d.M >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                        if (live) {
+                        if (live && p.K == 2) {
+                            const T inv = (T)1 / sum;
+                            const T bta = (e - em) * inv;
+                            beta[(size_t)c * d.Mc + (size_t)sec * d.M + k] = bta;
+                            const T pj = (e + em) * inv;
+                            psi_part += (double)pj * (double)((sum - (e + em)) * inv) + 4.0 * (double)(e * inv) * (double)(em * inv);
+                            const int truth = idx0 ? idx0[f * d.L + c * secs_per_col + sec] : -1;
+                            const double tv = truth < 0 || k != (truth & (d.M - 1)) ? 0.0 : (truth >= d.M ? -1.0 : 1.0);
+                            const double dlt = (double)bta - tv;
+                            nm_part += dlt * dlt;
+                        } else if (live) {
                             const T inv = (T)1 / sum;
                             const T bta = e * inv;
                             beta[(size_t)c * d.Mc + (size_t)sec * d.M + k] = bta;
@@ -429,14 +474,16 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
             T best = -INFINITY;
             int arg = 0x7fffffff;
             for (int j = lane; j < d.M; j += 32) {
-                const T v = ss[j];
-                if (v > best) { best = v; arg = j; }
+                const T sv = ss[j];
+                const T v = p.K == 2 ? fabs(sv) : sv;                        // K = 2: largest magnitude (:488-492)
+                if (v > best) { best = v; arg = j + ((p.K == 2 && sv < (T)0) ? d.M : 0); }
             }
+            const int loc_mask = d.M - 1;                                    // ties go to the lowest location
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const T ob = __shfl_xor_sync(0xffffffffu, best, off);
                 const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
-                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                if (ob > best || (ob == best && (oa & loc_mask) < (arg & loc_mask))) { best = ob; arg = oa; }
             }
             if (lane == 0) o.idx[f * d.L + sec] = arg;
         }
@@ -642,7 +689,8 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     if ((rc = ensure_scratch(g, need, st))) return rc;
     unsigned long long *queue = g->d_queue + (g->next_queue.fetch_add(1) % kCounters);
     LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
-    AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method};
+    LSB_REQUIRE(pp->modulation >= 0 && pp->modulation <= 2, "modulation must be 1 (none) or 2 (real 2-PSK)");
+    AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method, pp->modulation == 2 ? 2 : 1};
     AmpOut o{po->idx, po->t_final, po->psi, po->nmse, po->beta_soft, po->s_last, po->tau_trace, po->psi_trace};
     kernel<<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o, (T *)g->d_scratch,
                                                    (long long)n_frames, queue);

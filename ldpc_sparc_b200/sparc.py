@@ -15,8 +15,11 @@ libldpcsparc_b200.so:
   returns batched outputs (``beta`` is then the ``[F, L]`` array of decided
   section indices instead of F dense one-hot vectors).
 
-Complex / K-PSK modulated SPARCs (sparc.py:203-299,433-459,488-510,593-646) are
-not built: they raise NotImplementedError (there is no CPU fallback).
+Real SPARCs are built, unmodulated and 2-PSK modulated (``modulated=True, K=2``: the
+non-zero entry of a section is +1 or -1, one extra bit per section).  Complex SPARCs
+(sub-sampled FFT design, K = 4 and K > 4 denoisers, sparc.py:442-459,493-510,593-646)
+are not: they raise NotImplementedError (there is no CPU fallback).  In batched
+outputs a decided section is coded as ``location + M * (value < 0)``.
 """
 import ctypes as ct
 from copy import copy
@@ -101,9 +104,63 @@ def check_decode_params(decode_params):
 
 
 def _require_real_unmodulated(code_params):
-    if code_params.get('complex') or code_params.get('modulated'):
+    """Real designs only; modulation, if any, is 2-PSK (the only real one, sparc.py:117)."""
+    if code_params.get('complex') or (code_params.get('modulated') and code_params.get('K') != 2):
         raise NotImplementedError(
-            "complex / K-PSK modulated SPARCs are not built in the B200 path yet (no CPU fallback)")
+            "complex SPARCs (K-PSK with K > 2) are not built in the B200 path yet (no CPU fallback)")
+
+
+def _modulation(code_params):
+    return code_params['K'] if code_params.get('modulated') else 1
+
+
+# ------------------------------------------------------------ PSK helpers (host)
+def bin2gray(num):
+    """Binary -> Gray code (reference sparc.py:206-211)."""
+    return num ^ (num >> 1)
+
+
+def gray2bin(num):
+    """Gray -> binary code (reference sparc.py:214-223)."""
+    for shift in (1, 2, 4, 8, 16, 32):      # prefix XOR by doubling
+        num ^= num >> shift
+    return num
+
+
+def psk_constel(K):
+    """K-PSK constellation symbols (reference sparc.py:225-239)."""
+    assert type(K) == int and K > 1 and is_power_of_2(K)
+    if K == 2:
+        return np.array([1, -1])
+    if K == 4:
+        return np.array([1 + 0j, 0 + 1j, -1 + 0j, 0 - 1j])
+    theta = 2 * np.pi * np.arange(K) / K
+    return np.cos(theta) + 1J * np.sin(theta)
+
+
+def psk_mod(bin_arr, K):
+    """Gray-coded K-PSK modulation of ``L*log2(K)`` bits into L symbols (reference sparc.py:241-269)."""
+    assert type(K) == int and K > 1 and is_power_of_2(K)
+    assert bin_arr.dtype == 'bool'
+    c = psk_constel(K)
+    logK = int(round(np.log2(K)))
+    assert bin_arr.size % logK == 0
+    words = bin_arr.reshape(-1, logK).astype(np.int64).dot(1 << np.arange(logK)[::-1])
+    symbols = c[[gray2bin(int(w)) for w in words]]
+    return symbols[0] if words.size == 1 else symbols
+
+
+def psk_demod(symbols, K):
+    """Inverse of psk_mod (reference sparc.py:271-299)."""
+    assert type(K) == int and K > 1 and is_power_of_2(K)
+    c = psk_constel(K)
+    logK = int(round(np.log2(K)))
+    out = []
+    for sym in np.atleast_1d(symbols):
+        hit = np.flatnonzero(c == sym)
+        assert hit.size == 1, 'not a constellation symbol'
+        out.append(int_2_bin_arr(bin2gray(int(hit[0])), logK))
+    return np.concatenate(out)
 
 
 # ---------------------------------------------------------------- bit helpers
@@ -128,63 +185,86 @@ def int_2_bin_arr(integer, arr_length):
     return np.array([c == '1' for c in np.binary_repr(integer, arr_length)], dtype=bool)
 
 
-def section_indices(bin_arr, M):
-    """Section index (MSB first) of every logM-bit group; ``[..., L*logM] -> [..., L]``."""
+def section_indices(bin_arr, M, K=1):
+    """Section symbol of every bit group: location (logM bits, MSB first) plus, for K = 2,
+    ``M`` when the value bit that follows is set (value -1; 2-PSK Gray coding is the
+    identity).  ``[..., L*(logM+logK)] -> [..., L]``."""
     logM = int(round(np.log2(M)))
+    sec = logM + (1 if K == 2 else 0)
     b = np.asarray(bin_arr).astype(np.int64)
-    assert b.shape[-1] % logM == 0
-    return b.reshape(b.shape[:-1] + (-1, logM)).dot(1 << np.arange(logM)[::-1])
+    assert b.shape[-1] % sec == 0
+    b = b.reshape(b.shape[:-1] + (-1, sec))
+    idx = b[..., :logM].dot(1 << np.arange(logM)[::-1])
+    return idx + M * b[..., logM] if K == 2 else idx
 
 
-def indices_2_bin_arr(idx, M):
-    """Inverse of section_indices; ``[..., L] -> [..., L*logM]`` bool."""
+def indices_2_bin_arr(idx, M, K=1):
+    """Inverse of section_indices; ``[..., L] -> [..., L*(logM+logK)]`` bool."""
     logM = int(round(np.log2(M)))
     idx = np.asarray(idx)
-    bits = (idx[..., None] >> np.arange(logM)[::-1]) & 1
+    bits = ((idx % M)[..., None] >> np.arange(logM)[::-1]) & 1
+    if K == 2:
+        bits = np.concatenate([bits, (idx >= M)[..., None].astype(bits.dtype)], axis=-1)
     return bits.reshape(idx.shape[:-1] + (-1,)).astype(bool)
 
 
+def _real_only(K):
+    if K not in (1, 2):
+        raise NotImplementedError("complex SPARCs (K-PSK with K > 2) are not built")
+
+
 def rnd_msg_vector(L, M, rand_seed, K=1):
-    """Reference sparc.py:303-328 (K = 1)."""
-    if K != 1:
-        raise NotImplementedError("modulated SPARCs are not built")
+    """Reference sparc.py:303-328 (K = 1, 2): locations first, then values, from one stream."""
+    _real_only(K)
     rng = np.random.RandomState(rand_seed)
     assert type(M) == int and M > 0 and is_power_of_2(M)
     msg_vector = np.zeros((L, M))
-    msg_vector[(np.arange(L), rng.randint(0, M, L))] = 1
+    idxs = rng.randint(0, M, L)
+    vals = np.ones(L) if K == 1 else psk_constel(K)[rng.randint(0, K, L)]
+    msg_vector[(np.arange(L), idxs)] = vals
     return msg_vector.ravel()
 
 
 def bin_arr_2_msg_vector(bin_arr, M, K=1):
-    """Reference sparc.py:330-364 (K = 1)."""
-    if K != 1:
-        raise NotImplementedError("modulated SPARCs are not built")
+    """Reference sparc.py:330-364 (K = 1, 2): per section logM location bits, then logK value bits."""
+    _real_only(K)
     assert type(M) == int and M > 0 and is_power_of_2(M)
-    idx = section_indices(bin_arr, M)
+    idx = section_indices(bin_arr, M, K)
+    loc = idx % M
     msg_vector = np.zeros(idx.size * M)
-    msg_vector[np.arange(idx.size) * M + idx] = 1
+    msg_vector[np.arange(idx.size) * M + loc] = np.where(idx >= M, -1.0, 1.0)
     return msg_vector
 
 
 def msg_vector_2_bin_arr(msg_vector, M, K=1):
-    """Reference sparc.py:366-400 (K = 1)."""
-    if K != 1:
-        raise NotImplementedError("modulated SPARCs are not built")
+    """Reference sparc.py:366-400 (K = 1, 2)."""
+    _real_only(K)
     assert type(msg_vector) == np.ndarray
     assert type(M) == int and M > 0 and is_power_of_2(M)
     assert msg_vector.size % M == 0
     L = msg_vector.size // M
-    idxs1, idxs2 = np.nonzero(msg_vector.reshape(L, M))
+    rows = msg_vector.reshape(L, M)
+    idxs1, idxs2 = np.nonzero(rows)
     assert np.array_equal(idxs1, np.arange(L))   # exactly 1 nonzero in each row
-    return indices_2_bin_arr(idxs2, M)
+    if K == 2:
+        vals = rows[idxs1, idxs2]
+        assert np.all(np.abs(vals) == 1), 'not a constellation symbol'
+        idxs2 = idxs2 + M * (vals < 0)
+    return indices_2_bin_arr(idxs2, M, K)
 
 
 def msg_vector_map_estimator(s, M, K=1):
-    """Reference sparc.py:467-512 (K = 1): one-hot of the per-section argmax.
-    (Output formatting on the host; inside ``sparc_amp`` the decision is taken on
-    the GPU.)"""
-    if K != 1:
-        raise NotImplementedError("modulated SPARCs are not built")
+    """Reference sparc.py:467-512 (K = 1: one-hot of the per-section argmax; K = 2: the
+    entry of largest magnitude, set to its sign).  (Output formatting on the host;
+    inside ``sparc_amp`` the decision is taken on the GPU.)"""
+    _real_only(K)
+    if K == 2:
+        s2 = np.asarray(s).real.reshape(-1, M)
+        rows = np.arange(s2.shape[0])
+        idx = np.abs(s2).argmax(axis=1)
+        beta = np.zeros_like(s2, dtype=float)
+        beta[rows, idx] = np.sign(s2[rows, idx])
+        return beta.ravel()
     assert type(s) == np.ndarray
     assert s.size % M == 0
     L = s.size // M
@@ -351,9 +431,10 @@ def sparc_encode(code_params, awgn_var, rand_seed):
     check_code_params(code_params)
     _require_real_unmodulated(code_params)
     R, L, M = map(code_params.get, ['R', 'L', 'M'])
-    bit_len = int(round(L * np.log2(M)))
+    K = _modulation(code_params)
+    bit_len = int(round(L * np.log2(K * M)))
     bits_in = rnd_bin_arr(bit_len, rand_seed)
-    beta0 = bin_arr_2_msg_vector(bits_in, M, 1)
+    beta0 = bin_arr_2_msg_vector(bits_in, M, K)
 
     tmp = code_params.copy()
     tmp.update({'awgn_var': awgn_var})
@@ -382,6 +463,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     import torch
     _require_real_unmodulated(code_params)
     P, R, L, M, n = map(code_params.get, ['P', 'R', 'L', 'M', 'n'])
+    K = _modulation(code_params)
     tmp = code_params.copy()
     tmp.update({'awgn_var': awgn_var})
     W = create_base_matrix(**tmp)
@@ -417,7 +499,10 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     elif beta0 is not None:
         b0 = beta0.cpu().numpy() if isinstance(beta0, torch.Tensor) else np.asarray(beta0)
         if b0.shape[-1] == L * M:                       # dense message vector(s), as the reference passes
-            b0 = b0.reshape(-1, L, M).argmax(axis=2)
+            dense = b0.reshape(-1, L, M)
+            b0 = np.abs(dense).argmax(axis=2)
+            if K == 2:
+                b0 = b0 + M * (np.take_along_axis(dense, b0[..., None], axis=2)[..., 0] < 0)
         b0 = np.broadcast_to(b0.reshape(-1, L), (F, L)) if b0.reshape(-1, L).shape[0] in (1, F) else None
         if b0 is not None:
             idx0 = torch.from_numpy(np.array(b0, dtype=np.int32)).to(dev)
@@ -435,7 +520,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     # (sparc.py:916).  decode_params['atol'] (an extension, not validated by
     # check_decode_params) lets an fp32 run stop at its own noise floor, e.g. 1e-7.
     atol = float(decode_params.get('atol', 2 * np.finfo(float).resolution))
-    params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method))
+    params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method), int(K), 0)
     ptr = lambda t: t.data_ptr() if t is not None else None
     out = _lib.AmpOut(ptr(idx), ptr(t_final), ptr(psi), ptr(nmse), ptr(beta_soft), ptr(s_last), ptr(tau_tr), ptr(psi_tr))
     fn = _lib.lib().lsb_sparc_amp_dev_f64 if precision == "fp64" else _lib.lib().lsb_sparc_amp_dev_f32
@@ -465,7 +550,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     extra = {k: v.cpu().numpy() for k, v in extra.items()}
     if single:
         beta = np.zeros((L, M))
-        beta[np.arange(L), idx_np[0]] = 1
+        beta[np.arange(L), idx_np[0] % M] = np.where(idx_np[0] >= M, -1.0, 1.0)
         psi_out = psi_np[0, 0] if W.ndim == 0 else psi_np[0]
         res = (beta.ravel(), int(t_np[0]), nm[0], psi_out)
         extra = {k: v[0] for k, v in extra.items()}
@@ -481,15 +566,17 @@ def sparc_decode(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=N
     check_decode_params(decode_params)
     beta, t_final, nmse, psi = sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab, Az,
                                          precision=precision)
-    M = code_params['M']
+    M, K = code_params['M'], _modulation(code_params)
     if isinstance(beta, torch.Tensor):                  # batched device path
         expect_err = psi.mean(dim=1) >= 0.001
         logM = int(round(np.log2(M)))
         shifts = torch.arange(logM - 1, -1, -1, device=beta.device, dtype=torch.int32)
-        bits_out = ((beta.unsqueeze(-1) >> shifts) & 1).reshape(beta.shape[0], -1).bool()
-        return bits_out, beta, t_final, nmse, expect_err
-    if beta.ndim == 1 and beta.size == code_params['L'] * M:      # single frame: dense one-hot beta
+        bits_out = (((beta % M).unsqueeze(-1) >> shifts) & 1)
+        if K == 2:                                      # value bit after the location bits
+            bits_out = torch.cat([bits_out, (beta >= M).unsqueeze(-1).to(bits_out.dtype)], dim=-1)
+        return bits_out.reshape(beta.shape[0], -1).bool(), beta, t_final, nmse, expect_err
+    if beta.ndim == 1 and beta.size == code_params['L'] * M:      # single frame: dense beta
         expect_err = psi.mean() >= 0.001
-        return msg_vector_2_bin_arr(beta, M, 1), beta, t_final, nmse, expect_err
+        return msg_vector_2_bin_arr(beta, M, K), beta, t_final, nmse, expect_err
     psi2 = np.asarray(psi).reshape(len(beta), -1)
-    return indices_2_bin_arr(beta, M), beta, t_final, nmse, psi2.mean(axis=1) >= 0.001
+    return indices_2_bin_arr(beta, M, K), beta, t_final, nmse, psi2.mean(axis=1) >= 0.001

@@ -48,9 +48,30 @@ def calc_ser(beta0, beta, L):
     return num_of_sec_errs / L, np.flatnonzero(wrong), num_of_sec_errs
 
 
+def calc_ler_ver(beta0, beta, L, K):
+    """Location / value / section error rates of a modulated SPARC (sparc_sim.py:100-175).
+    Returns ``(ler, ver, ser), (loc_of_loc_errs, loc_of_val_errs, loc_of_sec_errs),
+    (num_of_loc_errs, num_of_val_errs, num_of_sec_errs)``."""
+    assert beta.size == beta0.size, 'beta and beta0 are of different size'
+    assert beta.dtype == beta0.dtype, 'beta and beta0 are of different type'
+    assert type(L) == int and L > 0
+    assert beta.size % L == 0
+    picked = []
+    for vec in (beta0, beta):
+        rows, cols = np.nonzero(vec.reshape(L, -1))
+        assert np.array_equal(rows, np.arange(L))        # exactly 1 nonzero in each row
+        picked.append((cols, vec.reshape(L, -1)[rows, cols]))
+    loc_err = picked[0][0] != picked[1][0]
+    val_err = picked[0][1] != picked[1][1]
+    errs = (loc_err, val_err, loc_err | val_err)
+    nums = tuple(int(np.count_nonzero(e)) for e in errs)
+    return tuple(k / L for k in nums), tuple(np.flatnonzero(e) for e in errs), nums
+
+
 def sparc_sim(code_params, decode_params, awgn_var, rand_seed=None, precision=None):
     """Encode, transmit and decode one frame (sparc_sim.py:8-58).  Returns the results dict
-    ``ber, cer, t_final, nmse, detect, ser, loc_of_sec_errs, num_of_sec_errs``.
+    ``ber, cer, t_final, nmse, detect, ser, loc_of_sec_errs, num_of_sec_errs`` (plus the
+    location / value error entries ``ler, ver, ...`` for a modulated code).
     ``precision`` ('fp32' default / 'fp64') selects the decoder kernel, as in sparc_decode."""
     bits_i, beta0, x, Ab, Az = sparc.sparc_encode(code_params, awgn_var, rand_seed)
     y = awgn_channel(x, awgn_var, rand_seed)
@@ -59,8 +80,14 @@ def sparc_sim(code_params, decode_params, awgn_var, rand_seed=None, precision=No
     ber = calc_ber(bits_i, bits_o)
     results = {'ber': ber, 'cer': 1.0 * (ber > 0), 't_final': T, 'nmse': nmse,
                'detect': 1.0 * (not (ber > 0) ^ bool(expect))}
-    ser, loc_of_sec_errs, num_of_sec_errs = calc_ser(beta0, beta, code_params['L'])
-    results.update({'ser': ser, 'loc_of_sec_errs': loc_of_sec_errs, 'num_of_sec_errs': num_of_sec_errs})
+    if not code_params['modulated']:
+        ser, loc_of_sec_errs, num_of_sec_errs = calc_ser(beta0, beta, code_params['L'])
+        results.update({'ser': ser, 'loc_of_sec_errs': loc_of_sec_errs, 'num_of_sec_errs': num_of_sec_errs})
+    else:
+        rates, locs, nums = calc_ler_ver(beta0, beta, code_params['L'], code_params['K'])
+        results.update({'ser': rates[2], 'ler': rates[0], 'ver': rates[1],
+                        'loc_of_sec_errs': locs[2], 'loc_of_loc_errs': locs[0], 'loc_of_val_errs': locs[1],
+                        'num_of_sec_errs': nums[2], 'num_of_loc_errs': nums[0], 'num_of_val_errs': nums[1]})
     return results
 
 
@@ -82,8 +109,9 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
     sparc.check_code_params(code_params)
     sparc._require_real_unmodulated(code_params)
     R, L, M = map(code_params.get, ['R', 'L', 'M'])
+    K = sparc._modulation(code_params)
     logM = int(round(np.log2(M)))
-    bit_len = L * logM
+    bit_len = L * (logM + (K == 2))
     tmp = code_params.copy()
     tmp.update({'awgn_var': awgn_var})
     W = sparc.create_base_matrix(**tmp)
@@ -99,19 +127,20 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
     dt = torch.float64 if precision == "fp64" else torch.float32
     counters = torch.zeros(len(BATCH_FIELDS), dtype=torch.int64, device=device)
     ranges = montecarlo.chunk_ranges(n_frames, chunk)
-    shifts = torch.arange(logM, device=device, dtype=torch.int32)
+    shifts = torch.arange(logM + (K == 2), device=device, dtype=torch.int32)
     for c in montecarlo.shard_chunks(len(ranges), rank, world):
         _, nf = ranges[c]
         gen = torch.Generator(device=device).manual_seed(montecarlo.chunk_seed(seed, 0, c))
-        idx0 = torch.randint(0, M, (nf, L), device=device, generator=gen, dtype=torch.int32)
+        idx0 = torch.randint(0, K * M, (nf, L), device=device, generator=gen, dtype=torch.int32)   # location + M * (value < 0)
         beta0 = torch.zeros((nf, L * M), dtype=dt, device=device)
-        beta0.view(nf, L, M).scatter_(2, idx0.long().unsqueeze(-1), 1.0)
+        beta0.view(nf, L, M).scatter_(2, (idx0 % M).long().unsqueeze(-1),
+                                      torch.where(idx0 >= M, -1.0, 1.0).to(dt).unsqueeze(-1))
         x = Ab(beta0, precision)
         del beta0
         y = x + float(np.sqrt(awgn_var)) * torch.randn((nf, n), device=device, generator=gen, dtype=dt)
         _, idx, t_final, _, expect = sparc.sparc_decode(y, code_params, decode_params, awgn_var, list(rand_seed),
                                                         idx0, Ab, Az, precision=precision)
-        diff = idx ^ idx0
+        diff = idx ^ idx0                                           # M is a power of two: the value bit is bit logM
         bit_err = ((diff.unsqueeze(-1) >> shifts) & 1).sum(dim=(1, 2))
         frame_err = bit_err > 0
         counters[0] += bit_err.sum()

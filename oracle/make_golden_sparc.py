@@ -98,3 +98,49 @@ def make_sophie(ref):
         print("sophie goldens: generator not present yet")
         return
     _mk(ref)
+
+
+# ------------------------------------------------------------------ real K = 2 modulation
+# Separate file (tests/golden/sparc_mod_reference.npz) so the unmodulated goldens above stay
+# byte-identical:  python oracle/make_golden_sparc.py mod
+MOD_CASES = {
+    "k2_reg": (dict(P=15.0, R=1.3, L=256, M=32, modulated=True, K=2), dict(t_max=25), 1.0),
+    "k2_pa_m64": (dict(P=15.0, R=1.5, L=256, M=64, modulated=True, K=2, power_allocated=True, B=8, R_PA_ratio=0.9),
+                  dict(t_max=25), 1.0),
+    # M < warp, SC, residual-variance estimate from z, rate close to capacity (section errors)
+    "k2_sc_m16": (dict(P=15.0, R=1.55, L=256, M=16, modulated=True, K=2, spatially_coupled=True, omega=3, Lambda=8),
+                  dict(t_max=20, phi_est_method=2), 1.0),
+}
+
+
+def make_sparc_mod(ref):
+    out, meta = {}, {}
+    for name, (cp, dp, var) in MOD_CASES.items():
+        meta[name] = dict(code_params=cp, decode_params=dp, awgn_var=var, seeds=[list(s) for s in SEEDS])
+        for si, seed in enumerate(SEEDS):
+            r = run_reference(ref, cp, dp, var, seed)
+            L, M = cp["L"], cp["M"]
+            sec = int(np.log2(M)) + 1
+            b = r["bits_in"].reshape(L, sec)
+            truth = b[:, :-1].astype(int).dot(1 << np.arange(sec - 1)[::-1])
+            dense = ref["sparc"].bin_arr_2_msg_vector(r["bits_out"], M, 2).reshape(L, M)
+            r["idx"] = np.abs(dense).argmax(1).astype(np.int32)                 # decided location ...
+            r["val"] = dense[np.arange(L), r["idx"]].astype(np.int8)            # ... and value (+1 / -1)
+            errs = int(((r["idx"] != truth) | ((r["val"] < 0) != b[:, -1])).sum())
+            print(name, seed, "t_final", int(r["t_final"]), "section errors", errs, "n", int(r["n"]))
+            for k, v in r.items():
+                out["%s_s%d_%s" % (name, si, k)] = v
+    out["meta_json"] = np.array(json.dumps(meta))
+    path = os.path.join(GOLD, "sparc_mod_reference.npz")
+    np.savez_compressed(path, **out)
+    print("sparc_mod_reference.npz: %.1f kB" % (os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_shims
+    if sys.argv[1:] == ["mod"]:
+        make_sparc_mod(ref_shims.load())
+    else:
+        make_sparc(ref_shims.load())

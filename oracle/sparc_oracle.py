@@ -60,7 +60,8 @@ def create_base_matrix(P, power_allocated=False, spatially_coupled=False, **kw):
 def code_dims(code_params, W):
     """n, R_actual as sparc_encode fixes them (sparc.py:27,39-45)."""
     L, M, R = code_params["L"], code_params["M"], code_params["R"]
-    bit_len = int(round(L * np.log2(M)))
+    K = code_params["K"] if code_params.get("modulated") else 1
+    bit_len = int(round(L * np.log2(K * M)))
     n = int(round(bit_len / R))
     if W.ndim == 2:
         Lr = W.shape[0]
@@ -148,20 +149,32 @@ class Design:
 
 
 # ------------------------------------------------------------------ estimators
-def mmse_estimator(s, tau, M):
-    """Section-wise softmax, K=1 branch (sparc.py:429-432,462-463): GLOBAL max
-    shift, extended-precision exp, cast back to float64."""
+def mmse_estimator(s, tau, M, K=1):
+    """Section-wise MMSE estimator, K=1 (sparc.py:429-432) and real K=2 (:433-441)
+    branches, cast back (:462-463): GLOBAL max shift, extended-precision exp."""
     x = s / tau
-    top = np.exp(x - x.max(), dtype=np.longdouble)
-    bot = top.reshape(-1, M).sum(axis=1).repeat(M)
+    if K == 1:
+        top = np.exp(x - x.max(), dtype=np.longdouble)
+        bot = top.reshape(-1, M).sum(axis=1).repeat(M)
+    else:
+        x_max = np.abs(x).max()
+        e1 = np.exp(x - x_max, dtype=np.longdouble)
+        e2 = np.exp(-x - x_max, dtype=np.longdouble)
+        top = e1 - e2
+        bot = (e1 + e2).reshape(-1, M).sum(axis=1).repeat(M)
     return (top / bot).astype(float)
 
 
-def map_estimator(s, M):
-    """sparc.py:485-487."""
+def map_estimator(s, M, K=1):
+    """sparc.py:485-487 (K=1), :488-492 (K=2: largest magnitude, its sign)."""
     L = s.size // M
     beta = np.zeros((L, M))
-    beta[np.arange(L), s.reshape(L, M).argmax(axis=1)] = 1
+    s2 = s.reshape(L, M)
+    if K == 1:
+        beta[np.arange(L), s2.argmax(axis=1)] = 1
+    else:
+        idx = np.abs(s2).argmax(axis=1)
+        beta[np.arange(L), idx] = np.sign(s2[np.arange(L), idx])
     return beta.ravel()
 
 
@@ -171,23 +184,29 @@ def rnd_bin_arr(k, rand_seed):
     return np.random.RandomState(rand_seed).randint(2, size=k, dtype="bool")
 
 
-def bin_arr_2_msg_vector(bits, M):
-    """sparc.py:330-364 (K=1): MSB-first section index."""
+def bin_arr_2_msg_vector(bits, M, K=1):
+    """sparc.py:330-364: per section logM index bits (MSB first) and, for K=2, one value
+    bit (2-PSK with Gray coding is the identity map: bit 0 -> +1, bit 1 -> -1, :227-253)."""
     logM = int(round(np.log2(M)))
-    L = bits.size // logM
-    idx = bits.reshape(L, logM).astype(np.int64).dot(1 << np.arange(logM)[::-1])
+    sec = logM + (1 if K == 2 else 0)
+    L = bits.size // sec
+    b = bits.reshape(L, sec)
+    idx = b[:, :logM].astype(np.int64).dot(1 << np.arange(logM)[::-1])
     beta = np.zeros(L * M)
-    beta[np.arange(L) * M + idx] = 1
+    beta[np.arange(L) * M + idx] = 1 if K == 1 else 1.0 - 2.0 * b[:, logM]
     return beta
 
 
-def msg_vector_2_bin_arr(beta, M):
-    """sparc.py:366-400 (K=1), with int_2_bin_arr's numpy-1.x meaning (:191-197)."""
+def msg_vector_2_bin_arr(beta, M, K=1):
+    """sparc.py:366-400, with int_2_bin_arr's numpy-1.x meaning (:191-197)."""
     logM = int(round(np.log2(M)))
     L = beta.size // M
     rows, idx = np.nonzero(beta.reshape(L, M))
     assert np.array_equal(rows, np.arange(L))
-    return ((idx[:, None] >> np.arange(logM)[::-1]) & 1).astype(bool).ravel()
+    bits = ((idx[:, None] >> np.arange(logM)[::-1]) & 1).astype(bool)
+    if K == 2:
+        bits = np.concatenate([bits, (beta.reshape(L, M)[rows, idx] < 0)[:, None]], axis=1)
+    return bits.ravel()
 
 
 def awgn_channel(x, awgn_var, rand_seed):
@@ -201,17 +220,21 @@ def normalise_code_params(cp):
     cp = dict(cp)
     for k in ("complex", "modulated", "power_allocated", "spatially_coupled"):
         cp.setdefault(k, False)
-    if cp["complex"] or cp["modulated"]:
-        raise NotImplementedError("complex / modulated SPARCs are outside the oracle's scope")
+    if cp["complex"] or (cp["modulated"] and cp.get("K") != 2):
+        raise NotImplementedError("complex SPARCs (K > 2) are outside the oracle's scope")
     return cp
+
+
+def modulation(cp):
+    return cp["K"] if cp.get("modulated") else 1
 
 
 def sparc_encode(code_params, awgn_var, rand_seed):
     """sparc.py:17-53.  Returns bits_in, beta0, x, design (instead of Ab, Az), n."""
     cp = normalise_code_params(code_params)
-    L, M = cp["L"], cp["M"]
-    bits_in = rnd_bin_arr(int(round(L * np.log2(M))), rand_seed)
-    beta0 = bin_arr_2_msg_vector(bits_in, M)
+    L, M, K = cp["L"], cp["M"], modulation(cp)
+    bits_in = rnd_bin_arr(int(round(L * np.log2(K * M))), rand_seed)
+    beta0 = bin_arr_2_msg_vector(bits_in, M, K)
     W = create_base_matrix(**dict(cp, awgn_var=awgn_var))
     n, _ = code_dims(cp, W)
     design = Design(W, L, M, n, rand_seed)
@@ -220,10 +243,10 @@ def sparc_encode(code_params, awgn_var, rand_seed):
 
 # ------------------------------------------------------------------ AMP decoder
 def sparc_amp(y, code_params, decode_params, awgn_var, design, beta0=None, trace=None):
-    """sparc.py:883-999 (K=1).  `trace`, if a list, receives one dict per
+    """sparc.py:883-999 (K=1, real K=2).  `trace`, if a list, receives one dict per
     iteration with the quantities the parity tests compare (tau, phi, psi, s, beta)."""
     cp = normalise_code_params(code_params)
-    L, M, n = cp["L"], cp["M"], design.n
+    L, M, n, K = cp["L"], cp["M"], design.n, modulation(cp)
     W = create_base_matrix(**dict(cp, awgn_var=awgn_var))
     t_max = decode_params["t_max"]
     rtol = decode_params.get("rtol", 1e-6)
@@ -264,7 +287,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, design, beta0=None, trace
             tau = (L / Mr) / np.dot(W.T, 1 / phi)
             tau_use, phi_use = tau.repeat(Mc), phi.repeat(Mr)
         s = beta + tau_use * design.Az(z / phi_use)
-        beta = mmse_estimator(s, tau_use, M)
+        beta = mmse_estimator(s, tau_use, M, K)
         if W.ndim == 0:
             psi = 1 - (np.abs(beta) ** 2).sum() / L
             nmse[t + 1] = (np.abs(beta - beta0) ** 2).sum() / L
@@ -277,7 +300,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, design, beta0=None, trace
             nmse[t:] = nmse[t]
             break
     t_final = t + 1
-    return map_estimator(s, M), t_final, nmse, psi
+    return map_estimator(s, M, K), t_final, nmse, psi
 
 
 def sparc_decode(y, code_params, decode_params, awgn_var, design, beta0=None, trace=None):
@@ -287,4 +310,5 @@ def sparc_decode(y, code_params, decode_params, awgn_var, design, beta0=None, tr
     dp.setdefault("phi_est_method", 1)
     beta, t_final, nmse, psi = sparc_amp(y, code_params, dp, awgn_var, design, beta0, trace)
     expect_err = psi.mean() >= 0.001
-    return msg_vector_2_bin_arr(beta, code_params["M"]), beta, t_final, nmse, expect_err
+    K = code_params["K"] if code_params.get("modulated") else 1
+    return msg_vector_2_bin_arr(beta, code_params["M"], K), beta, t_final, nmse, expect_err

@@ -127,3 +127,27 @@ def test_oracle_bit_exact_vs_imported_reference():
         bits_i, beta0, x2, y2, design, (bits_o, beta2, T2, nmse2, ex2), _ = _run_oracle(cp, dict(t_max=20), 1.0, seed)
         assert np.array_equal(x, x2) and np.array_equal(y, y2) and T == T2
         assert np.array_equal(bo, bits_o) and np.array_equal(beta, beta2) and np.array_equal(nmse, nmse2)
+
+
+def test_oracle_matches_reference_golden_k2_modulated():
+    """Real 2-PSK modulated SPARCs (sparc.py:433-441, 488-492): goldens of
+    oracle/make_golden_sparc.py mod."""
+    g = np.load(os.path.join(GOLDEN, "sparc_mod_reference.npz"))
+    meta = json.loads(str(g["meta_json"]))
+    assert set(meta) == {"k2_reg", "k2_pa_m64", "k2_sc_m16"}
+    for name, m in meta.items():
+        for si, seed in enumerate(m["seeds"]):
+            pre = "%s_s%d_" % (name, si)
+            bits_i, beta0, x, y, design, (bits_o, beta, T, nmse, expect), trace = _run_oracle(
+                m["code_params"], m["decode_params"], m["awgn_var"], seed)
+            assert np.array_equal(bits_i, g[pre + "bits_in"])
+            assert np.array_equal(x, g[pre + "x"]) and np.array_equal(y, g[pre + "y"])
+            assert T == int(g[pre + "t_final"]) and bool(expect) == bool(g[pre + "expect_err"])
+            assert np.array_equal(bits_o, g[pre + "bits_out"])
+            dense = beta.reshape(-1, design.M)
+            idx = np.abs(dense).argmax(1)
+            assert np.array_equal(idx, g[pre + "idx"]) and np.array_equal(dense[np.arange(len(idx)), idx], g[pre + "val"])
+            assert np.array_equal(nmse, g[pre + "nmse"])
+            assert np.array_equal(np.array([np.broadcast_to(t["tau"], (design.Lc,)) for t in trace]), g[pre + "tau_it"])
+            assert np.array_equal(np.array([np.broadcast_to(t["psi"], (design.Lc,)) for t in trace]), g[pre + "psi_it"])
+            assert np.array_equal(trace[-1]["s"].astype(np.float32), g[pre + "s_last"])

@@ -210,3 +210,83 @@ def test_config4_sc_wave_matches_reference_golden(gold):
             assert T - 1 <= t_final <= dp["t_max"] - 1
             Tc = min(T, t_final)
             assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < 1e-4
+
+
+# ---------------------------------------------------------------- real 2-PSK modulation
+@pytest.fixture(scope="module")
+def gold_mod():
+    g = np.load(os.path.join(GOLDEN, "sparc_mod_reference.npz"))
+    return g, json.loads(str(g["meta_json"]))
+
+
+def _decided(beta, M):
+    dense = beta.reshape(-1, M)
+    idx = np.abs(dense).argmax(1)
+    return idx, dense[np.arange(len(idx)), idx]
+
+
+@pytest.mark.parametrize("name", ["k2_reg", "k2_pa_m64", "k2_sc_m16"])
+def test_amp_k2_fp64_matches_reference_golden(gold_mod, name):
+    g, meta = gold_mod
+    for si in range(2):
+        pre, cp, dp, (beta, t_final, nmse, psi, ex) = _decode_case(g, meta, name, si, "fp64")
+        T = int(g[pre + "t_final"])
+        assert t_final == T
+        idx, val = _decided(beta, cp["M"])
+        assert np.array_equal(idx, g[pre + "idx"]) and np.array_equal(val, g[pre + "val"])      # locations and signs exact
+        assert rel_err(ex["tau"][:T], g[pre + "tau_it"]) < 1e-9
+        ref_psi = g[pre + "psi_it"]
+        assert np.max(np.abs(ex["psi"][:T] - ref_psi)) <= 1e-9 * np.max(np.abs(ref_psi)) + 1e-13
+        assert np.max(np.abs(ex["s"] - g[pre + "s_last"])) <= 2e-6 * np.max(np.abs(g[pre + "s_last"]))
+        assert np.max(np.abs(ex["beta_soft"] - g[pre + "beta_soft"])) < 1e-6                        # golden beta is fp32
+        assert np.allclose(nmse, g[pre + "nmse"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["k2_reg", "k2_pa_m64", "k2_sc_m16"])
+def test_amp_k2_fp32_matches_reference_golden(gold_mod, name):
+    g, meta = gold_mod
+    for si in range(2):
+        pre, cp, dp, (beta, t_final, nmse, psi, ex) = _decode_case(g, meta, name, si, "fp32")
+        T = int(g[pre + "t_final"])
+        idx, val = _decided(beta, cp["M"])
+        assert np.array_equal(idx, g[pre + "idx"]) and np.array_equal(val, g[pre + "val"])
+        assert T - 1 <= t_final <= dp["t_max"] - 1, (t_final, T)
+        Tc = min(T, t_final)
+        assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < 1e-4
+        ref_psi = g[pre + "psi_it"][:Tc]
+        assert np.all(np.abs(ex["psi"][:Tc] - ref_psi) <= 1e-4 * ref_psi + 2e-8)
+
+
+def test_k2_dropin_bits_and_sim(gold_mod):
+    """sparc_encode -> awgn -> sparc_decode and sparc_sim for a modulated code, single frame
+    and batched (bits: logM location bits then the value bit, sparc.py:330-400)."""
+    from ldpc_sparc_b200 import sparc_sim
+    g, meta = gold_mod
+    m = meta["k2_sc_m16"]
+    seed = m["seeds"][0]
+    pre = "k2_sc_m16_s0_"
+    cp, dp = dict(m["code_params"]), dict(m["decode_params"])
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], seed)
+    assert np.array_equal(bits_in, g[pre + "bits_in"]) and cp["n"] == int(g[pre + "n"])
+    assert np.max(np.abs(x - g[pre + "x"])) < 1e-9
+    bits_o, beta, T, nmse, expect = sparc.sparc_decode(g[pre + "y"], cp, dp, m["awgn_var"], seed, beta0, Ab, Az,
+                                                       precision="fp64")
+    assert np.array_equal(bits_o, g[pre + "bits_out"]) and T == int(g[pre + "t_final"])
+    assert bool(expect) == bool(g[pre + "expect_err"])
+    # batched: three copies of the frame + the other seed's noise realisation
+    y2 = np.stack([g[pre + "y"], g[pre + "y"], g["k2_sc_m16_s0_x"] + (g[pre + "y"] - g[pre + "x"])[::-1]])
+    bits_b, idx_b, T_b, _, _ = sparc.sparc_decode(y2, cp, dp, m["awgn_var"], seed, beta0, Ab, Az, precision="fp64")
+    assert bits_b.shape == (3, bits_in.size) and np.array_equal(bits_b[0], bits_o) and np.array_equal(bits_b[1], bits_o)
+    assert np.array_equal(idx_b[0] % cp["M"], g[pre + "idx"]) and np.array_equal(idx_b[0] >= cp["M"], g[pre + "val"] < 0)
+    res = sparc_sim.sparc_sim(dict(m["code_params"]), dict(m["decode_params"]), m["awgn_var"], seed, precision="fp64")
+    L, M = cp["L"], cp["M"]
+    b = g[pre + "bits_in"].reshape(L, -1)
+    truth = b[:, :-1].astype(int).dot(1 << np.arange(b.shape[1] - 1)[::-1])
+    loc_err = truth != g[pre + "idx"]
+    val_err = b[:, -1] != (g[pre + "val"] < 0)
+    assert res["num_of_loc_errs"] == int(loc_err.sum()) and res["num_of_sec_errs"] == int((loc_err | val_err).sum())
+    assert res["ber"] == np.count_nonzero(g[pre + "bits_in"] ^ g[pre + "bits_out"]) / bits_in.size
+    out = sparc_sim.sparc_sim_batch(dict(P=15.0, R=1.3, L=256, M=32, modulated=True, K=2), dict(t_max=25), 1.0, 384,
+                                    chunk=128)
+    assert out["frames"] == 384 and out["n"] == 1182 and out["ser"] < 2e-3
+    assert out["section_errors"] <= out["bit_errors"] <= 6 * out["section_errors"]
