@@ -136,11 +136,87 @@ def make_sparc_mod(ref):
     print("sparc_mod_reference.npz: %.1f kB" % (os.path.getsize(path) / 1e3))
 
 
+# ------------------------------------------------------------------ complex designs
+# tests/golden/sparc_complex_reference.npz:  python oracle/make_golden_sparc.py complex
+COMPLEX_CASES = {
+    "c_k1": (dict(P=15.0, R=2.6, L=256, M=32, complex=True), dict(t_max=25), 1.0),
+    "c_k2": (dict(P=15.0, R=2.4, L=128, M=64, complex=True, modulated=True, K=2), dict(t_max=25), 1.0),
+    "c_k4_pa": (dict(P=15.0, R=3.0, L=256, M=32, complex=True, modulated=True, K=4, power_allocated=True, B=8,
+                     R_PA_ratio=0.9), dict(t_max=25), 1.0),
+    # K > 4 branch, M < warp, SC, residual-variance estimate from z, rate near capacity (section errors)
+    "c_k8_sc_m16": (dict(P=15.0, R=3.3, L=256, M=16, complex=True, modulated=True, K=8, spatially_coupled=True,
+                         omega=3, Lambda=8), dict(t_max=20, phi_est_method=2), 1.0),
+}
+
+
+def symbols_of(ref, beta, L, M, K):
+    """Decided / true section symbols as location + M * constellation index."""
+    dense = beta.reshape(L, M)
+    loc = np.abs(dense).argmax(1)
+    if K == 1:
+        return loc.astype(np.int32)
+    c = ref["sparc"].psk_constel(K)
+    k = np.array([int(np.flatnonzero(c == v)[0]) for v in dense[np.arange(L), loc]])
+    return (loc + M * k).astype(np.int32)
+
+
+def run_reference_complex(ref, cp, dp, var, seed):
+    R, RS = ref["sparc"], ref["sparc_sim"]
+    cp, dp = dict(cp), dict(dp)
+    bits_i, beta0, x, Ab, Az = R.sparc_encode(cp, var, seed)
+    y = RS.awgn_channel(x, var, seed)
+    trace = []
+    orig = R.msg_vector_mmse_estimator
+
+    def spy(s, tau, M, K=1):
+        tau_in = np.copy(tau)                  # the estimator halves a complex design's tau in place (:417-418)
+        out = orig(s, tau, M, K)
+        trace.append((s.copy(), tau_in, out.copy()))
+        return out
+
+    R.msg_vector_mmse_estimator = spy
+    try:
+        bits_o, beta, T, nmse, expect = R.sparc_decode(y, cp, dp, var, seed, beta0, Ab, Az)
+    finally:
+        R.msg_vector_mmse_estimator = orig
+    L, M = cp["L"], cp["M"]
+    K = cp["K"] if cp["modulated"] else 1
+    W = R.create_base_matrix(**dict(cp, awgn_var=var))
+    Lc = 1 if W.ndim == 0 else W.shape[-1]
+    Mc = L * M // Lc
+    tau_it = np.array([np.broadcast_to(np.asarray(t[1], dtype=float).reshape(-1), (L * M,))[::Mc] if np.ndim(t[1]) else
+                       np.full(Lc, float(t[1])) for t in trace])
+    psi_it = np.array([1 - (np.abs(t[2]) ** 2).reshape(Lc, -1).sum(axis=1) / (L / Lc) for t in trace])
+    return dict(bits_in=bits_i, x=x, y=y, bits_out=bits_o, sym=symbols_of(ref, beta, L, M, K),
+                sym0=symbols_of(ref, beta0, L, M, K), t_final=np.array(T), nmse=np.asarray(nmse),
+                expect_err=np.array(bool(expect)), tau_it=tau_it, psi_it=psi_it,
+                s_last=trace[-1][0].astype(np.complex64), beta_soft=trace[-1][2].astype(np.complex64),
+                n=np.array(cp["n"]))
+
+
+def make_sparc_complex(ref):
+    out, meta = {}, {}
+    for name, (cp, dp, var) in COMPLEX_CASES.items():
+        meta[name] = dict(code_params=cp, decode_params=dp, awgn_var=var, seeds=[list(s) for s in SEEDS])
+        for si, seed in enumerate(SEEDS):
+            r = run_reference_complex(ref, cp, dp, var, seed)
+            print(name, seed, "t_final", int(r["t_final"]), "section errors", int((r["sym"] != r["sym0"]).sum()),
+                  "bit errors", int((r["bits_in"] != r["bits_out"]).sum()), "n", int(r["n"]))
+            for k, v in r.items():
+                out["%s_s%d_%s" % (name, si, k)] = v
+    out["meta_json"] = np.array(json.dumps(meta))
+    path = os.path.join(GOLD, "sparc_complex_reference.npz")
+    np.savez_compressed(path, **out)
+    print("sparc_complex_reference.npz: %.1f kB" % (os.path.getsize(path) / 1e3))
+
+
 if __name__ == "__main__":
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import ref_shims
     if sys.argv[1:] == ["mod"]:
         make_sparc_mod(ref_shims.load())
+    elif sys.argv[1:] == ["complex"]:
+        make_sparc_complex(ref_shims.load())
     else:
         make_sparc(ref_shims.load())

@@ -78,9 +78,9 @@ class Design:
     shuffled IN PLACE, cumulatively, once per non-zero block, by one
     RandomState(rand_seed) (generate_ordering, sparc.py:735-775)."""
 
-    def __init__(self, W, L, M, n, rand_seed):
+    def __init__(self, W, L, M, n, rand_seed, csparc=False):
         W = np.asarray(W, dtype=float)
-        self.W, self.L, self.M, self.n = W, L, M, n
+        self.W, self.L, self.M, self.n, self.csparc = W, L, M, n, csparc
         if W.ndim == 0:
             self.Lr, self.Lc = 1, 1
             Wm = W.reshape(1, 1)
@@ -93,9 +93,14 @@ class Design:
         assert (L * M) % self.Lc == 0 and n % self.Lr == 0
         self.Wm = Wm
         self.Mr, self.Mc = n // self.Lr, L * M // self.Lc
-        self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 1, self.Mc + 1))))
-        idx0 = np.arange(1, self.w, dtype=np.uint32)
-        idx1 = np.arange(1, self.w, dtype=np.uint32)
+        if not csparc:
+            self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 1, self.Mc + 1))))
+            idx0 = np.arange(1, self.w, dtype=np.uint32)
+            idx1 = np.arange(1, self.w, dtype=np.uint32)
+        else:      # sub-sampled DFT design: rows/columns 0 and w/2 are never used (sparc.py:747-750)
+            self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 2, self.Mc + 2))))
+            idx0 = np.delete(np.arange(self.w, dtype=np.uint32), [0, self.w // 2])
+            idx1 = np.delete(np.arange(self.w, dtype=np.uint32), [0, self.w // 2])
         rng = np.random.RandomState(rand_seed)
         self.order0 = np.zeros((self.Lr, self.Lc, self.Mr), dtype=np.uint32)
         self.order1 = np.zeros((self.Lr, self.Lc, self.Mc), dtype=np.uint32)
@@ -109,6 +114,8 @@ class Design:
 
     def Ab(self, x):
         """A @ x (sparc.py:786-789,811-819,851-862 with sub_dct.Ax :687-692)."""
+        if self.csparc:
+            return self._cab(np.asarray(x))
         x = np.asarray(x, dtype=float)
         assert x.size == self.Lc * self.Mc
         out = np.zeros(self.Lr * self.Mr)
@@ -123,6 +130,8 @@ class Design:
 
     def Az(self, y):
         """A.T @ y (sparc.py:791-794,821-829,864-875 with sub_dct.Ay :694-699)."""
+        if self.csparc:
+            return self._caz(np.asarray(y))
         y = np.asarray(y, dtype=float)
         assert y.size == self.Lr * self.Mr
         out = np.zeros(self.Lc * self.Mc)
@@ -135,8 +144,41 @@ class Design:
                     out[c * self.Mc:(c + 1) * self.Mc] += np.sqrt(self.Wm[r, c] / self.L) * x[self.order1[r, c]]
         return out
 
+    def _cab(self, x):
+        """Complex design, A @ x: zero-padded scatter, FFT, gather (sub_fft.Ax, sparc.py:632-637)."""
+        out = np.zeros(self.Lr * self.Mr, dtype=complex)
+        for r in range(self.Lr):
+            for c in range(self.Lc):
+                if self.Wm[r, c] != 0:
+                    ext = np.zeros(self.w, dtype=complex)
+                    ext[self.order1[r, c]] = x[c * self.Mc:(c + 1) * self.Mc]
+                    out[r * self.Mr:(r + 1) * self.Mr] += np.sqrt(self.Wm[r, c] / self.L) * np.fft.fft(ext)[self.order0[r, c]]
+        return out
+
+    def _caz(self, y):
+        """Complex design, A^H @ y (sub_fft.Ay, sparc.py:639-644)."""
+        out = np.zeros(self.Lc * self.Mc, dtype=complex)
+        for r in range(self.Lr):
+            for c in range(self.Lc):
+                if self.Wm[r, c] != 0:
+                    ext = np.zeros(self.w, dtype=complex)
+                    ext[self.order0[r, c]] = y[r * self.Mr:(r + 1) * self.Mr]
+                    back = np.fft.fft(ext.conj()).conj()
+                    out[c * self.Mc:(c + 1) * self.Mc] += np.sqrt(self.Wm[r, c] / self.L) * back[self.order1[r, c]]
+        return out
+
     def dense(self):
         """Explicit A from the closed form (small sizes only)."""
+        if self.csparc:
+            A = np.zeros((self.Lr * self.Mr, self.Lc * self.Mc), dtype=complex)
+            for r in range(self.Lr):
+                for c in range(self.Lc):
+                    if self.Wm[r, c] != 0:
+                        o0 = self.order0[r, c].astype(float)[:, None]
+                        o1 = self.order1[r, c].astype(float)[None, :]
+                        A[r * self.Mr:(r + 1) * self.Mr, c * self.Mc:(c + 1) * self.Mc] = (
+                            np.sqrt(self.Wm[r, c] / self.L) * np.exp(-2j * np.pi * o0 * o1 / self.w))
+            return A
         A = np.zeros((self.Lr * self.Mr, self.Lc * self.Mc))
         for r in range(self.Lr):
             for c in range(self.Lc):
@@ -148,11 +190,49 @@ class Design:
         return A
 
 
+# ------------------------------------------------------------------ PSK
+def psk_constel(K):
+    """sparc.py:225-239."""
+    if K == 2:
+        return np.array([1, -1])
+    if K == 4:
+        return np.array([1 + 0j, 0 + 1j, -1 + 0j, 0 - 1j])
+    theta = 2 * np.pi * np.arange(K) / K
+    return np.cos(theta) + 1j * np.sin(theta)
+
+
+def gray_to_binary(g):
+    """sparc.py:214-223."""
+    mask = g >> 1
+    while mask:
+        g ^= mask
+        mask >>= 1
+    return g
+
+
 # ------------------------------------------------------------------ estimators
 def mmse_estimator(s, tau, M, K=1):
-    """Section-wise MMSE estimator, K=1 (sparc.py:429-432) and real K=2 (:433-441)
-    branches, cast back (:462-463): GLOBAL max shift, extended-precision exp."""
-    x = s / tau
+    """Section-wise MMSE estimator (sparc.py:402-465): K=1 (:429-432), K=2 (:433-441),
+    K=4 (:442-453), K>4 (:454-459); complex observations halve tau first (:417-418);
+    GLOBAL max shift, extended-precision exp, cast back (:462-465)."""
+    if np.iscomplexobj(s):
+        tau = tau / 2
+    if K > 2:
+        if K == 4:
+            x, yv = s.real / tau, s.imag / tau
+            mx = np.maximum(np.abs(x), np.abs(yv)).max()
+            ex1, ex2 = np.exp(x - mx, dtype=np.longdouble), np.exp(-x - mx, dtype=np.longdouble)
+            ey1, ey2 = np.exp(yv - mx, dtype=np.longdouble), np.exp(-yv - mx, dtype=np.longdouble)
+            top = (ex1 - ex2) + 1j * (ey1 - ey2)
+            bot = ((ex1 + ex2) + (ey1 + ey2)).reshape(-1, M).sum(axis=1).repeat(M)
+        else:
+            c = psk_constel(K)
+            x = np.outer(s / tau, c.conj()).real
+            tmp = np.exp(x - np.abs(x).max(), dtype=np.longdouble)
+            top = np.dot(tmp, c)
+            bot = tmp.sum(axis=1).reshape(-1, M).sum(axis=1).repeat(M)
+        return (top / bot).astype(complex)
+    x = s.real / tau
     if K == 1:
         top = np.exp(x - x.max(), dtype=np.longdouble)
         bot = top.reshape(-1, M).sum(axis=1).repeat(M)
@@ -166,10 +246,26 @@ def mmse_estimator(s, tau, M, K=1):
 
 
 def map_estimator(s, M, K=1):
-    """sparc.py:485-487 (K=1), :488-492 (K=2: largest magnitude, its sign)."""
+    """sparc.py:485-487 (K=1), :488-492 (K=2: largest magnitude, its sign), :493-501 (K=4),
+    :502-510 (K>4)."""
     L = s.size // M
+    if K > 2:
+        c = psk_constel(K)
+        beta = np.zeros((L, M), dtype=complex)
+        sm = s.reshape(L, M)
+        if K == 4:
+            idx = np.maximum(np.abs(sm.real), np.abs(sm.imag)).argmax(axis=1)
+            k = np.rint(K * np.angle(sm[np.arange(L), idx]) / (2 * np.pi)).astype(int)
+            k[k < 0] += K
+            beta[np.arange(L), idx] = c[k]
+        else:
+            for l in range(L):
+                corr = np.outer(sm[l].conj(), c).real
+                j, k = np.unravel_index(corr.argmax(), corr.shape)
+                beta[l, j] = c[k]
+        return beta.ravel()
     beta = np.zeros((L, M))
-    s2 = s.reshape(L, M)
+    s2 = s.real.reshape(L, M)
     if K == 1:
         beta[np.arange(L), s2.argmax(axis=1)] = 1
     else:
@@ -188,10 +284,16 @@ def bin_arr_2_msg_vector(bits, M, K=1):
     """sparc.py:330-364: per section logM index bits (MSB first) and, for K=2, one value
     bit (2-PSK with Gray coding is the identity map: bit 0 -> +1, bit 1 -> -1, :227-253)."""
     logM = int(round(np.log2(M)))
-    sec = logM + (1 if K == 2 else 0)
+    logK = int(round(np.log2(K)))
+    sec = logM + logK
     L = bits.size // sec
     b = bits.reshape(L, sec)
     idx = b[:, :logM].astype(np.int64).dot(1 << np.arange(logM)[::-1])
+    if K > 2:       # Gray-coded K-PSK value (psk_mod, sparc.py:241-269)
+        word = b[:, logM:].astype(np.int64).dot(1 << np.arange(logK)[::-1])
+        beta = np.zeros(L * M, dtype=complex)
+        beta[np.arange(L) * M + idx] = psk_constel(K)[[gray_to_binary(int(v)) for v in word]]
+        return beta
     beta = np.zeros(L * M)
     beta[np.arange(L) * M + idx] = 1 if K == 1 else 1.0 - 2.0 * b[:, logM]
     return beta
@@ -206,12 +308,20 @@ def msg_vector_2_bin_arr(beta, M, K=1):
     bits = ((idx[:, None] >> np.arange(logM)[::-1]) & 1).astype(bool)
     if K == 2:
         bits = np.concatenate([bits, (beta.reshape(L, M)[rows, idx] < 0)[:, None]], axis=1)
+    elif K > 2:     # psk_demod (sparc.py:271-299): exact match against the constellation, Gray index
+        c, logK = psk_constel(K), int(round(np.log2(K)))
+        k = np.array([int(np.flatnonzero(c == v)[0]) for v in beta.reshape(L, M)[rows, idx]])
+        gray = k ^ (k >> 1)
+        bits = np.concatenate([bits, ((gray[:, None] >> np.arange(logK)[::-1]) & 1).astype(bool)], axis=1)
     return bits.ravel()
 
 
 def awgn_channel(x, awgn_var, rand_seed):
-    """sparc_sim.py:179-198 (real input)."""
-    return x + np.sqrt(awgn_var) * np.random.RandomState(rand_seed).randn(x.size)
+    """sparc_sim.py:179-204: variance awgn_var, split over the two dimensions of a complex input."""
+    rng = np.random.RandomState(rand_seed)
+    if np.iscomplexobj(x):
+        return x + np.sqrt(awgn_var / 2) * (rng.randn(x.size) + 1j * rng.randn(x.size))
+    return x + np.sqrt(awgn_var) * rng.randn(x.size)
 
 
 # ------------------------------------------------------------------------ encoder
@@ -220,8 +330,8 @@ def normalise_code_params(cp):
     cp = dict(cp)
     for k in ("complex", "modulated", "power_allocated", "spatially_coupled"):
         cp.setdefault(k, False)
-    if cp["complex"] or (cp["modulated"] and cp.get("K") != 2):
-        raise NotImplementedError("complex SPARCs (K > 2) are outside the oracle's scope")
+    if cp["modulated"] and not cp["complex"]:
+        assert cp["K"] == 2, "Real-modulated SPARCs requires K=2"
     return cp
 
 
@@ -237,7 +347,7 @@ def sparc_encode(code_params, awgn_var, rand_seed):
     beta0 = bin_arr_2_msg_vector(bits_in, M, K)
     W = create_base_matrix(**dict(cp, awgn_var=awgn_var))
     n, _ = code_dims(cp, W)
-    design = Design(W, L, M, n, rand_seed)
+    design = Design(W, L, M, n, rand_seed, cp["complex"])
     return bits_in, beta0, design.Ab(beta0), design, n
 
 
@@ -253,7 +363,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, design, beta0=None, trace
     method = decode_params.get("phi_est_method", 1)
     if beta0 is None:
         beta0 = np.zeros(L * M)
-    beta = np.zeros(L * M)
+    beta = np.zeros(L * M) if K in (1, 2) else np.zeros(L * M, dtype=complex)
     z = y
     atol = 2 * np.finfo(float).resolution
     if W.ndim == 0:

@@ -151,3 +151,44 @@ def test_oracle_matches_reference_golden_k2_modulated():
             assert np.array_equal(np.array([np.broadcast_to(t["tau"], (design.Lc,)) for t in trace]), g[pre + "tau_it"])
             assert np.array_equal(np.array([np.broadcast_to(t["psi"], (design.Lc,)) for t in trace]), g[pre + "psi_it"])
             assert np.array_equal(trace[-1]["s"].astype(np.float32), g[pre + "s_last"])
+
+
+def test_oracle_matches_reference_golden_complex():
+    """Complex designs (sub-sampled DFT, sparc.py:593-646) with K = 1, 2, 4 and 8: goldens of
+    oracle/make_golden_sparc.py complex."""
+    g = np.load(os.path.join(GOLDEN, "sparc_complex_reference.npz"))
+    meta = json.loads(str(g["meta_json"]))
+    assert set(meta) == {"c_k1", "c_k2", "c_k4_pa", "c_k8_sc_m16"}
+    for name, m in meta.items():
+        cp = so.normalise_code_params(m["code_params"])
+        K = so.modulation(cp)
+        for si, seed in enumerate(m["seeds"]):
+            pre = "%s_s%d_" % (name, si)
+            bits_i, beta0, x, y, design, (bits_o, beta, T, nmse, expect), trace = _run_oracle(
+                cp, m["decode_params"], m["awgn_var"], seed)
+            assert design.csparc and np.iscomplexobj(x)
+            assert np.array_equal(bits_i, g[pre + "bits_in"])
+            assert np.array_equal(x, g[pre + "x"]) and np.array_equal(y, g[pre + "y"])
+            assert T == int(g[pre + "t_final"]) and bool(expect) == bool(g[pre + "expect_err"])
+            assert np.array_equal(bits_o, g[pre + "bits_out"])
+            dense = beta.reshape(-1, design.M)
+            loc = np.abs(dense).argmax(1)
+            assert np.array_equal(loc, g[pre + "sym"] % design.M)
+            if K > 1:
+                assert np.array_equal(dense[np.arange(len(loc)), loc], so.psk_constel(K)[g[pre + "sym"] // design.M])
+            assert np.array_equal(nmse, g[pre + "nmse"])
+            assert np.array_equal(np.array([np.broadcast_to(t["tau"], (design.Lc,)) for t in trace]), g[pre + "tau_it"])
+            assert np.array_equal(np.array([np.broadcast_to(t["psi"], (design.Lc,)) for t in trace]), g[pre + "psi_it"])
+            assert np.array_equal(trace[-1]["s"].astype(np.complex64), g[pre + "s_last"])
+
+
+def test_complex_operators_equal_closed_form_matrix():
+    """A = sqrt(W/L) exp(-2 pi i o0 o1 / w): Ab = A x, Az = A^H y."""
+    rng = np.random.RandomState(0)
+    for W, L, M, n in ((np.array(3.0), 8, 8, 20), (so.sc_basic(np.array(2.0), 2, 3), 6, 8, 32)):
+        d = so.Design(W, L, M, n, [3, 4], csparc=True)
+        A = d.dense()
+        x = rng.randn(L * M) + 1j * rng.randn(L * M)
+        y = rng.randn(n) + 1j * rng.randn(n)
+        assert np.allclose(d.Ab(x), A @ x, atol=1e-11) and np.allclose(d.Az(y), A.conj().T @ y, atol=1e-11)
+        assert not np.isin(d.order0[d.Wm != 0], [0, d.w // 2]).any()
