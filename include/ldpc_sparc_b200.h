@@ -181,7 +181,8 @@ typedef struct lsb_sparc_amp_params {
     int32_t t_max;         /* the loop runs at most t_max - 1 iterations (:931)     */
     int32_t phi_est_method;/* 1: awgn_var + gamma, 2: mean(z^2)  (:949-955)         */
     int32_t modulation;    /* K of the reference: 0 or 1 = unmodulated, 2 = real    *
-                            * 2-PSK values +1 / -1 (:433-441, 488-492)              */
+                            * 2-PSK values +1 / -1 (:433-441, 488-492); complex     *
+                            * designs (lsb_csparc_*) take any power of two <= 64    */
     int32_t reserved;      /* must be 0                                             */
 } lsb_sparc_amp_params;
 
@@ -283,6 +284,31 @@ int lsb_tc_ab_dev_f32(lsb_tc_design *g, const float *x /* [F, ML] */, float *out
                       void *stream);
 int lsb_tc_az_dev_f32(lsb_tc_design *g, const float *z /* [F, n] */, float *out /* [F, ML] */, int64_t F,
                       void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Complex SPARCs: sub-sampled DFT design (sparc.py sub_fft :593-646, sparc_transforms
+ * :703-880 with csparc=True) and the AMP decoder on complex observations with K-PSK
+ * modulated sections (sparc_amp :883-999; estimators :402-512, all K branches).
+ * Complex vectors are interleaved (re, im) pairs of the entry point's element type.
+ * order0 / order1 as for lsb_sparc_design_create, entries in [0, w) with
+ * w = 2^ceil(log2(max(Mr + 2, Mc + 2))) (:747).  A section symbol (idx0, out->idx) is
+ * location + M * k, k the index into the K-PSK constellation psk_constel(K) (:225-239);
+ * p->modulation = K (0 or 1: unmodulated). */
+typedef struct lsb_csparc_design lsb_csparc_design;
+int lsb_csparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n, const uint32_t *order0,
+                             const uint32_t *order1, lsb_csparc_design **out);
+void lsb_csparc_design_destroy(lsb_csparc_design *g);
+int lsb_csparc_ab_dev_f32(lsb_csparc_design *g, const void *x /* [F, LM] complex */, void *out /* [F, n] */,
+                          int64_t n_frames, void *stream);
+int lsb_csparc_ab_dev_f64(lsb_csparc_design *g, const void *x, void *out, int64_t n_frames, void *stream);
+int lsb_csparc_az_dev_f32(lsb_csparc_design *g, const void *y /* [F, n] complex */, void *out /* [F, LM] */,
+                          int64_t n_frames, void *stream);
+int lsb_csparc_az_dev_f64(lsb_csparc_design *g, const void *y, void *out, int64_t n_frames, void *stream);
+int lsb_csparc_amp_dev_f32(lsb_csparc_design *g, const void *y /* [F, n] complex */, int64_t n_frames,
+                           const lsb_sparc_amp_params *p, const int32_t *idx0, const lsb_sparc_amp_out *out,
+                           void *stream);
+int lsb_csparc_amp_dev_f64(lsb_csparc_design *g, const void *y, int64_t n_frames, const lsb_sparc_amp_params *p,
+                           const int32_t *idx0, const lsb_sparc_amp_out *out, void *stream);
 
 /* ---------------------------------------------------------------------------
  * State evolution (sparc_public/sparc_se.py).  Replaces sparc_se_E (:82-118):

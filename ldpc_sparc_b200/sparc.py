@@ -15,11 +15,11 @@ libldpcsparc_b200.so:
   returns batched outputs (``beta`` is then the ``[F, L]`` array of decided
   section indices instead of F dense one-hot vectors).
 
-Real SPARCs are built, unmodulated and 2-PSK modulated (``modulated=True, K=2``: the
-non-zero entry of a section is +1 or -1, one extra bit per section).  Complex SPARCs
-(sub-sampled FFT design, K = 4 and K > 4 denoisers, sparc.py:442-459,493-510,593-646)
-are not: they raise NotImplementedError (there is no CPU fallback).  In batched
-outputs a decided section is coded as ``location + M * (value < 0)``.
+Every SPARC type of the reference is built: real designs (sub-sampled DCT), unmodulated
+or 2-PSK modulated, and complex designs (``complex=True``: sub-sampled DFT, sparc.py:593-646)
+with K-PSK modulated sections for any power-of-two K (estimators :402-512).  In batched
+outputs a decided section is coded as the symbol ``location + M * k``, k the index into
+``psk_constel(K)`` (K = 2: k = 1 is the value -1).
 """
 import ctypes as ct
 from copy import copy
@@ -104,10 +104,12 @@ def check_decode_params(decode_params):
 
 
 def _require_real_unmodulated(code_params):
-    """Real designs only; modulation, if any, is 2-PSK (the only real one, sparc.py:117)."""
-    if code_params.get('complex') or (code_params.get('modulated') and code_params.get('K') != 2):
-        raise NotImplementedError(
-            "complex SPARCs (K-PSK with K > 2) are not built in the B200 path yet (no CPU fallback)")
+    """Kept for callers of earlier versions: every SPARC type is built now; a real design still
+    needs K = 2 when modulated (sparc.py:117), and the kernels hold at most 64 constellation points."""
+    if code_params.get('modulated'):
+        assert code_params.get('complex') or code_params.get('K') == 2, 'Real-modulated SPARCs requires K=2'
+        if code_params['K'] > 64:
+            raise NotImplementedError("K-PSK with K > 64 is not built")
 
 
 def _modulation(code_params):
@@ -122,8 +124,8 @@ def bin2gray(num):
 
 def gray2bin(num):
     """Gray -> binary code (reference sparc.py:214-223)."""
-    for shift in (1, 2, 4, 8, 16, 32):      # prefix XOR by doubling
-        num ^= num >> shift
+    for shift in (1, 2, 4, 8, 16, 32):      # prefix XOR by doubling (ints and integer arrays)
+        num = num ^ (num >> shift)
     return num
 
 
@@ -186,39 +188,56 @@ def int_2_bin_arr(integer, arr_length):
 
 
 def section_indices(bin_arr, M, K=1):
-    """Section symbol of every bit group: location (logM bits, MSB first) plus, for K = 2,
-    ``M`` when the value bit that follows is set (value -1; 2-PSK Gray coding is the
-    identity).  ``[..., L*(logM+logK)] -> [..., L]``."""
-    logM = int(round(np.log2(M)))
-    sec = logM + (1 if K == 2 else 0)
+    """Section symbol ``location + M * k`` of every bit group: logM location bits (MSB first)
+    then logK value bits, the Gray code of the constellation index k (psk_mod, sparc.py:241-269).
+    ``[..., L*(logM+logK)] -> [..., L]``."""
+    logM, logK = int(round(np.log2(M))), int(round(np.log2(K)))
+    sec = logM + logK
     b = np.asarray(bin_arr).astype(np.int64)
     assert b.shape[-1] % sec == 0
     b = b.reshape(b.shape[:-1] + (-1, sec))
     idx = b[..., :logM].dot(1 << np.arange(logM)[::-1])
-    return idx + M * b[..., logM] if K == 2 else idx
+    if K == 1:
+        return idx
+    return idx + M * gray2bin(b[..., logM:].dot(1 << np.arange(logK)[::-1]))
 
 
 def indices_2_bin_arr(idx, M, K=1):
     """Inverse of section_indices; ``[..., L] -> [..., L*(logM+logK)]`` bool."""
-    logM = int(round(np.log2(M)))
+    logM, logK = int(round(np.log2(M))), int(round(np.log2(K)))
     idx = np.asarray(idx)
     bits = ((idx % M)[..., None] >> np.arange(logM)[::-1]) & 1
-    if K == 2:
-        bits = np.concatenate([bits, (idx >= M)[..., None].astype(bits.dtype)], axis=-1)
+    if K > 1:
+        bits = np.concatenate([bits, (bin2gray(idx // M)[..., None] >> np.arange(logK)[::-1]) & 1], axis=-1)
     return bits.reshape(idx.shape[:-1] + (-1,)).astype(bool)
 
 
-def _real_only(K):
-    if K not in (1, 2):
-        raise NotImplementedError("complex SPARCs (K-PSK with K > 2) are not built")
+def symbols_2_msg_vector(sym, M, K=1):
+    """Dense message vector(s) of section symbols ``location + M * k``; ``[..., L] -> [..., L*M]``
+    (real for K <= 2, complex otherwise, as the reference's vectors)."""
+    sym = np.asarray(sym)
+    vals = np.ones(sym.shape) if K == 1 else psk_constel(K)[sym // M]
+    out = np.zeros(sym.shape + (M,), dtype=vals.dtype if K > 2 else float)
+    np.put_along_axis(out, (sym % M)[..., None], vals[..., None], axis=-1)
+    return out.reshape(sym.shape[:-1] + (-1,))
+
+
+def msg_vector_2_symbols(msg_vector, M, K=1):
+    """Inverse of symbols_2_msg_vector for vectors with one constellation point per section."""
+    rows = np.asarray(msg_vector).reshape(msg_vector.shape[:-1] + (-1, M))
+    loc = np.abs(rows).argmax(axis=-1)
+    if K == 1:
+        return loc
+    vals = np.take_along_axis(rows, loc[..., None], axis=-1)[..., 0]
+    k = (vals[..., None] * psk_constel(K).conj()).real.argmax(axis=-1)
+    return loc + M * k
 
 
 def rnd_msg_vector(L, M, rand_seed, K=1):
-    """Reference sparc.py:303-328 (K = 1, 2): locations first, then values, from one stream."""
-    _real_only(K)
+    """Reference sparc.py:303-328: locations first, then values, from one stream."""
     rng = np.random.RandomState(rand_seed)
     assert type(M) == int and M > 0 and is_power_of_2(M)
-    msg_vector = np.zeros((L, M))
+    msg_vector = np.zeros((L, M)) if K in (1, 2) else np.zeros((L, M), dtype=complex)
     idxs = rng.randint(0, M, L)
     vals = np.ones(L) if K == 1 else psk_constel(K)[rng.randint(0, K, L)]
     msg_vector[(np.arange(L), idxs)] = vals
@@ -226,19 +245,13 @@ def rnd_msg_vector(L, M, rand_seed, K=1):
 
 
 def bin_arr_2_msg_vector(bin_arr, M, K=1):
-    """Reference sparc.py:330-364 (K = 1, 2): per section logM location bits, then logK value bits."""
-    _real_only(K)
+    """Reference sparc.py:330-364: per section logM location bits, then logK Gray-coded value bits."""
     assert type(M) == int and M > 0 and is_power_of_2(M)
-    idx = section_indices(bin_arr, M, K)
-    loc = idx % M
-    msg_vector = np.zeros(idx.size * M)
-    msg_vector[np.arange(idx.size) * M + loc] = np.where(idx >= M, -1.0, 1.0)
-    return msg_vector
+    return symbols_2_msg_vector(section_indices(bin_arr, M, K), M, K)
 
 
 def msg_vector_2_bin_arr(msg_vector, M, K=1):
-    """Reference sparc.py:366-400 (K = 1, 2)."""
-    _real_only(K)
+    """Reference sparc.py:366-400."""
     assert type(msg_vector) == np.ndarray
     assert type(M) == int and M > 0 and is_power_of_2(M)
     assert msg_vector.size % M == 0
@@ -246,18 +259,24 @@ def msg_vector_2_bin_arr(msg_vector, M, K=1):
     rows = msg_vector.reshape(L, M)
     idxs1, idxs2 = np.nonzero(rows)
     assert np.array_equal(idxs1, np.arange(L))   # exactly 1 nonzero in each row
-    if K == 2:
-        vals = rows[idxs1, idxs2]
-        assert np.all(np.abs(vals) == 1), 'not a constellation symbol'
-        idxs2 = idxs2 + M * (vals < 0)
+    if K > 1:
+        hit = rows[idxs1, idxs2][:, None] == psk_constel(K)[None, :]     # exact match, as psk_demod (:271-299)
+        assert np.all(hit.sum(axis=1) == 1), 'not a constellation symbol'
+        idxs2 = idxs2 + M * hit.argmax(axis=1)
     return indices_2_bin_arr(idxs2, M, K)
 
 
 def msg_vector_map_estimator(s, M, K=1):
     """Reference sparc.py:467-512 (K = 1: one-hot of the per-section argmax; K = 2: the
-    entry of largest magnitude, set to its sign).  (Output formatting on the host;
-    inside ``sparc_amp`` the decision is taken on the GPU.)"""
-    _real_only(K)
+    entry of largest magnitude, set to its sign; K > 2: the (location, symbol) pair with the
+    largest Re(s conj(c_k)), which is what the reference's K = 4 angle rounding and K > 4
+    search both select).  (Output formatting on the host; inside ``sparc_amp`` the decision
+    is taken on the GPU.)"""
+    if K > 2:
+        sm = np.asarray(s).reshape(-1, M)
+        corr = (sm[:, :, None] * psk_constel(K).conj()[None, None, :]).real.reshape(sm.shape[0], -1)
+        best = corr.argmax(axis=1)
+        return symbols_2_msg_vector(best // K + M * (best % K), M, K)
     if K == 2:
         s2 = np.asarray(s).real.reshape(-1, M)
         rows = np.arange(s2.shape[0])
@@ -315,13 +334,15 @@ def create_base_matrix(P, power_allocated=False, spatially_coupled=False, **kwar
 
 # ----------------------------------------------------------- design + operators
 class Design:
-    """Sub-sampled DCT design matrix: host description + device handle.
+    """Sub-sampled DCT (real) or DFT (``csparc``) design matrix: host description + device handle.
 
     Orderings are drawn exactly as the reference's generate_ordering
-    (sparc.py:735-775): one ``RandomState(rand_seed)``, two ``arange(1, w)`` arrays
-    shuffled in place, cumulatively, once per non-zero block."""
+    (sparc.py:735-775): one ``RandomState(rand_seed)``, two index arrays (``arange(1, w)``;
+    for the DFT design ``arange(w)`` without 0 and w/2) shuffled in place, cumulatively,
+    once per non-zero block."""
 
-    def __init__(self, W, L, M, n, rand_seed):
+    def __init__(self, W, L, M, n, rand_seed, csparc=False):
+        self.csparc = bool(csparc)
         assert type(W) == np.ndarray
         assert type(L) == int and type(M) == int and type(n) == int
         assert L > 0 and M > 0 and n > 0
@@ -340,9 +361,14 @@ class Design:
         self.Wm = np.ascontiguousarray(Wm)
         self.Lr, self.Lc = Wm.shape
         self.Mr, self.Mc = n // self.Lr, L * M // self.Lc
-        self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 1, self.Mc + 1))))
-        idxs0 = np.arange(1, self.w, dtype=np.uint32)
-        idxs1 = np.arange(1, self.w, dtype=np.uint32)
+        if not self.csparc:
+            self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 1, self.Mc + 1))))
+            idxs0 = np.arange(1, self.w, dtype=np.uint32)
+            idxs1 = np.arange(1, self.w, dtype=np.uint32)
+        else:
+            self.w = 2 ** int(np.ceil(np.log2(max(self.Mr + 2, self.Mc + 2))))
+            idxs0 = np.delete(np.arange(self.w, dtype=np.uint32), [0, self.w // 2])
+            idxs1 = np.delete(np.arange(self.w, dtype=np.uint32), [0, self.w // 2])
         rng = np.random.RandomState(rand_seed)
         self.order0 = np.zeros((self.Lr, self.Lc, self.Mr), dtype=np.uint32)
         self.order1 = np.zeros((self.Lr, self.Lc, self.Mc), dtype=np.uint32)
@@ -359,7 +385,8 @@ class Design:
         if self._handle is None:
             _lib.require_device()
             h = ct.c_void_p()
-            rc = _lib.lib().lsb_sparc_design_create(
+            create = _lib.lib().lsb_csparc_design_create if self.csparc else _lib.lib().lsb_sparc_design_create
+            rc = create(
                 self.Wm.ctypes.data_as(_lib.c_f64p), self.Lr, self.Lc, self.L, self.M, self.n,
                 self.order0.ctypes.data_as(_lib.c_u32p), self.order1.ctypes.data_as(_lib.c_u32p), ct.byref(h))
             if rc == -1 and "transform size" in _lib.last_error():
@@ -371,7 +398,8 @@ class Design:
     def __del__(self):
         try:
             if getattr(self, "_handle", None) is not None:
-                _lib.lib().lsb_sparc_design_destroy(self._handle)
+                destroy = _lib.lib().lsb_csparc_design_destroy if self.csparc else _lib.lib().lsb_sparc_design_destroy
+                destroy(self._handle)
                 self._handle = None
         except Exception:
             pass
@@ -381,6 +409,8 @@ class Design:
         ``vec`` is ``[len]`` or ``[F, len]``; numpy in -> float64 numpy out, CUDA
         tensor in -> tensor out."""
         import torch
+        if self.csparc:
+            return self._apply_complex(vec, transpose, precision)
         n_in = self.n if transpose else self.L * self.M
         n_out = self.L * self.M if transpose else self.n
         is_tensor = isinstance(vec, torch.Tensor)
@@ -405,6 +435,33 @@ class Design:
         return out if is_tensor else out.cpu().numpy().astype(np.float64)
 
 
+    def _apply_complex(self, vec, transpose, precision):
+        """DFT design: A @ vec or A^H @ vec on complex vectors (real input is promoted)."""
+        import torch
+        n_in = self.n if transpose else self.L * self.M
+        n_out = self.L * self.M if transpose else self.n
+        is_tensor = isinstance(vec, torch.Tensor)
+        dt = torch.complex128 if precision == "fp64" else torch.complex64
+        if is_tensor:
+            x = vec.to(dt)
+        else:
+            _lib.require_device()
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(vec, dtype=np.complex128))).to("cuda").to(dt)
+        single = x.dim() == 1
+        assert x.shape[-1] == n_in, "x must be %d long" % n_in
+        x = x.reshape(-1, n_in).contiguous()
+        out = torch.empty((x.shape[0], n_out), dtype=dt, device=x.device)
+        L_ = _lib.lib()
+        fn = {(False, "fp32"): L_.lsb_csparc_ab_dev_f32, (False, "fp64"): L_.lsb_csparc_ab_dev_f64,
+              (True, "fp32"): L_.lsb_csparc_az_dev_f32, (True, "fp64"): L_.lsb_csparc_az_dev_f64}[(transpose, precision)]
+        with torch.cuda.device(x.device):
+            _lib.check(fn(self.handle(), x.data_ptr(), out.data_ptr(), x.shape[0],
+                          torch.cuda.current_stream().cuda_stream), "lsb_csparc_ab/az")
+        if single:
+            out = out[0]
+        return out if is_tensor else out.cpu().numpy().astype(np.complex128)
+
+
 class _Operator:
     """Callable returned by sparc_transforms: ``Ab(x)`` / ``Az(y)`` (sparc.py:786-875)."""
 
@@ -417,10 +474,9 @@ class _Operator:
 
 def sparc_transforms(W, L, M, n, rand_seed, csparc=False):
     """Returns ``Ab(x)`` (A times x, x of length L*M) and ``Az(y)`` (A transpose
-    times y, y of length n) for the sub-sampled DCT design (reference sparc.py:703-880)."""
-    if csparc:
-        raise NotImplementedError("complex SPARCs (sub-sampled FFT design) are not built")
-    design = Design(W, L, M, n, rand_seed)
+    times y -- conjugate transpose for ``csparc`` --, y of length n) for the sub-sampled DCT
+    design or, with ``csparc``, the sub-sampled DFT design (reference sparc.py:703-880)."""
+    design = Design(W, L, M, n, rand_seed, csparc)
     return _Operator(design, False), _Operator(design, True)
 
 
@@ -477,16 +533,20 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
         raise TypeError("Ab/Az must come from this module's sparc_transforms / sparc_encode "
                         "(arbitrary Python closures cannot run on the GPU)")
     design = Ab.design
+    cplx = design.csparc
     precision = precision or DEFAULT_PRECISION
-    dt = torch.float64 if precision == "fp64" else torch.float32
-    np_dt = np.float64 if precision == "fp64" else np.float32
+    if cplx:
+        dt = torch.complex128 if precision == "fp64" else torch.complex64
+    else:
+        dt = torch.float64 if precision == "fp64" else torch.float32
 
     is_tensor = isinstance(y, torch.Tensor)
     if is_tensor:
         yt = y.to(dt)
     else:
         _lib.require_device()
-        yt = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64))).to("cuda").to(dt)
+        host = np.asarray(y, dtype=np.complex128 if cplx else np.float64)
+        yt = torch.from_numpy(np.ascontiguousarray(host)).to("cuda").to(dt)
     single = yt.dim() == 1
     assert yt.shape[-1] == n
     yt = yt.reshape(-1, n).contiguous()
@@ -499,10 +559,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     elif beta0 is not None:
         b0 = beta0.cpu().numpy() if isinstance(beta0, torch.Tensor) else np.asarray(beta0)
         if b0.shape[-1] == L * M:                       # dense message vector(s), as the reference passes
-            dense = b0.reshape(-1, L, M)
-            b0 = np.abs(dense).argmax(axis=2)
-            if K == 2:
-                b0 = b0 + M * (np.take_along_axis(dense, b0[..., None], axis=2)[..., 0] < 0)
+            b0 = msg_vector_2_symbols(b0.reshape(-1, L * M), M, K)
         b0 = np.broadcast_to(b0.reshape(-1, L), (F, L)) if b0.reshape(-1, L).shape[0] in (1, F) else None
         if b0 is not None:
             idx0 = torch.from_numpy(np.array(b0, dtype=np.int32)).to(dev)
@@ -523,7 +580,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method), int(K), 0)
     ptr = lambda t: t.data_ptr() if t is not None else None
     out = _lib.AmpOut(ptr(idx), ptr(t_final), ptr(psi), ptr(nmse), ptr(beta_soft), ptr(s_last), ptr(tau_tr), ptr(psi_tr))
-    fn = _lib.lib().lsb_sparc_amp_dev_f64 if precision == "fp64" else _lib.lib().lsb_sparc_amp_dev_f32
+    fn = getattr(_lib.lib(), "lsb_%s_amp_dev_%s" % ("csparc" if cplx else "sparc", "f64" if precision == "fp64" else "f32"))
     with torch.cuda.device(dev):
         _lib.check(fn(design.handle(), yt.data_ptr(), F, ct.byref(params), ptr(idx0), ct.byref(out),
                       torch.cuda.current_stream().cuda_stream), "lsb_sparc_amp_dev")
@@ -549,8 +606,7 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
         nm = nm[:, :, 0]
     extra = {k: v.cpu().numpy() for k, v in extra.items()}
     if single:
-        beta = np.zeros((L, M))
-        beta[np.arange(L), idx_np[0] % M] = np.where(idx_np[0] >= M, -1.0, 1.0)
+        beta = symbols_2_msg_vector(idx_np[0], M, K).reshape(L, M)
         psi_out = psi_np[0, 0] if W.ndim == 0 else psi_np[0]
         res = (beta.ravel(), int(t_np[0]), nm[0], psi_out)
         extra = {k: v[0] for k, v in extra.items()}
@@ -572,8 +628,10 @@ def sparc_decode(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=N
         logM = int(round(np.log2(M)))
         shifts = torch.arange(logM - 1, -1, -1, device=beta.device, dtype=torch.int32)
         bits_out = (((beta % M).unsqueeze(-1) >> shifts) & 1)
-        if K == 2:                                      # value bit after the location bits
-            bits_out = torch.cat([bits_out, (beta >= M).unsqueeze(-1).to(bits_out.dtype)], dim=-1)
+        if K > 1:                                       # Gray-coded value bits after the location bits
+            k = beta // M
+            kshifts = torch.arange(int(round(np.log2(K))) - 1, -1, -1, device=beta.device, dtype=torch.int32)
+            bits_out = torch.cat([bits_out, (((k ^ (k >> 1)).unsqueeze(-1) >> kshifts) & 1)], dim=-1)
         return bits_out.reshape(beta.shape[0], -1).bool(), beta, t_final, nmse, expect_err
     if beta.ndim == 1 and beta.size == code_params['L'] * M:      # single frame: dense beta
         expect_err = psi.mean() >= 0.001

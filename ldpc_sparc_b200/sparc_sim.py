@@ -16,15 +16,15 @@ from . import montecarlo, sparc
 
 # ------------------------------------------------------------------ reference API
 def awgn_channel(input_array, awgn_var, rand_seed):
-    """x + N(0, awgn_var) (sparc_sim.py:179-204; real inputs)."""
+    """x + N(0, awgn_var), real or circularly-symmetric complex (sparc_sim.py:179-204)."""
     assert input_array.ndim == 1, 'input array must be one-dimensional'
     assert awgn_var >= 0
     rng = np.random.RandomState(rand_seed)
     n = input_array.size
     if input_array.dtype == float:
         return input_array + np.sqrt(awgn_var) * rng.randn(n)
-    if input_array.dtype == complex:
-        raise NotImplementedError("complex SPARCs (sub-sampled FFT design) are not built")
+    if input_array.dtype == complex:            # awgn_var / 2 per dimension
+        return input_array + np.sqrt(awgn_var / 2) * (rng.randn(n) + 1j * rng.randn(n))
     raise Exception("Unknown input type '{}'".format(input_array.dtype))
 
 
@@ -110,8 +110,9 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
     sparc._require_real_unmodulated(code_params)
     R, L, M = map(code_params.get, ['R', 'L', 'M'])
     K = sparc._modulation(code_params)
-    logM = int(round(np.log2(M)))
-    bit_len = L * (logM + (K == 2))
+    cplx = code_params['complex']
+    logM, logK = int(round(np.log2(M))), int(round(np.log2(K)))
+    bit_len = L * (logM + logK)
     tmp = code_params.copy()
     tmp.update({'awgn_var': awgn_var})
     W = sparc.create_base_matrix(**tmp)
@@ -124,23 +125,33 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
     rank, world = montecarlo._rank_world()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    dt = torch.float64 if precision == "fp64" else torch.float32
+    rdt = torch.float64 if precision == "fp64" else torch.float32
+    dt = rdt if not cplx else (torch.complex128 if precision == "fp64" else torch.complex64)
     counters = torch.zeros(len(BATCH_FIELDS), dtype=torch.int64, device=device)
     ranges = montecarlo.chunk_ranges(n_frames, chunk)
-    shifts = torch.arange(logM + (K == 2), device=device, dtype=torch.int32)
+    shifts = torch.arange(logM + logK, device=device, dtype=torch.int32)
+    constel = torch.as_tensor(np.asarray(sparc.psk_constel(K) if K > 1 else np.ones(1)), device=device).to(dt)
+
+    def bit_pattern(sym):          # location bits, then the Gray code of the constellation index
+        k = sym // M
+        return ((sym % M) << logK) | (k ^ (k >> 1))
+
     for c in montecarlo.shard_chunks(len(ranges), rank, world):
         _, nf = ranges[c]
         gen = torch.Generator(device=device).manual_seed(montecarlo.chunk_seed(seed, 0, c))
-        idx0 = torch.randint(0, K * M, (nf, L), device=device, generator=gen, dtype=torch.int32)   # location + M * (value < 0)
+        idx0 = torch.randint(0, K * M, (nf, L), device=device, generator=gen, dtype=torch.int32)   # location + M * k
         beta0 = torch.zeros((nf, L * M), dtype=dt, device=device)
-        beta0.view(nf, L, M).scatter_(2, (idx0 % M).long().unsqueeze(-1),
-                                      torch.where(idx0 >= M, -1.0, 1.0).to(dt).unsqueeze(-1))
+        beta0.view(nf, L, M).scatter_(2, (idx0 % M).long().unsqueeze(-1), constel[(idx0 // M).long()].unsqueeze(-1))
         x = Ab(beta0, precision)
         del beta0
-        y = x + float(np.sqrt(awgn_var)) * torch.randn((nf, n), device=device, generator=gen, dtype=dt)
+        if cplx:                                                    # awgn_var / 2 per dimension
+            noise = torch.view_as_complex(torch.randn((nf, n, 2), device=device, generator=gen, dtype=rdt))
+            y = x + float(np.sqrt(awgn_var / 2)) * noise
+        else:
+            y = x + float(np.sqrt(awgn_var)) * torch.randn((nf, n), device=device, generator=gen, dtype=dt)
         _, idx, t_final, _, expect = sparc.sparc_decode(y, code_params, decode_params, awgn_var, list(rand_seed),
                                                         idx0, Ab, Az, precision=precision)
-        diff = idx ^ idx0                                           # M is a power of two: the value bit is bit logM
+        diff = bit_pattern(idx) ^ bit_pattern(idx0)
         bit_err = ((diff.unsqueeze(-1) >> shifts) & 1).sum(dim=(1, 2))
         frame_err = bit_err > 0
         counters[0] += bit_err.sum()

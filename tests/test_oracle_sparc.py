@@ -110,8 +110,8 @@ def test_code_params_semantics():
     assert dp == dict(t_max=25, rtol=1e-6, phi_est_method=1)
     with pytest.raises(Exception, match="Need decode parameters"):
         sparc.check_decode_params({})
-    with pytest.raises(NotImplementedError):
-        sparc.sparc_encode(dict(P=15.0, R=1.5, L=64, M=8, complex=True), 1.0, [1, 2])
+    with pytest.raises(AssertionError, match="K=2"):                # a real design modulates with 2-PSK only
+        sparc.sparc_encode(dict(P=15.0, R=1.5, L=64, M=8, modulated=True, K=4), 1.0, [1, 2])
 
 
 @pytest.mark.reference

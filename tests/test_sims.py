@@ -79,8 +79,9 @@ def test_modulated_bit_maps_and_error_rates():
     s = np.array([0.1, -3.0, 0.5, 2.0, 0.2, 0.1, 0.0, -0.1, 1.0, 0.3, 0.2, 0.1, 0.0, 0.0, 0.0, 0.9])
     assert np.array_equal(np.flatnonzero(sparc.msg_vector_map_estimator(s, 8, 2)), [1, 8])
     assert sparc.msg_vector_map_estimator(s, 8, 2)[1] == -1
-    with pytest.raises(NotImplementedError):
-        sparc.bin_arr_2_msg_vector(bits, 8, 4)
+    v4 = sparc.bin_arr_2_msg_vector(np.array([1, 0, 1, 1, 1, 0, 1, 1, 0, 1], dtype=bool), 8, 4)   # value bits 11 -> Gray index 2
+    assert v4.dtype == complex and v4[5] == -1 and v4[8 + 3] == 1j                                 # 01 -> index 1 -> +i
+    assert np.array_equal(sparc.msg_vector_2_symbols(v4, 8, 4), [5 + 8 * 2, 3 + 8 * 1])
     beta0 = np.zeros(12)
     beta0[[1, 4, 10]] = [1, -1, 1]
     beta = np.zeros(12)

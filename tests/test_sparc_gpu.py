@@ -290,3 +290,96 @@ def test_k2_dropin_bits_and_sim(gold_mod):
                                     chunk=128)
     assert out["frames"] == 384 and out["n"] == 1182 and out["ser"] < 2e-3
     assert out["section_errors"] <= out["bit_errors"] <= 6 * out["section_errors"]
+
+
+# ---------------------------------------------------------------- complex designs (sub-sampled DFT, K-PSK)
+@pytest.fixture(scope="module")
+def gold_cplx():
+    g = np.load(os.path.join(GOLDEN, "sparc_complex_reference.npz"))
+    return g, json.loads(str(g["meta_json"]))
+
+
+def test_complex_operators_match_dense_and_golden(gold_cplx):
+    import sparc_oracle as so
+    rng = np.random.RandomState(0)
+    for W, L, M, n in ((np.array(3.0), 8, 8, 20), (so.sc_basic(np.array(2.0), 2, 3), 6, 8, 32),
+                       (np.array([1.0, 2.0, 0.5, 3.0]), 64, 16, 300)):
+        d = sparc.Design(W, L, M, n, [3, 4], csparc=True)
+        ref = so.Design(W, L, M, n, [3, 4], csparc=True)
+        assert d.w == ref.w and np.array_equal(d.order0, ref.order0) and np.array_equal(d.order1, ref.order1)
+        x = rng.randn(3, L * M) + 1j * rng.randn(3, L * M)
+        y = rng.randn(3, n) + 1j * rng.randn(3, n)
+        for prec, tol in (("fp64", 1e-12), ("fp32", 2e-6)):
+            ab, az = d.apply(x, False, prec), d.apply(y, True, prec)
+            for f in range(3):
+                assert np.max(np.abs(ab[f] - ref.Ab(x[f]))) <= tol * np.max(np.abs(ref.Ab(x[f])))
+                assert np.max(np.abs(az[f] - ref.Az(y[f]))) <= tol * np.max(np.abs(ref.Az(y[f])))
+    g, meta = gold_cplx                                   # encoder output of the reference itself
+    m = meta["c_k4_pa"]
+    cp = dict(m["code_params"])
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], m["seeds"][0])
+    assert np.array_equal(bits_in, g["c_k4_pa_s0_bits_in"]) and cp["n"] == int(g["c_k4_pa_s0_n"])
+    assert np.max(np.abs(x - g["c_k4_pa_s0_x"])) < 1e-10 * np.max(np.abs(x))
+
+
+@pytest.mark.parametrize("name", ["c_k1", "c_k2", "c_k4_pa", "c_k8_sc_m16"])
+def test_complex_amp_fp64_matches_reference_golden(gold_cplx, name):
+    g, meta = gold_cplx
+    for si in range(2):
+        pre, cp, dp, (beta, t_final, nmse, psi, ex) = _decode_case(g, meta, name, si, "fp64")
+        K = cp["K"] if cp["modulated"] else 1
+        T = int(g[pre + "t_final"])
+        assert t_final == T
+        assert np.array_equal(sparc.msg_vector_2_symbols(beta, cp["M"], K), g[pre + "sym"])     # locations and PSK symbols exact
+        assert beta.dtype == (complex if K > 2 else float)
+        assert rel_err(ex["tau"][:T], g[pre + "tau_it"]) < 1e-9
+        ref_psi = g[pre + "psi_it"]
+        assert np.max(np.abs(ex["psi"][:T] - ref_psi)) <= 1e-9 * np.max(np.abs(ref_psi)) + 1e-13
+        assert np.max(np.abs(ex["s"] - g[pre + "s_last"])) <= 2e-6 * np.max(np.abs(g[pre + "s_last"]))
+        assert np.max(np.abs(ex["beta_soft"] - g[pre + "beta_soft"])) < 1e-6
+        assert np.allclose(nmse, g[pre + "nmse"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["c_k1", "c_k2", "c_k4_pa", "c_k8_sc_m16"])
+def test_complex_amp_fp32_matches_reference_golden(gold_cplx, name):
+    g, meta = gold_cplx
+    for si in range(2):
+        pre, cp, dp, (beta, t_final, nmse, psi, ex) = _decode_case(g, meta, name, si, "fp32")
+        K = cp["K"] if cp["modulated"] else 1
+        T = int(g[pre + "t_final"])
+        sym = sparc.msg_vector_2_symbols(beta, cp["M"], K)
+        if name in ("c_k1", "c_k2"):                      # converged frames: decisions exact
+            assert np.array_equal(sym, g[pre + "sym"])
+        else:                                             # frames that end above capacity: undecided sections may flip
+            assert np.mean(sym != g[pre + "sym"]) < 0.02
+        assert T - 1 <= t_final <= dp["t_max"] - 1, (t_final, T)
+        Tc = min(T, t_final)
+        assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < 1e-4
+        ref_psi = g[pre + "psi_it"][:Tc]
+        assert np.all(np.abs(ex["psi"][:Tc] - ref_psi) <= 1e-4 * ref_psi + 1e-6)
+
+
+def test_complex_dropin_decode_and_sims(gold_cplx):
+    from ldpc_sparc_b200 import sparc_sim
+    g, meta = gold_cplx
+    for name in ("c_k4_pa", "c_k8_sc_m16"):
+        m = meta[name]
+        seed = m["seeds"][1]
+        pre = "%s_s1_" % name
+        cp, dp = dict(m["code_params"]), dict(m["decode_params"])
+        bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], seed)
+        bits_o, beta, T, nmse, expect = sparc.sparc_decode(g[pre + "y"], cp, dp, m["awgn_var"], seed, beta0, Ab, Az,
+                                                           precision="fp64")
+        assert np.array_equal(bits_o, g[pre + "bits_out"]) and T == int(g[pre + "t_final"])
+        assert bool(expect) == bool(g[pre + "expect_err"])
+        y2 = np.stack([g[pre + "y"], g[pre + "y"][::-1].copy()])
+        bits_b, sym_b, T_b, _, _ = sparc.sparc_decode(y2, cp, dp, m["awgn_var"], seed, beta0, Ab, Az, precision="fp64")
+        assert np.array_equal(bits_b[0], bits_o) and np.array_equal(sym_b[0], g[pre + "sym"]) and T_b[0] == T
+        res = sparc_sim.sparc_sim(dict(m["code_params"]), dict(m["decode_params"]), m["awgn_var"], seed, precision="fp64")
+        assert res["ber"] == np.count_nonzero(g[pre + "bits_in"] ^ g[pre + "bits_out"]) / bits_in.size
+        assert res["num_of_sec_errs"] == int((g[pre + "sym"] != g[pre + "sym0"]).sum())
+        assert res["num_of_loc_errs"] == int((g[pre + "sym"] % cp["M"] != g[pre + "sym0"] % cp["M"]).sum())
+    out = sparc_sim.sparc_sim_batch(dict(P=15.0, R=2.0, L=256, M=32, complex=True, modulated=True, K=4), dict(t_max=25),
+                                    1.0, 256, chunk=128)
+    assert out["frames"] == 256 and out["ser"] < 5e-3
+    assert out["section_errors"] <= out["bit_errors"] <= 7 * out["section_errors"]
