@@ -314,12 +314,17 @@ int lsb_csparc_amp_dev_f64(lsb_csparc_design *g, const void *y, int64_t n_frames
  * State evolution (sparc_public/sparc_se.py).  Replaces sparc_se_E (:82-118):
  *   E[t] = mean over the mc_samples rows of u [mc_samples, M] (device, standard
  *   normals, row-major) of A / (A + sum_{j>=1} C_j) at noise level tau[t], K = 1
- *   (exp) or real K = 2 (sinh / cosh).  tau and E are HOST arrays of n_tau
+ *   (exp) or K = 2 (sinh / cosh).  tau and E are HOST arrays of n_tau
  *   entries (the column blocks of one iteration); the call returns after the
  *   stream has finished.  sparc_se's outer recursion (:120-183) stays on the host. */
 int lsb_sparc_se_expect_f64(const double *u_dev, int64_t mc_samples, int M, int K, const double *tau_host,
                             int n_tau, double *E_host, void *stream);
 int lsb_sparc_se_expect_f32(const float *u_dev, int64_t mc_samples, int M, int K, const double *tau_host,
+                            int n_tau, double *E_host, void *stream);
+/* complex samples u [mc_samples, M] of interleaved (re, im), K-PSK with K = 4 .. 64 (:100-113) */
+int lsb_sparc_se_expect_c128(const double *u_dev, int64_t mc_samples, int M, int K, const double *tau_host,
+                             int n_tau, double *E_host, void *stream);
+int lsb_sparc_se_expect_c64(const float *u_dev, int64_t mc_samples, int M, int K, const double *tau_host,
                             int n_tau, double *E_host, void *stream);
 
 #ifdef __cplusplus

@@ -91,6 +91,8 @@ SIGNATURES = {
     # state evolution
     "lsb_sparc_se_expect_f64": (ct.c_int, [ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, c_f64p, ct.c_int, c_f64p, ct.c_void_p]),
     "lsb_sparc_se_expect_f32": (ct.c_int, [ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, c_f64p, ct.c_int, c_f64p, ct.c_void_p]),
+    "lsb_sparc_se_expect_c128": (ct.c_int, [ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, c_f64p, ct.c_int, c_f64p, ct.c_void_p]),
+    "lsb_sparc_se_expect_c64": (ct.c_int, [ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, c_f64p, ct.c_int, c_f64p, ct.c_void_p]),
 }
 _VP = ct.c_void_p
 for _suf in ("f32", "f64"):

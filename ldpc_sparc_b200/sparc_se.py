@@ -4,8 +4,8 @@
 The recursion over iterations is a handful of scalars per step and stays on the host;
 the Monte-Carlo expectation over ``mc_samples x M`` Gaussians (all of the reference's
 run time) is one kernel launch per iteration covering every column block
-(csrc/sparc_se.cu).  Built for K = 1 and real K = 2; complex / K > 2 designs raise
-NotImplementedError, as in the rest of the package.  No CPU fallback.
+(csrc/sparc_se.cu), for every SPARC type of the reference (real or complex design,
+K-PSK with K up to 64).  No CPU fallback.
 
 As in the reference (sparc_se.py:150-153) the samples come from NumPy's global generator
 (``np.random.randn``) and are drawn once per call, so ``np.random.seed(s)`` before the call
@@ -70,17 +70,23 @@ class _Samples:
         import torch
         _lib.require_device()
         u = np.ascontiguousarray(u)
-        if np.iscomplexobj(u):
-            raise NotImplementedError("complex SPARCs (K > 2) are not built")
+        self.cplx = np.iscomplexobj(u)
         self.mc, self.M = u.shape
         self.f32 = precision == "fp32"
-        self.dev = torch.from_numpy(u).to("cuda").to(torch.float32 if self.f32 else torch.float64).contiguous()
+        if self.cplx:
+            dt = torch.complex64 if self.f32 else torch.complex128
+        else:
+            dt = torch.float32 if self.f32 else torch.float64
+        self.dev = torch.from_numpy(u).to("cuda").to(dt).contiguous()
 
     def expect(self, taus, K):
         import torch
         taus = np.ascontiguousarray(np.atleast_1d(np.asarray(taus, dtype=np.float64)))
         E = np.empty_like(taus)
-        fn = _lib.lib().lsb_sparc_se_expect_f32 if self.f32 else _lib.lib().lsb_sparc_se_expect_f64
+        if (K > 2) != self.cplx:
+            raise ValueError("K > 2 needs complex samples, K <= 2 real ones (sparc_se.py:150-153)")
+        name = {(False, False): "f64", (False, True): "f32", (True, False): "c128", (True, True): "c64"}[(self.cplx, self.f32)]
+        fn = getattr(_lib.lib(), "lsb_sparc_se_expect_" + name)
         with torch.cuda.device(self.dev.device):
             _lib.check(fn(self.dev.data_ptr(), self.mc, self.M, int(K), taus.ctypes.data_as(_lib.c_f64p), taus.size,
                           E.ctypes.data_as(_lib.c_f64p), torch.cuda.current_stream().cuda_stream), "lsb_sparc_se_expect")
@@ -89,8 +95,6 @@ class _Samples:
 
 def sparc_se_E(tau, K, u, precision="fp64"):
     """Monte-Carlo estimate of E[beta_1-hat] at noise level ``tau`` (sparc_se.py:82-118)."""
-    if K not in (1, 2):
-        raise NotImplementedError("state evolution is built for K = 1 and real K = 2")
     s = u if isinstance(u, _Samples) else _Samples(u, precision)
     return float(s.expect([tau], K)[0])
 
@@ -105,15 +109,21 @@ def sparc_se(awgn_var, code_params, t_max, mc_samples, precision="fp64"):
     assert 0 <= W.ndim <= 2
     P, R, M = map(code_params.get, ['P', 'R', 'M'])
     K = code_params['K'] if code_params['modulated'] else 1
-    if code_params['complex'] or K > 2:
-        raise NotImplementedError("complex / K > 2 SPARCs are not built")
+    if K > 64:
+        raise NotImplementedError("K-PSK with K > 64 is not built")
+    if code_params['complex']:
+        R /= 2                    # complex SPARCs: rate per dimension (sparc_se.py:141-142)
 
     if W.ndim == 0:
         psi = np.ones(t_max)
     else:
         Lr, Lc = (1, W.size) if W.ndim == 1 else W.shape
         psi = np.ones((t_max, Lc))
-    samples = _Samples(np.random.randn(mc_samples, M), precision)
+    if K > 2:                     # must be complex (:150-153); two draws, real parts first
+        u = np.random.randn(mc_samples, M) + 1j * np.random.randn(mc_samples, M)
+    else:
+        u = np.random.randn(mc_samples, M)
+    samples = _Samples(u, precision)
 
     for t in range(t_max - 1):
         if t > 0:

@@ -24,6 +24,11 @@ SE_CASES = {
     "k2": (dict(P=15.0, R=1.3, M=32, modulated=True, K=2), 1.0, 25, 4000, 16),
     "k2_sc_pa": (dict(P=15.0, R=1.4, M=16, modulated=True, K=2, spatially_coupled=True, omega=3, Lambda=8,
                       power_allocated=True, B=2, R_PA_ratio=0.5), 1.0, 20, 3000, 17),
+    "c_k1": (dict(P=15.0, R=2.6, M=32, complex=True), 1.0, 25, 3000, 18),
+    "c_k4_pa": (dict(P=15.0, R=2.8, M=32, complex=True, modulated=True, K=4, power_allocated=True, B=8, R_PA_ratio=0.9),
+                1.0, 25, 2000, 19),
+    "c_k8_sc": (dict(P=15.0, R=3.0, M=16, complex=True, modulated=True, K=8, spatially_coupled=True, omega=3, Lambda=8),
+                1.0, 25, 1500, 20),
 }
 
 

@@ -1,5 +1,5 @@
 """CPU restatement of the reference's state evolution (sparc_public/sparc_se.py) for
-K = 1 and real K = 2.  ORACLE / TEST INFRASTRUCTURE ONLY: imported from tests/ only,
+every K.  ORACLE / TEST INFRASTRUCTURE ONLY: imported from tests/ only,
 never from ldpc_sparc_b200/.  Pinned against the unmodified reference by
 oracle/make_golden_se.py -> tests/golden/se_reference.npz (tests/test_oracle_se.py).
 """
@@ -18,8 +18,18 @@ def se_expectation(tau, K, u):
     elif K == 2:
         a = np.sinh(itau + rtau * u[:, 0])
         c = np.cosh(rtau * u[:, 1:])
+    elif K == 4:
+        a = np.sinh(itau + rtau * u[:, 0].real)
+        b = np.cosh(itau + rtau * u[:, 0].real) + np.cosh(rtau * u[:, 0].imag)
+        c = np.cosh(rtau * u[:, 1:].real) + np.cosh(rtau * u[:, 1:].imag)
+        return (a / (b + c.sum(axis=1))).mean()
     else:
-        raise NotImplementedError
+        from sparc_oracle import psk_constel
+        con = psk_constel(K)
+        tb = np.exp(np.real((itau + rtau * u[:, 0])[None, :] * con.conj()[:, None]))
+        ta = con.real[:, None] * tb
+        tc = np.exp(np.real((rtau * u[:, 1:])[None, :, :] * con.conj()[:, None, None]))
+        return (ta.mean(axis=0) / (tb.mean(axis=0) + tc.mean(axis=0).sum(axis=1))).mean()
     return (a / (a + c.sum(axis=1))).mean()
 
 
@@ -29,6 +39,8 @@ def state_evolution(awgn_var, code_params, t_max, u):
     W = create_base_matrix(**dict(cp, awgn_var=awgn_var))
     P, R, M = cp['P'], cp['R'], cp['M']
     K = cp['K'] if cp.get('modulated') else 1
+    if cp.get('complex'):
+        R = R / 2
     if W.ndim == 0:
         psi = np.ones(t_max)
     else:

@@ -24,13 +24,15 @@ def test_golden_is_finite_and_covers_both_regimes(gold):
     assert g["reg_psi"][-1] < 1e-6 and g["reg_m512_low_snr_psi"][-1] > 0.5     # decodes / stalls
 
 
-@pytest.mark.parametrize("name", ["reg", "reg_m512_low_snr", "pa", "sc", "sc_wave", "k2", "k2_sc_pa"])
+@pytest.mark.parametrize("name", ["reg", "reg_m512_low_snr", "pa", "sc", "sc_wave", "k2", "k2_sc_pa", "c_k1", "c_k4_pa", "c_k8_sc"])
 def test_oracle_matches_reference(gold, name):
     g, meta = gold
     m = meta[name]
     cp = m["code_params"]
     np.random.seed(m["seed"])
-    u = np.random.randn(m["mc_samples"], cp["M"])              # the draw sparc_se.py:153 makes
+    u = np.random.randn(m["mc_samples"], cp["M"])              # the draws sparc_se.py:150-153 make
+    if cp.get("modulated") and cp["K"] > 2:
+        u = u + 1j * np.random.randn(m["mc_samples"], cp["M"])
     psi, tau = so.state_evolution(m["awgn_var"], cp, m["t_max"], u)
     assert psi.shape == g[name + "_psi"].shape
     assert np.allclose(psi, g[name + "_psi"], rtol=1e-12, atol=1e-14)

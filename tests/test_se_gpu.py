@@ -18,7 +18,7 @@ def gold():
     return g, json.loads(str(g["meta_json"]))
 
 
-@pytest.mark.parametrize("name", ["reg", "reg_m512_low_snr", "pa", "sc", "sc_wave", "k2", "k2_sc_pa"])
+@pytest.mark.parametrize("name", ["reg", "reg_m512_low_snr", "pa", "sc", "sc_wave", "k2", "k2_sc_pa", "c_k1", "c_k4_pa", "c_k8_sc"])
 def test_sparc_se_matches_reference_golden(gold, name):
     from ldpc_sparc_b200 import sparc_se
     g, meta = gold
@@ -42,8 +42,18 @@ def test_expectation_matches_oracle_and_survives_small_tau(K):
         assert abs(sparc_se.sparc_se_E(tau, K, u) - so.se_expectation(tau, K, u)) < 1e-12
     # 1 / tau > 709: the reference's exp overflows to nan, the shifted form gives the limit 1
     assert sparc_se.sparc_se_E(1e-3, K, u) == 1.0
-    with pytest.raises(NotImplementedError):
-        sparc_se.sparc_se_E(0.3, 4, u)
+    with pytest.raises(ValueError):
+        sparc_se.sparc_se_E(0.3, 4, u)                                    # K > 2 needs complex samples
+
+
+@pytest.mark.parametrize("K", [4, 8, 16])
+def test_complex_expectation_matches_oracle(K):
+    from ldpc_sparc_b200 import sparc_se
+    rng = np.random.RandomState(6)
+    u = rng.randn(1500, 32) + 1j * rng.randn(1500, 32)
+    for tau in (2.0, 0.3, 0.05):
+        assert abs(sparc_se.sparc_se_E(tau, K, u) - so.se_expectation(tau, K, u)) < 1e-12
+    assert abs(sparc_se.sparc_se_E(0.3, K, u, precision="fp32") - so.se_expectation(0.3, K, u)) < 1e-5
 
 
 def test_large_sample_count_runs_fast():
