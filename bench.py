@@ -200,6 +200,24 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------- main
+def bind_to_gpu_numa(torch, local_rank):
+    """Multi-rank runs: keep this process (and so its pinned host buffers, first-touched by it) on the
+    CPUs NVML reports as local to its GPU; with 8 ranks the host<->device copies of the e2e leg
+    otherwise cross the socket interconnect.  Best effort -- any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        p = torch.cuda.get_device_properties(local_rank)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -216,6 +234,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        bind_to_gpu_numa(torch, local_rank)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     code = ldpc.code("802.11n", "1/2", 81)
@@ -341,6 +360,26 @@ def main():
                       "h2d_bytes_per_step": F * N * 4, "d2h_bytes_per_step": F * N * 4 + F * 4,
                       "ms_per_step": 1e3 * float(te.item()) / n_e2e,
                       "api": "lsb_ldpc_decode_host_f32 (C-ABI, pinned host LLR in, APP + iteration counts out)"}
+
+        # same call returning hard decisions (what a BER Monte-Carlo consumes) instead of APP LLRs:
+        # 4x fewer D2H bytes -- matters once several ranks share the host's PCIe / memory bandwidth
+        h_hard = torch.empty((F, N), dtype=torch.uint8).pin_memory()
+
+        def e2e_hard_step():
+            _lib.check(L.lsb_ldpc_decode_host_f32(g, h_llr.data_ptr(), None, h_hard.data_ptr(), h_it.data_ptr(), F,
+                                                  args.max_it, 0, 1.0), "decode_host")
+
+        e2e_hard_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_hard_step()
+        th = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        out["e2e_hard_decisions"] = {"value": world * F * K * n_e2e / float(th.item()), "unit": "info bits/s",
+                                     "h2d_bytes_per_step": F * N * 4, "d2h_bytes_per_step": F * N + F * 4,
+                                     "ms_per_step": 1e3 * float(th.item()) / n_e2e}
 
     out["clocks"] = clocks.summary()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
