@@ -389,7 +389,9 @@ def main():
         out["extra_workloads"] = {}
         for key, cmd in (("sparc_amp_config1", ["tools/bench_amp.py", "--frames", "4096", "--steps", "2", "--warmup", "1"]),
                          ("dense_amp_config3_tcgen05", ["tools/bench_dense.py", "--precision", "tc", "--frames", "1024",
-                                                        "--steps", "2", "--warmup", "1"])):
+                                                        "--steps", "2", "--warmup", "1"]),
+                         ("ldpc_sparc_config5", ["tools/bench_c5.py", "--frames", "1024", "--chunk", "1024", "--sims",
+                                                 "SPARC+LDPC", "Integrated_decoder"])):
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], capture_output=True,
                                    text=True, timeout=240, cwd=ROOT)

@@ -325,6 +325,75 @@ onsager_kernel(const T *__restrict__ beta, const T *__restrict__ vk, const T *__
     if (threadIdx.x == 0) out[f] = tot;
 }
 
+// Same sum in closed form for the fp32 modes: with alpha = alpha_w / sqrt_nPl and
+// A_k = sum_{q in S_k} alpha_q, the inner sum over q of the reference collapses to
+//   alpha_i c ([i in S_k] - A_k),
+// so a section costs O(M logM) instead of O(M^2 logM).  G = min(M, 32) lanes
+// share a section (PER = M / G entries each, at most 8), A_k by a shuffle reduction inside
+// the group; one CTA per frame, fixed summation order.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+onsager_closed_kernel(const T *__restrict__ beta, const T *__restrict__ vk, const T *__restrict__ vk0,
+                      const T *__restrict__ alpha_w, const double *tau_sqr, double *out, int L, int M, int logM,
+                      double sqrt_nPl)
+{
+    constexpr int kMaxPer = 8;
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    const T c = (T)(sqrt_nPl / tau_sqr[f]);
+    const T inv_amp = (T)(1.0 / sqrt_nPl);
+    const int G = M < 32 ? M : 32, per = M / G;
+    const int gl = threadIdx.x % G;                       // lane inside the section's group
+    const int groups = kThreads / G;
+    double part = 0.0;
+    for (int l0 = 0; l0 < L; l0 += groups) {
+        const int l = l0 + threadIdx.x / G;
+        const bool live = l < L;                          // whole groups are live or not: shuffles stay inside a group
+        const size_t base = f * (size_t)L * M + (size_t)(live ? l : 0) * M;
+        T a[kMaxPer], acc[kMaxPer];
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u) {
+            a[u] = (live && u < per) ? alpha_w[base + gl + u * G] * inv_amp : (T)0;
+            acc[u] = (T)0;
+        }
+        for (int k = 0; k < logM; ++k) {
+            const int shift = logM - 1 - k;
+            T Ak = (T)0;
+#pragma unroll
+            for (int u = 0; u < kMaxPer; ++u)
+                if (u < per && !(((gl + u * G) >> shift) & 1)) Ak += a[u];
+            for (int o = G >> 1; o > 0; o >>= 1) Ak += __shfl_xor_sync(0xffffffffu, Ak, o);
+            const size_t bi = f * (size_t)L * logM + (size_t)(live ? l : 0) * logM + k;
+            const double v0 = fmin(fmax((double)vk0[bi], 1e-10), 1.0 - 1e-10);     // clip in fp64, as onsager_kernel
+            const T sub = (T)(1.0 / (v0 * (1.0 - v0)));
+            const T v = vk[bi];
+#pragma unroll
+            for (int u = 0; u < kMaxPer; ++u) {
+                const bool one = ((gl + u * G) >> shift) & 1;
+                acc[u] += (one ? -v : (T)1 - v) * sub * ((one ? (T)0 : (T)1) - Ak);
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int u = 0; u < kMaxPer; ++u)
+                if (u < per) part += (double)(beta[base + gl + u * G] * (c * a[u] * acc[u]));
+        }
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) out[f] = tot;
+}
+
+template <typename T>
+void launch_onsager(const T *beta, const T *vk, const T *vk0, const T *alpha_w, const double *tau_sqr, double *out,
+                    int64_t F, int L, int M, int logM, double sqrt_nPl, cudaStream_t st)
+{
+    // fp64 is the parity mode and keeps the reference's operation order; fp32 takes the closed form
+    if (sizeof(T) == 4 && M <= 256)
+        onsager_closed_kernel<T><<<(unsigned)F, kThreads, 0, st>>>(beta, vk, vk0, alpha_w, tau_sqr, out, L, M, logM, sqrt_nPl);
+    else
+        onsager_kernel<T><<<(unsigned)F, kThreads, 0, st>>>(beta, vk, vk0, alpha_w, tau_sqr, out, L, M, logM, sqrt_nPl);
+}
+
 }  // namespace
 
 struct lsb_dense_design {
@@ -520,9 +589,8 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
         int logM = 0;                                                                                            \
         while ((1 << logM) < M) ++logM;                                                                          \
         if (F <= 0) return LSB_OK;                                                                               \
-        onsager_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta, vk, vk0, alpha_weighted,     \
-                                                                              tau_sqr, out, L, M, logM,         \
-                                                                              sqrt_nPl);                        \
+        launch_onsager<T>(beta, vk, vk0, alpha_weighted, tau_sqr, out, F, L, M, logM, sqrt_nPl,                  \
+                          (cudaStream_t)stream);                                                                 \
         lsb::count_launch();                                                                                     \
         LSB_CUDA(cudaGetLastError());                                                                            \
         return LSB_OK;                                                                                           \

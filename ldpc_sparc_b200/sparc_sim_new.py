@@ -49,6 +49,18 @@ def sparc_ldpc_integrated_sim(sparc_params, ldpc_params, lengths, ldpc_bool, dec
 
 
 # ------------------------------------------------------------------ batched sweep
+_sweep_engines = {}     # (L, M, n, design_seed, precision) -> device-resident design (generation takes seconds)
+
+
+def _sweep_engine(L, M, n, design_seed, precision):
+    key = (L, M, n, design_seed, precision)
+    if key not in _sweep_engines:
+        if len(_sweep_engines) >= 2:
+            _sweep_engines.clear()
+        _sweep_engines[key] = _engine(create_design_matrix(L, M, n, design_seed), precision)
+    return _sweep_engines[key]
+
+
 SIMS = ('SPARC', 'SPARC+LDPC', 'Naive_decoder', 'Integrated_decoder')     # performance_plots_general.py:19
 
 
@@ -75,7 +87,7 @@ def _frames(eng, c, sparc_params, lengths, ldpc_bool, nf, gen):
 
 
 def performance_sweep(sparc_params, sparc_ldpc_params, ldpc_params, lengths, decode_params, snr_store,
-                      frames_per_point, sims=SIMS, seed=0, design_seed=0, chunk=256, precision="tc", save_path=None,
+                      frames_per_point, sims=SIMS, seed=0, design_seed=0, chunk=1024, precision="tc", save_path=None,
                       decode_params_integrated=None):
     """BER of the four schemes of performance_plots_general.py:101-118 at every SNR of
     ``snr_store`` (linear, ``awgn_var = P / snr``), ``frames_per_point`` frames each.
@@ -108,7 +120,7 @@ def performance_sweep(sparc_params, sparc_ldpc_params, ldpc_params, lengths, dec
         if any(runs[s][1] == ldpc_bool for s in sims):
             L, M = sp['L'], sp['M']
             n = int(L * int(np.log2(M)) / sp['R'])
-            engines[ldpc_bool] = _engine(create_design_matrix(L, M, n, design_seed), precision)
+            engines[ldpc_bool] = _sweep_engine(L, M, n, design_seed, precision)
     dev = next(iter(engines.values())).dev
     ranges = montecarlo.chunk_ranges(frames_per_point, chunk)
     mine = montecarlo.shard_chunks(len(ranges), rank, world)

@@ -109,6 +109,9 @@ def test_decoders_fp32_converging_case(gold):
         bits, tau, ons = sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="fp32", return_trace=True)
         assert np.array_equal(bits, g[pre + "bits_integrated"])
         assert np.max(np.abs(tau - g[pre + "int_tau_sqr"]) / g[pre + "int_tau_sqr"]) < 1e-4
+        # Onsager sums (closed-form fp32 kernel) against the reference's nested loops
+        ref_ons = g[pre + "int_onsager_sum"]
+        assert np.max(np.abs(ons - ref_ons)) <= 1e-4 * np.max(np.abs(ref_ons))
 
 
 def test_encode_and_batched_decode(gold):
