@@ -329,55 +329,57 @@ onsager_kernel(const T *__restrict__ beta, const T *__restrict__ vk, const T *__
 // A_k = sum_{q in S_k} alpha_q, the inner sum over q of the reference collapses to
 //   alpha_i c ([i in S_k] - A_k),
 // so a section costs O(M logM) instead of O(M^2 logM).  G = min(M, 32) lanes
-// share a section (PER = M / G entries each, at most 8), A_k by a shuffle reduction inside
-// the group; one CTA per frame, fixed summation order.
-template <typename T>
+// share a section (PER = M / G entries each, compile time, at most 8), A_k by a shuffle
+// reduction inside the group; one CTA per frame, fixed summation order.
+template <typename T, int PER>
 __global__ void __launch_bounds__(kThreads)
 onsager_closed_kernel(const T *__restrict__ beta, const T *__restrict__ vk, const T *__restrict__ vk0,
                       const T *__restrict__ alpha_w, const double *tau_sqr, double *out, int L, int M, int logM,
                       double sqrt_nPl)
 {
-    constexpr int kMaxPer = 8;
     __shared__ double red[kThreads / 32];
     const size_t f = blockIdx.x;
     const T c = (T)(sqrt_nPl / tau_sqr[f]);
     const T inv_amp = (T)(1.0 / sqrt_nPl);
-    const int G = M < 32 ? M : 32, per = M / G;
-    const int gl = threadIdx.x % G;                       // lane inside the section's group
-    const int groups = kThreads / G;
+    const int G = M / PER;                                // lanes per section: M for M <= 32, else 32
+    const int logG = 31 - __clz(G);
+    const int gl = threadIdx.x & (G - 1);                 // lane inside the section's group
+    const int groups = kThreads >> logG;
+    const T *a_f = alpha_w + f * (size_t)L * M, *b_f = beta + f * (size_t)L * M;
+    const T *v_f = vk + f * (size_t)L * logM, *v0_f = vk0 + f * (size_t)L * logM;
     double part = 0.0;
     for (int l0 = 0; l0 < L; l0 += groups) {
-        const int l = l0 + threadIdx.x / G;
+        const int l = l0 + (threadIdx.x >> logG);
         const bool live = l < L;                          // whole groups are live or not: shuffles stay inside a group
-        const size_t base = f * (size_t)L * M + (size_t)(live ? l : 0) * M;
-        T a[kMaxPer], acc[kMaxPer];
+        const int e0 = (live ? l : 0) * M + gl;
+        T a[PER], acc[PER], b[PER];
 #pragma unroll
-        for (int u = 0; u < kMaxPer; ++u) {
-            a[u] = (live && u < per) ? alpha_w[base + gl + u * G] * inv_amp : (T)0;
+        for (int u = 0; u < PER; ++u) {
+            a[u] = live ? a_f[e0 + u * G] * inv_amp : (T)0;
+            b[u] = live ? b_f[e0 + u * G] : (T)0;
             acc[u] = (T)0;
         }
         for (int k = 0; k < logM; ++k) {
             const int shift = logM - 1 - k;
             T Ak = (T)0;
 #pragma unroll
-            for (int u = 0; u < kMaxPer; ++u)
-                if (u < per && !(((gl + u * G) >> shift) & 1)) Ak += a[u];
+            for (int u = 0; u < PER; ++u)
+                if (!(((gl + u * G) >> shift) & 1)) Ak += a[u];
             for (int o = G >> 1; o > 0; o >>= 1) Ak += __shfl_xor_sync(0xffffffffu, Ak, o);
-            const size_t bi = f * (size_t)L * logM + (size_t)(live ? l : 0) * logM + k;
-            const double v0 = fmin(fmax((double)vk0[bi], 1e-10), 1.0 - 1e-10);     // clip in fp64, as onsager_kernel
-            const T sub = (T)(1.0 / (v0 * (1.0 - v0)));
-            const T v = vk[bi];
+            const int bi = (live ? l : 0) * logM + k;
+            // v0 clipped to [1e-10, 1 - 1e-10] (:881): 1 - v0 is formed in fp64 (1 - 1e-10 is not an fp32 number)
+            const T v0 = v0_f[bi];
+            const T lo = fmax(v0, (T)1e-10), hi = fmax((T)(1.0 - (double)v0), (T)1e-10);
+            const T sub = (T)1 / (lo * hi);
+            const T v = v_f[bi];
 #pragma unroll
-            for (int u = 0; u < kMaxPer; ++u) {
+            for (int u = 0; u < PER; ++u) {
                 const bool one = ((gl + u * G) >> shift) & 1;
                 acc[u] += (one ? -v : (T)1 - v) * sub * ((one ? (T)0 : (T)1) - Ak);
             }
         }
-        if (live) {
 #pragma unroll
-            for (int u = 0; u < kMaxPer; ++u)
-                if (u < per) part += (double)(beta[base + gl + u * G] * (c * a[u] * acc[u]));
-        }
+        for (int u = 0; u < PER; ++u) part += (double)(b[u] * (c * a[u] * acc[u]));
     }
     const double tot = block_sum(part, red);
     if (threadIdx.x == 0) out[f] = tot;
@@ -388,10 +390,15 @@ void launch_onsager(const T *beta, const T *vk, const T *vk0, const T *alpha_w, 
                     int64_t F, int L, int M, int logM, double sqrt_nPl, cudaStream_t st)
 {
     // fp64 is the parity mode and keeps the reference's operation order; fp32 takes the closed form
-    if (sizeof(T) == 4 && M <= 256)
-        onsager_closed_kernel<T><<<(unsigned)F, kThreads, 0, st>>>(beta, vk, vk0, alpha_w, tau_sqr, out, L, M, logM, sqrt_nPl);
+#define LSB_ONSAGER_CLOSED(PER) \
+    onsager_closed_kernel<T, PER><<<(unsigned)F, kThreads, 0, st>>>(beta, vk, vk0, alpha_w, tau_sqr, out, L, M, logM, sqrt_nPl)
+    if (sizeof(T) == 4 && M <= 32) LSB_ONSAGER_CLOSED(1);
+    else if (sizeof(T) == 4 && M == 64) LSB_ONSAGER_CLOSED(2);
+    else if (sizeof(T) == 4 && M == 128) LSB_ONSAGER_CLOSED(4);
+    else if (sizeof(T) == 4 && M == 256) LSB_ONSAGER_CLOSED(8);
     else
         onsager_kernel<T><<<(unsigned)F, kThreads, 0, st>>>(beta, vk, vk0, alpha_w, tau_sqr, out, L, M, logM, sqrt_nPl);
+#undef LSB_ONSAGER_CLOSED
 }
 
 }  // namespace
