@@ -389,9 +389,9 @@ int build_operand(TcOperand *op, const double *d_src, int64_t rows, int64_t K)
 
 int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out, int64_t F, cudaStream_t st)
 {
+    if (F == 0) return LSB_OK;                     // an empty batch is valid with any pointers
     LSB_REQUIRE(g && x && out, "null pointer");
     LSB_REQUIRE(F >= 0, "negative frame count");
-    if (F == 0) return LSB_OK;
     int dev = -1;
     LSB_CUDA(cudaGetDevice(&dev));
     LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);

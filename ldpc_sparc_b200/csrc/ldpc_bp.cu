@@ -152,10 +152,10 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
                int64_t n_frames, int max_it, int algo, double scale, cudaStream_t st)
 {
     lsb_ldpc_graph *g = const_cast<lsb_ldpc_graph *>(cg);
+    if (n_frames == 0) return LSB_OK;                  // an empty batch is valid with any pointers
     LSB_REQUIRE(g && llr && iters, "null graph / llr / iters pointer");
     LSB_REQUIRE(n_frames >= 0 && max_it >= 0, "negative n_frames or max_it");
     LSB_REQUIRE(algo >= 0 && algo <= 2, "unknown algo %d", algo);
-    if (n_frames == 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
 
@@ -284,9 +284,9 @@ int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, i
                 int64_t n_frames, int max_it, int algo, double scale, bool compute_f32_from_f64)
 {
     lsb_ldpc_graph *g = const_cast<lsb_ldpc_graph *>(cg);
+    if (n_frames == 0) return LSB_OK;                  // an empty batch is valid with any pointers
     LSB_REQUIRE(g && llr && iters, "null graph / llr / iters pointer");
     LSB_REQUIRE(n_frames >= 0 && max_it >= 0, "negative n_frames or max_it");
-    if (n_frames == 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(g->stage_mu);   // staging buffers are per handle
@@ -544,10 +544,10 @@ void lsb_ldpc_graph_destroy(lsb_ldpc_graph *g)
 int lsb_ldpc_encode_dev(const lsb_ldpc_graph *g, const uint8_t *info, uint8_t *codewords, int64_t n_frames,
                         void *stream)
 {
-    LSB_REQUIRE(g && info && codewords, "null pointer");
+    if (n_frames == 0) return LSB_OK;                  // an empty batch is valid with any pointers
+    LSB_REQUIRE(g && info && codewords && n_frames > 0, "null pointer or negative frame count");
     LSB_REQUIRE(g->is_qc && g->d_proto, "encoding needs a QC graph (lsb_ldpc_graph_create_qc)");
     LSB_REQUIRE(g->enc_toff >= 0, "The offsets in colum Kp+1 of proto do not add to a single offset");
-    if (n_frames <= 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
     const size_t smem = (size_t)(g->cols + g->rows) * g->z;

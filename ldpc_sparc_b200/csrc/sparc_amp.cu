@@ -621,6 +621,7 @@ template <typename T>
 int run_op(const lsb_sparc_design *cg, bool transpose, const T *in, T *out, int64_t n_frames, cudaStream_t st)
 {
     lsb_sparc_design *g = const_cast<lsb_sparc_design *>(cg);
+    if (n_frames == 0) return LSB_OK;              // an empty batch is valid with any pointers
     LSB_REQUIRE(g && in && out, "null pointer");
     LSB_REQUIRE(n_frames >= 0, "negative frame count");
     if (n_frames == 0) return LSB_OK;
@@ -662,6 +663,7 @@ template <typename T>
 int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_amp_params *pp,
             const int32_t *idx0, const lsb_sparc_amp_out *po, cudaStream_t st)
 {
+    if (n_frames == 0) return LSB_OK;              // an empty batch is valid with any pointers
     LSB_REQUIRE(g && y && pp && po && po->idx && po->t_final && po->psi, "null pointer");
     LSB_REQUIRE(pp->t_max > 1, "t_max must be > 1");
     LSB_REQUIRE(pp->phi_est_method == 1 || pp->phi_est_method == 2, "phi_est_method must be 1 or 2");

@@ -456,6 +456,7 @@ template <typename T, bool TRANS>
 int run_cop(lsb_csparc_design *g, const void *in, void *out, int64_t n_frames, cudaStream_t st)
 {
     typedef typename Cplx<T>::type T2;
+    if (n_frames == 0) return LSB_OK;              // an empty batch is valid with any pointers
     LSB_REQUIRE(g && in && out, "null pointer");
     LSB_REQUIRE(n_frames >= 0, "negative frame count");
     if (n_frames == 0) return LSB_OK;
@@ -483,6 +484,7 @@ int run_camp(lsb_csparc_design *g, const void *y, int64_t n_frames, const lsb_sp
              const lsb_sparc_amp_out *po, cudaStream_t st)
 {
     typedef typename Cplx<T>::type T2;
+    if (n_frames == 0) return LSB_OK;              // an empty batch is valid with any pointers
     LSB_REQUIRE(g && y && pp && po && po->idx && po->t_final && po->psi, "null pointer");
     LSB_REQUIRE(pp->t_max > 1, "t_max must be > 1");
     LSB_REQUIRE(pp->phi_est_method == 1 || pp->phi_est_method == 2, "phi_est_method must be 1 or 2");

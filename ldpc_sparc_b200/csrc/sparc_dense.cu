@@ -427,6 +427,7 @@ template <> const double *mat<double>(const lsb_dense_design *g) { return g->d_A
 template <typename T>
 int run_gemm(const lsb_dense_design *g, bool transpose, const T *x, T *out, int64_t F, cudaStream_t st)
 {
+    if (F == 0) return LSB_OK;                     // an empty batch is valid with any pointers
     LSB_REQUIRE(g && x && out, "null pointer");
     LSB_REQUIRE(mat<T>(g), "the design holds no %s copy of A", sizeof(T) == 4 ? "fp32" : "fp64");
     LSB_REQUIRE(F >= 0, "negative frame count");
@@ -523,6 +524,7 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
                                    const double *onsager_sum, double *tau_sqr, int64_t F, int n, double P,       \
                                    int mode, int first, void *stream)                                            \
     {                                                                                                            \
+        if (F <= 0) return LSB_OK;                                                                               \
         LSB_REQUIRE(y && z && tau_sqr && (first || ab), "null pointer");                                         \
         LSB_REQUIRE(first || (mode == 0 ? beta_sq != nullptr : onsager_sum != nullptr), "missing coefficient");  \
         if (F <= 0) return LSB_OK;                                                                               \
@@ -536,6 +538,7 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
                                   const double *tau_sqr, double *beta_sq, int64_t F, int L, int M,               \
                                   double sqrt_nPl, void *stream)                                                 \
     {                                                                                                            \
+        if (F <= 0) return LSB_OK;                                                                               \
         LSB_REQUIRE(beta_out && atz && tau_sqr && beta_sq, "null pointer");                                      \
         LSB_REQUIRE(M >= 2 && M <= 256 && (M & (M - 1)) == 0, "M must be a power of two in [2, 256]");            \
         if (F <= 0) return LSB_OK;                                                                               \
@@ -553,6 +556,7 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
     int lsb_section_to_bit_dev_##SUF(const T *beta, T *probs, T *llr, int64_t n_sections, int M,                 \
                                      double sqrt_nPl, void *stream)                                              \
     {                                                                                                            \
+        if (n_sections <= 0) return LSB_OK;                                                                      \
         LSB_REQUIRE(beta && (probs || llr), "null pointer");                                                     \
         int logM = 0;                                                                                            \
         while ((1 << logM) < M) ++logM;                                                                          \
@@ -568,6 +572,7 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
     int lsb_bit_to_section_dev_##SUF(const T *app, T *probs, T *beta, double *beta_sq, int64_t F, int L, int M,  \
                                      double sqrt_nPl, void *stream)                                              \
     {                                                                                                            \
+        if (F <= 0) return LSB_OK;                                                                               \
         LSB_REQUIRE(app && beta, "null pointer");                                                                \
         int logM = 0;                                                                                            \
         while ((1 << logM) < M) ++logM;                                                                          \
@@ -580,6 +585,7 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
     }                                                                                                            \
     int lsb_hard_info_bits_dev_##SUF(const T *app, uint8_t *bits, int64_t n_blocks, int N, int K, void *stream)  \
     {                                                                                                            \
+        if (n_blocks <= 0) return LSB_OK;                                                                        \
         LSB_REQUIRE(app && bits, "null pointer");                                                                \
         if (n_blocks <= 0) return LSB_OK;                                                                        \
         hard_bits_kernel<T><<<blocks_for((long long)n_blocks * K), kThreads, 0, (cudaStream_t)stream>>>(         \
@@ -592,6 +598,7 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
                                          const double *tau_sqr, double *out, int64_t F, int L, int M,            \
                                          double sqrt_nPl, void *stream)                                          \
     {                                                                                                            \
+        if (F <= 0) return LSB_OK;                                                                               \
         LSB_REQUIRE(beta && vk && vk0 && alpha_weighted && tau_sqr && out, "null pointer");                      \
         int logM = 0;                                                                                            \
         while ((1 << logM) < M) ++logM;                                                                          \

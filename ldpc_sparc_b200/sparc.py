@@ -195,7 +195,7 @@ def section_indices(bin_arr, M, K=1):
     sec = logM + logK
     b = np.asarray(bin_arr).astype(np.int64)
     assert b.shape[-1] % sec == 0
-    b = b.reshape(b.shape[:-1] + (-1, sec))
+    b = b.reshape(b.shape[:-1] + (b.shape[-1] // sec, sec))
     idx = b[..., :logM].dot(1 << np.arange(logM)[::-1])
     if K == 1:
         return idx
@@ -209,7 +209,7 @@ def indices_2_bin_arr(idx, M, K=1):
     bits = ((idx % M)[..., None] >> np.arange(logM)[::-1]) & 1
     if K > 1:
         bits = np.concatenate([bits, (bin2gray(idx // M)[..., None] >> np.arange(logK)[::-1]) & 1], axis=-1)
-    return bits.reshape(idx.shape[:-1] + (-1,)).astype(bool)
+    return bits.reshape(idx.shape[:-1] + (idx.shape[-1] * (logM + logK),)).astype(bool)
 
 
 def symbols_2_msg_vector(sym, M, K=1):
@@ -636,5 +636,5 @@ def sparc_decode(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=N
     if beta.ndim == 1 and beta.size == code_params['L'] * M:      # single frame: dense beta
         expect_err = psi.mean() >= 0.001
         return msg_vector_2_bin_arr(beta, M, K), beta, t_final, nmse, expect_err
-    psi2 = np.asarray(psi).reshape(len(beta), -1)
+    psi2 = np.asarray(psi).reshape(len(beta), max(1, np.asarray(psi).size // max(len(beta), 1)))
     return indices_2_bin_arr(beta, M, K), beta, t_final, nmse, psi2.mean(axis=1) >= 0.001
