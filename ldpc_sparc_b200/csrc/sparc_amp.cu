@@ -241,6 +241,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     T *s = beta + LM;
     const int secs_per_col = d.Mc / d.M;                       // sections per column block
     const double sec_norm = (double)d.L / d.Lc;
+    const bool fuse_denoiser = p.K == 1 && d.M <= 32;
 
     for (;;) {
         if (tid == 0) s_frame = (long long)atomicAdd(queue, 1ull);
@@ -314,15 +315,63 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
             for (int c = 0; c < d.Lc; ++c) {
                 const T tau_c = (T)tau[c];
                 T *s_c = s + (size_t)c * d.Mc;
-                const T *beta_c = beta + (size_t)c * d.Mc;
+                T *beta_c = beta + (size_t)c * d.Mc;
                 const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
                 for (int bi = b0; bi < b1; ++bi) {
                     const BlockDev b = d.blocks[bi];
                     block_transpose<T, LOGH>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid);
                     const T *bf = reinterpret_cast<const T *>(buf);
                     const T sc = Scale<T>::get(b) * tau_c;
-                    {
-                        const T *prev = bi == b0 ? (t > 0 ? beta_c : nullptr) : s_c;
+                    const T *prev = bi == b0 ? (t > 0 ? beta_c : nullptr) : s_c;
+                    if (fuse_denoiser && bi == b1 - 1) {
+                        // last block of the column, unmodulated, M <= 32: a row of 32 consecutive j in a
+                        // warp holds whole sections, so the softmax runs on the gathered values in
+                        // registers (no second pass over s, one exp per entry, one barrier less)
+                        const T inv_tau = (T)1 / tau_c;
+                        double psi_part = 0.0, nm_part = 0.0;
+                        for (int base = 0; base < d.Mc; base += kThreads * kBatch) {     // warp-uniform trip count
+                            int id[kBatch];
+                            T pv[kBatch];
+#pragma unroll
+                            for (int u = 0; u < kBatch; ++u) {
+                                const int j = base + tid + u * kThreads;
+                                id[u] = j < d.Mc ? (int)__ldg(b.az_gather + j) : 0;
+                                pv[u] = (prev && j < d.Mc) ? prev[j] : (T)0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < kBatch; ++u) {
+                                const int j = base + tid + u * kThreads;
+                                const bool live = j < d.Mc;
+                                const T v = pv[u] + sc * bf[id[u]];
+                                if (live) s_c[j] = v;
+                                T mx = live ? v : -INFINITY;
+                                for (int off = d.M >> 1; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                                const T e = live ? exp((v - mx) * inv_tau) : (T)0;
+                                T sum = e;
+                                for (int off = d.M >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                                if (live) {
+                                    const T inv = (T)1 / sum;
+                                    const T bta = e * inv;
+                                    beta_c[j] = bta;
+                                    psi_part += (double)bta * (double)((sum - e) * inv);
+                                    if (idx0) {
+                                        const int sec = j / d.M;
+                                        const int truth = idx0[f * d.L + c * secs_per_col + sec];
+                                        const double dlt = (double)bta - ((j - sec * d.M) == truth ? 1.0 : 0.0);
+                                        nm_part += dlt * dlt;
+                                    } else {
+                                        nm_part += (double)bta * (double)bta;
+                                    }
+                                }
+                            }
+                        }
+                        psi_part = warp_sum(psi_part);
+                        nm_part = warp_sum(nm_part);
+                        if (lane == 0) {
+                            atomicAdd(&psi[c], psi_part);
+                            atomicAdd(&nm[c], nm_part);
+                        }
+                    } else {
                         for (int j0 = tid; j0 < d.Mc; j0 += kThreads * kBatch) {
                             int id[kBatch];
                             T pv[kBatch];
@@ -341,6 +390,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                     }
                     __syncthreads();
                 }
+                if (fuse_denoiser && b1 > b0) continue;      // beta, psi, nmse of this column are done
                 // denoiser: sections of M entries, beta = softmax(s / tau) (:429-432)
                 double psi_part = 0.0, nm_part = 0.0;
                 const T inv_tau = (T)1 / tau_c;
