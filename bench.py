@@ -401,6 +401,19 @@ def main():
                 out["extra_workloads"][key] = json.loads(r.stdout.strip().splitlines()[-1])
             except Exception as e:   # the headline line must still be printed
                 out["extra_workloads"][key] = {"error": repr(e)[:200]}
+        # CPU baselines of the two SPARC configs: the numpy oracle (a port of the reference, kind "port")
+        # timed on the host cores over a bounded sample -- the cpu_baseline leg is allowed to execute oracle/
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            for key, cmd in (("sparc_amp_config1", ["c1", "--frames", str(4 * cores), "--procs", str(cores)]),
+                             ("dense_amp_config3_tcgen05", ["c3", "--frames", "4"])):
+                try:
+                    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_time.py")] + cmd,
+                                       capture_output=True, text=True, timeout=180, cwd=ROOT)
+                    if isinstance(out["extra_workloads"].get(key), dict):
+                        out["extra_workloads"][key]["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])
+                except Exception as e:
+                    out["extra_workloads"][key]["cpu_baseline"] = {"error": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
