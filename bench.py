@@ -391,6 +391,8 @@ def main():
                          # same decode with the early-stop atol at the fp32 noise floor instead of the reference's 2e-15
                          ("sparc_amp_config1_atol_1e-7", ["tools/bench_amp.py", "--frames", "4096", "--steps", "2",
                                                           "--warmup", "1", "--atol", "1e-7"]),
+                         ("sparc_amp_config4_sc_wave", ["tools/bench_amp.py", "--config", "c4", "--frames", "592",
+                                                        "--steps", "1", "--warmup", "0"]),
                          ("dense_amp_config3_tcgen05", ["tools/bench_dense.py", "--precision", "tc", "--frames", "1024",
                                                         "--steps", "2", "--warmup", "1"]),
                          ("ldpc_sparc_config5", ["tools/bench_c5.py", "--frames", "1024", "--chunk", "1024", "--sims",
