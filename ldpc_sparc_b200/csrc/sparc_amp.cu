@@ -80,6 +80,9 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v)
 // one (ncu: the table load -> address -> shared access chain was the top stall site).
 constexpr int kBatch = 4;
 
+// byte offset of the staged-FFT tile behind the n residual entries (16-byte aligned)
+__host__ __device__ inline size_t staged_tile_offset(int n, size_t elem) { return (((size_t)n * elem) + 15) & ~(size_t)15; }
+
 template <typename T>
 __device__ __forceinline__ void gather_add(T *dst, const T *bf, const uint16_t *__restrict__ tab, T sc, int n, int tid)
 {
@@ -121,7 +124,7 @@ __device__ __forceinline__ void scatter_scaled(T *bf, const uint16_t *__restrict
 template <typename T, int LOGH = 0>
 __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
                               const T *x /* Mc entries of the column block, or null */, int one_hot_pos,
-                              int Mc, int H, int tid)
+                              int Mc, int H, int tid, typename Cplx<T>::type *tile = nullptr)
 {
     T *bf = reinterpret_cast<T *>(buf);
     for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
@@ -131,6 +134,7 @@ __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &t
     }
     __syncthreads();
     if constexpr (LOGH > 0) fft_fixed<T, LOGH, false, kThreads>(buf, tb, tid);
+    else if (tile) fft_staged_h15<T, false>(buf, tile, tb, tid, kThreads);      // buffer in global memory, H = 2^15
     else fft_inplace<T, false>(buf, tb, tid, kThreads);
     dct2_post<T>(buf, tb, tid, kThreads);
 }
@@ -138,7 +142,8 @@ __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &t
 // ---- A_rc^T y : scatter a row block into the FFT buffer, DCT-III, leave X in buf
 template <typename T, int LOGH = 0>
 __device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
-                                const T *y /* Mr entries of the row block */, T yscale, int Mr, int H, int tid)
+                                const T *y /* Mr entries of the row block */, T yscale, int Mr, int H, int tid,
+                                typename Cplx<T>::type *tile = nullptr)
 {
     T *bf = reinterpret_cast<T *>(buf);
     for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
@@ -147,6 +152,7 @@ __device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> 
     __syncthreads();
     dct3_pre<T>(buf, tb, tid, kThreads);
     if constexpr (LOGH > 0) fft_fixed<T, LOGH, true, kThreads>(buf, tb, tid);
+    else if (tile) fft_staged_h15<T, true>(buf, tile, tb, tid, kThreads);
     else fft_inplace<T, true>(buf, tb, tid, kThreads);
 }
 
@@ -231,6 +237,8 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     T *cta_scratch = scratch + (size_t)blockIdx.x * (2 * (size_t)LM + (GBUF ? (size_t)d.w : 0));
     T2 *buf = GBUF ? reinterpret_cast<T2 *>(cta_scratch + 2 * (size_t)LM) : reinterpret_cast<T2 *>(smem);
     T *z = GBUF ? reinterpret_cast<T *>(smem) : reinterpret_cast<T *>(buf + H);     // [n]
+    // GBUF, H = 2^15: a 4096-point tile behind z stages the FFT passes through shared memory
+    T2 *tile = (GBUF && d.h == 15) ? reinterpret_cast<T2 *>(smem + staged_tile_offset(d.n, sizeof(T))) : nullptr;
     __shared__ double psi[kMaxLc], psi_prev[kMaxLc], tau[kMaxLc], nm[kMaxLc];
     __shared__ double phi[kMaxLr], phi_prev[kMaxLr], gam[kMaxLr], zsq[kMaxLr];
     __shared__ long long s_frame;
@@ -277,7 +285,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                 }
                 for (int bi = 0; bi < d.n_blocks; ++bi) {
                     const BlockDev b = d.blocks[bi];
-                    block_forward<T, LOGH>(buf, tb, b, beta + (size_t)b.c * d.Mc, -1, d.Mc, H, tid);
+                    block_forward<T, LOGH>(buf, tb, b, beta + (size_t)b.c * d.Mc, -1, d.Mc, H, tid, tile);
                     const T *bf = reinterpret_cast<const T *>(buf);
                     gather_add<T>(z + b.r * d.Mr, bf, b.ab_gather, -Scale<T>::get(b), d.Mr, tid);
                     __syncthreads();
@@ -319,7 +327,7 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                 const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
                 for (int bi = b0; bi < b1; ++bi) {
                     const BlockDev b = d.blocks[bi];
-                    block_transpose<T, LOGH>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid);
+                    block_transpose<T, LOGH>(buf, tb, b, z + b.r * d.Mr, (T)(1.0 / phi[b.r]), d.Mr, H, tid, tile);
                     const T *bf = reinterpret_cast<const T *>(buf);
                     const T sc = Scale<T>::get(b) * tau_c;
                     const T *prev = bi == b0 ? (t > 0 ? beta_c : nullptr) : s_c;
@@ -620,7 +628,11 @@ int check_device(const lsb_sparc_design *g)
 }
 
 // shared memory per CTA; gbuf = FFT buffer kept in global memory instead
-size_t amp_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + (size_t)d.n) * elem; }
+size_t amp_smem(const DesignDev &d, size_t elem, bool gbuf)
+{
+    if (gbuf && d.h == 15) return staged_tile_offset(d.n, elem) + (size_t)kTilePts * 2 * elem;   // z + staged-FFT tile
+    return ((gbuf ? 0 : (size_t)d.w) + (size_t)d.n) * elem;
+}
 size_t ab_smem(const DesignDev &d, size_t elem, bool gbuf) { return ((gbuf ? 0 : (size_t)d.w) + (size_t)d.n) * elem; }
 size_t az_smem(const DesignDev &d, size_t elem, bool gbuf) { return (gbuf ? 16 : (size_t)d.w * elem); }
 bool needs_gbuf(const DesignDev &d, size_t elem) { return amp_smem(d, elem, false) + 8192 > (size_t)lsb::max_smem_optin(); }
@@ -733,6 +745,15 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
         LSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
         if (per_sm < 1) per_sm = 1;
+        if (gbuf) {
+            // the FFT buffers of all resident CTAs should stay in L2 (w elements each): more CTAs than
+            // that turn every radix pass into DRAM traffic
+            int l2 = 0;
+            LSB_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, g->device));
+            int cap = (int)((0.6 * l2) / ((double)g->dev.w * sizeof(T)) / lsb::sm_count());   // measured: 2 CTAs/SM best for w = 65536 fp32
+            if (cap < 1) cap = 1;
+            if (cap < per_sm) per_sm = cap;
+        }
         cached = per_sm * lsb::sm_count();
     }
     long long grid = cached < n_frames ? cached : n_frames;

@@ -255,6 +255,105 @@ __device__ __forceinline__ void fft_fixed(typename Cplx<T>::type *buf, const Fft
     fft_fixed_from<T, LOGH, LOGH, INV, NT>(buf, tb.tw, tid);
 }
 
+// ---------------------------------------------------------------- staged FFT (buffer in global memory)
+// Transforms whose buffer lives in global memory (w = 65536: 256 KB, more than one SM's shared
+// memory) would touch L2 once per radix pass.  The same in-place passes are regrouped so that
+// a 4096-point tile is staged through shared memory and several passes run on it there:
+//   stage A: the passes above sub-transform size 512 (element i = j + 512 m: a tile holds the
+//            64 values of m for 64 consecutive j -- rows of 512 B in global memory);
+//   stage B: the passes of the last 512-point sub-transforms, 8 of them per contiguous tile.
+// Element order, swizzle and twiddles are exactly those of fft_inplace, so the index tables
+// and the DCT pre/post-processing are unchanged.  Built for H = 2^15 (two radix-8 passes in
+// stage A, three in stage B): 2 L2 round trips instead of 5.
+constexpr int kTilePts = 4096;
+
+// one radix-8 DIF pass over a 4096-point tile in shared memory; slot(l) = tile slot of local index l,
+// twi(jl) = twiddle-table index of the butterfly whose first local index has offset jl inside its sub-transform
+template <typename T, bool INV, typename SlotFn, typename TwFn>
+__device__ __forceinline__ void tile_pass8(typename Cplx<T>::type *tile, const typename Cplx<T>::type *tw, int logS,
+                                           SlotFn slot, TwFn twi, int tid, int nthreads)
+{
+    typedef typename Cplx<T>::type T2;
+    const int logQ = logS - 3, stride = 1 << logQ;
+    for (int q = tid; q < (kTilePts >> 3); q += nthreads) {
+        const int jl = q & (stride - 1);
+        const int base = ((q >> logQ) << logS) + jl;
+        T2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = tile[slot(base + m * stride)];
+        bfly1(v[0], v[4]);
+        bfly1(v[1], v[5]);
+        bfly1(v[2], v[6]);
+        bfly1(v[3], v[7]);
+        v[5] = mul_w8<INV>(v[5]);
+        v[6] = mul_mi<INV>(v[6]);
+        v[7] = mul_mi<INV>(mul_w8<INV>(v[7]));
+        bfly1(v[0], v[2]);
+        bfly1(v[1], v[3]);
+        bfly1(v[4], v[6]);
+        bfly1(v[5], v[7]);
+        v[3] = mul_mi<INV>(v[3]);
+        v[7] = mul_mi<INV>(v[7]);
+        bfly1(v[0], v[1]);
+        bfly1(v[2], v[3]);
+        bfly1(v[4], v[5]);
+        bfly1(v[6], v[7]);
+        const int ti = twi(jl);
+        if (ti != 0) {
+            const T2 w1 = twiddle<INV>(tw, ti), w2 = twiddle<INV>(tw, 2 * ti), w4 = twiddle<INV>(tw, 4 * ti);
+            const T2 w3 = cmul(w1, w2);
+            v[1] = cmul(v[1], w4);
+            v[2] = cmul(v[2], w2);
+            v[3] = cmul(v[3], cmul(w2, w4));
+            v[4] = cmul(v[4], w1);
+            v[5] = cmul(v[5], cmul(w1, w4));
+            v[6] = cmul(v[6], w3);
+            v[7] = cmul(v[7], cmul(w3, w4));
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) tile[slot(base + m * stride)] = v[m];
+    }
+}
+
+// In-place FFT of 2^15 points held in global memory at gbuf (slots as fft_inplace), staged through the
+// 4096-point shared-memory tile.  Ends with __syncthreads().
+template <typename T, bool INV>
+__device__ void fft_staged_h15(typename Cplx<T>::type *gbuf, typename Cplx<T>::type *tile, const FftTables<T> &tb,
+                               int tid, int nthreads)
+{
+    typedef typename Cplx<T>::type T2;
+    const T2 *tw = tb.tw;
+    // ---- stage A: passes with sub-transform sizes 2^15 and 2^12 (strides 4096 and 512)
+    for (int t = 0; t < 8; ++t) {
+        for (int e = tid; e < kTilePts; e += nthreads) tile[e] = gbuf[512 * (e >> 6) + 64 * t + (e & 63)];
+        __syncthreads();
+        // local index l = 64 m + jj  <->  global element i = 512 m + 64 t + jj; the global swizzle only
+        // permutes the low 4 bits as a function of bits 4..6 of i (bit 6 = bit 0 of t)
+        auto slot = [t](int l) { return (l & ~63) | (swz(((t & 1) << 6) | (l & 63)) & 63); };
+        tile_pass8<T, INV>(tile, tw, 12, slot, [t](int jl) { return 64 * t + (jl & 63) + 512 * (jl >> 6); }, tid, nthreads);
+        __syncthreads();
+        tile_pass8<T, INV>(tile, tw, 9, slot, [t](int jl) { return (64 * t + jl) * 8; }, tid, nthreads);
+        __syncthreads();
+        for (int e = tid; e < kTilePts; e += nthreads) gbuf[512 * (e >> 6) + 64 * t + (e & 63)] = tile[e];
+        __syncthreads();
+    }
+    // ---- stage B: the 512-point sub-transforms (sizes 2^9, 2^6, 2^3), 8 per contiguous tile
+    for (int c = 0; c < 8; ++c) {
+        T2 *src = gbuf + (size_t)c * kTilePts;
+        for (int e = tid; e < kTilePts; e += nthreads) tile[e] = src[e];
+        __syncthreads();
+        auto slot = [](int l) { return swz(l); };
+        tile_pass8<T, INV>(tile, tw, 9, slot, [](int jl) { return jl * 64; }, tid, nthreads);
+        __syncthreads();
+        tile_pass8<T, INV>(tile, tw, 6, slot, [](int jl) { return jl * 512; }, tid, nthreads);
+        __syncthreads();
+        tile_pass8<T, INV>(tile, tw, 3, slot, [](int) { return 0; }, tid, nthreads);
+        __syncthreads();
+        for (int e = tid; e < kTilePts; e += nthreads) src[e] = tile[e];
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ int bitrev(int k, int h) { return (int)(__brev((unsigned)k) >> (32 - h)); }
 
 // After the forward FFT of the packed sequence: slot brev(k) <- (Y[k], Y[N-k]),
