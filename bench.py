@@ -382,6 +382,16 @@ def main():
                                      "ms_per_step": 1e3 * float(th.item()) / n_e2e}
 
     out["clocks"] = clocks.summary()
+    # the pipe the kernel is really bound by: 4 MUFU (2 ex2 + 2 lg2) per corrected Lxor, 3 dc - 6 of them per
+    # check of degree dc (cdeg 7 x 810, 8 x 162 for this code), against 16 MUFU lanes per SM per clock
+    mufu_per_frame_iter = 4 * int(sum(3 * int(dc) - 6 for dc in code.cdeg))
+    sm_mhz = out["clocks"].get("sm_mhz") or out["clocks"].get("sm_max_mhz") or 1965.0
+    mufu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * float(sm_mhz) * 1e6
+    mufu_rate = mufu_per_frame_iter * frame_iters_rank / (kernel_ms_avg * 1e-3)
+    out["roofline_mufu"] = {"bound": "mufu", "achieved": mufu_rate / 1e12, "peak": mufu_peak / 1e12, "unit": "T MUFU op/s",
+                            "frac": mufu_rate / mufu_peak, "mufu_per_frame_iteration": mufu_per_frame_iter,
+                            "note": "secondary roofline: 16 MUFU lanes/SM/clk at the SM clock sampled under load; "
+                                    "ncu reports the XU pipe 83 % busy (profiles/r1_bp_qc_f32_v3_ncu_full.csv)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(code, args, args.cpu_seconds)
     if rank == 0 and world == 1 and not args.no_extras:
