@@ -103,3 +103,28 @@ def test_performance_sweep_small(tmp_path, precision):
     saved = np.load(path)
     assert set(saved.files) == {'ber_store_averages', 'ber_store_max', 'ber_store_min', 'snr_store'}
     assert np.array_equal(saved['ber_store_averages'], avg)
+
+
+def test_config1_error_statistics_match_oracle():
+    """Full-size statistical parity at BASELINE config 1: frame error rate, section error rate and
+    mean iteration count of the batched GPU path over 4096 fresh frames against the oracle's
+    statistics over 1536 frames (tests/golden/c1_statistics.json, oracle/make_golden_stats.py).
+    Different frames on the two sides, so the bounds are 4 sigma of the two binomial / sample errors."""
+    from ldpc_sparc_b200 import sparc_sim
+    ref = json.load(open(os.path.join(GOLDEN, "c1_statistics.json")))
+    n_ref, L = ref["frames"], ref["code_params"]["L"]
+    fer_ref = ref["frames_in_error"] / n_ref
+    ser_ref = ref["section_errors"] / (n_ref * L)
+    F = 4096
+    for precision in ("fp64", "fp32"):
+        out = sparc_sim.sparc_sim_batch(dict(ref["code_params"]), dict(t_max=ref["t_max"]), ref["awgn_var"], F,
+                                        rand_seed=tuple(ref["design_seed"]), seed=11, chunk=1024, precision=precision)
+        sig_fer = np.sqrt(fer_ref * (1 - fer_ref) * (1 / n_ref + 1 / F))
+        assert abs(out["cer"] - fer_ref) < 4 * sig_fer, (precision, out["cer"], fer_ref)
+        sig_ser = np.sqrt(ref["section_errors_per_frame_var"] * (1 / n_ref + 1 / F)) / L
+        assert abs(out["ser"] - ser_ref) < 4 * sig_ser, (precision, out["ser"], ser_ref)
+        if precision == "fp64":          # fp32 meets the stop rule a few iterations later (DESIGN.md section 4)
+            sig_t = ref["std_t_final"] * np.sqrt(1 / n_ref + 1 / F)
+            assert abs(out["t_final"] - ref["mean_t_final"]) < 4 * sig_t, (out["t_final"], ref["mean_t_final"])
+        else:
+            assert ref["mean_t_final"] - 0.5 < out["t_final"] <= ref["t_max"] - 1
