@@ -200,3 +200,31 @@ def test_config5_small_variant_vs_oracle():
             assert np.array_equal(sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="tc"), ub)
             assert np.array_equal(sparc_new.naively_integrated_decoder(y, sp, lp, dp, A, precision="tc"),
                                   sph.naively_integrated_decoder(y, sp, oc, dp, A))
+
+
+def test_config3_full_size_tensor_core_amp_vs_oracle():
+    """BASELINE config 3 at full size (L = 512, M = 64, n = 3072: A 3072 x 32768, P = 19.44,
+    t_max = 25): the tcgen05 AMP path against the numpy oracle on the same A and y --
+    per-iteration tau^2 and the final beta within 1e-4, identical section decisions."""
+    L, M, n, P = 512, 64, 3072, 19.44
+    rng = np.random.default_rng(0)
+    A = rng.normal(0, 1 / np.sqrt(n), (n, L * M))
+    sq = np.sqrt(n * P / L)
+    sp, dp = dict(P=P, R=1.0, L=L, M=M), dict(t_max=25)
+    ys, idx0 = [], []
+    for f in range(3):
+        idx = rng.integers(0, M, L)
+        beta0 = np.zeros(L * M)
+        beta0[np.arange(L) * M + idx] = sq
+        ys.append(A @ beta0 + np.sqrt(P / 6.0) * rng.standard_normal(n))
+        idx0.append(idx)
+    ys = np.stack(ys)
+    beta, s, tau = sparc_new.sparc_amp(ys, sp, dp, A, precision="tc", return_trace=True)
+    for f in range(3):
+        trace = []
+        ref_beta, ref_s = sph.sparc_amp(ys[f], sp, dp, A, trace)
+        ref_tau = np.array([t["tau_sqr"] for t in trace])
+        assert np.max(np.abs(tau[f] - ref_tau) / ref_tau) < 1e-4
+        assert np.max(np.abs(beta[f] - ref_beta)) < 1e-4 * sq
+        dec, ref_dec = s[f].reshape(L, M).argmax(1), ref_s.reshape(L, M).argmax(1)
+        assert np.array_equal(dec, ref_dec) and np.mean(dec != idx0[f]) < 0.01
