@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <map>
 #include <mutex>
 #include <new>
 
@@ -361,11 +362,16 @@ struct lsb_tc_design {
     int64_t n = 0, ML = 0;
     TcOperand A, At;              // A: [n, ML] (K = ML) for A beta;  At: [ML, n] (K = n) for A^T z
     std::mutex mu;
-    __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr;   // staging of the split frame operand
-    size_t x_cap = 0;
-    float *part = nullptr;                             // partial products of a K-split launch
-    size_t part_cap = 0;
-    cudaEvent_t x_event = nullptr;
+    // Staging (split frame operand, K-split partials) is kept per stream: calls on one stream are
+    // ordered by the stream itself, calls on different streams (two half-batches whose element-wise
+    // kernels overlap each other's GEMMs) never share a buffer.
+    struct Staging {
+        __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr;
+        size_t x_cap = 0;
+        float *part = nullptr;
+        size_t part_cap = 0;
+    };
+    std::map<cudaStream_t, Staging> staging;
 };
 
 namespace {
@@ -395,26 +401,27 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     int dev = -1;
     LSB_CUDA(cudaGetDevice(&dev));
     LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);
-    std::lock_guard<std::mutex> lock(g->mu);
+    std::unique_lock<std::mutex> lock(g->mu);
+    LSB_REQUIRE(g->staging.size() < 32 || g->staging.count(st), "more than 32 streams use this design");
+    lsb_tc_design::Staging &sg = g->staging[st];
+    lock.unlock();                                       // entries are never erased; each stream touches only its own
     const size_t need = (size_t)F * (size_t)(g->n > g->ML ? g->n : g->ML);
-    if (g->x_cap < need) {
-        LSB_CUDA(cudaDeviceSynchronize());
-        cudaFree(g->x_hi);
-        cudaFree(g->x_lo);
-        g->x_hi = g->x_lo = nullptr;
-        g->x_cap = 0;
-        LSB_CUDA(cudaMalloc((void **)&g->x_hi, need * sizeof(__nv_bfloat16)));
-        LSB_CUDA(cudaMalloc((void **)&g->x_lo, need * sizeof(__nv_bfloat16)));
-        g->x_cap = need;
+    if (sg.x_cap < need) {
+        LSB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(sg.x_hi);
+        cudaFree(sg.x_lo);
+        sg.x_hi = sg.x_lo = nullptr;
+        sg.x_cap = 0;
+        LSB_CUDA(cudaMalloc((void **)&sg.x_hi, need * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.x_lo, need * sizeof(__nv_bfloat16)));
+        sg.x_cap = need;
     }
-    if (!g->x_event) LSB_CUDA(cudaEventCreateWithFlags(&g->x_event, cudaEventDisableTiming));
-    else LSB_CUDA(cudaStreamWaitEvent(st, g->x_event, 0));      // staging buffers are shared by all calls
     const long long count = (long long)F * W.K;
-    split_kernel<float><<<lsb::sm_count() * 4, 256, 0, st>>>(x, g->x_hi, g->x_lo, count);
+    split_kernel<float><<<lsb::sm_count() * 4, 256, 0, st>>>(x, sg.x_hi, sg.x_lo, count);
     lsb::count_launch();
     CUtensorMap mx_hi, mx_lo;
-    int rc = make_map(&mx_hi, g->x_hi, (uint64_t)F, (uint64_t)W.K);
-    if (!rc) rc = make_map(&mx_lo, g->x_lo, (uint64_t)F, (uint64_t)W.K);
+    int rc = make_map(&mx_hi, sg.x_hi, (uint64_t)F, (uint64_t)W.K);
+    if (!rc) rc = make_map(&mx_lo, sg.x_lo, (uint64_t)F, (uint64_t)W.K);
     if (rc) return rc;
     static bool configured = false;
     if (!configured) {
@@ -442,15 +449,15 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     float *dst = out;
     if (splits > 1) {
         const size_t need_part = out_count * (size_t)splits;
-        if (g->part_cap < need_part) {
-            LSB_CUDA(cudaDeviceSynchronize());
-            cudaFree(g->part);
-            g->part = nullptr;
-            g->part_cap = 0;
-            LSB_CUDA(cudaMalloc((void **)&g->part, need_part * sizeof(float)));
-            g->part_cap = need_part;
+        if (sg.part_cap < need_part) {
+            LSB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(sg.part);
+            sg.part = nullptr;
+            sg.part_cap = 0;
+            LSB_CUDA(cudaMalloc((void **)&sg.part, need_part * sizeof(float)));
+            sg.part_cap = need_part;
         }
-        dst = g->part;
+        dst = sg.part;
     }
     const int n_items = n_tiles * splits;
     tc_gemm_kernel<<<n_items < sms ? n_items : sms, kThreadsTc, kSmemBytes, st>>>(
@@ -459,12 +466,11 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     if (splits > 1) {
         lsb::count_launch();
         LSB_CUDA(cudaGetLastError());
-        reduce_splits_kernel<<<sms * 8, 256, 0, st>>>((const float4 *)g->part, (float4 *)out, (long long)(out_count / 4),
+        reduce_splits_kernel<<<sms * 8, 256, 0, st>>>((const float4 *)sg.part, (float4 *)out, (long long)(out_count / 4),
                                                      splits);
     }
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
-    LSB_CUDA(cudaEventRecord(g->x_event, st));
     return LSB_OK;
 }
 
@@ -525,10 +531,11 @@ void lsb_tc_design_destroy(lsb_tc_design *g)
     cudaFree(g->A.lo);
     cudaFree(g->At.hi);
     cudaFree(g->At.lo);
-    cudaFree(g->x_hi);
-    cudaFree(g->x_lo);
-    cudaFree(g->part);
-    if (g->x_event) cudaEventDestroy(g->x_event);
+    for (auto &kv : g->staging) {
+        cudaFree(kv.second.x_hi);
+        cudaFree(kv.second.x_lo);
+        cudaFree(kv.second.part);
+    }
     delete g;
 }
 

@@ -46,11 +46,7 @@ def main():
     del beta0
 
     def step():
-        st = sparc_new._amp_state(eng, y, L, M)
-        s = eng.empty(F, L * M)
-        for t in range(t_max):
-            sparc_new._amp_iteration(eng, y, st, P, L, M, sq, t == 0, s)
-        return s
+        return sparc_new._amp_device(eng, y, P, L, M, sq, t_max)[1]
 
     for _ in range(args.warmup):
         s = step()
