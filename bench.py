@@ -418,7 +418,9 @@ def main():
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             for key, cmd in (("sparc_amp_config1", ["c1", "--frames", str(4 * cores), "--procs", str(cores)]),
-                             ("dense_amp_config3_tcgen05", ["c3", "--frames", "4"])):
+                             ("dense_amp_config3_tcgen05", ["c3", "--frames", "4"]),
+                             ("sparc_amp_config4_sc_wave", ["c4", "--frames", "1"]),
+                             ("ldpc_sparc_config5", ["c5", "--frames", "1"])):
                 try:
                     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_time.py")] + cmd,
                                        capture_output=True, text=True, timeout=180, cwd=ROOT)
