@@ -93,6 +93,14 @@ __device__ void transform(typename Cplx<T>::type *buf, const FftTables<T> &tb, c
         buf[tab[i]] = T2{v.x * src_scale, v.y * src_scale};
     }
     __syncthreads();
+    if constexpr (sizeof(T) == 4) {          // compile-time-size passes for the common fp32 sizes (sparc_dct.cuh)
+        switch (tb.h) {
+            case 11: fft_fixed<T, 11, INV, kThreads>(buf, tb, tid); return;
+            case 12: fft_fixed<T, 12, INV, kThreads>(buf, tb, tid); return;
+            case 13: fft_fixed<T, 13, INV, kThreads>(buf, tb, tid); return;
+            default: break;
+        }
+    }
     fft_inplace<T, INV>(buf, tb, tid, kThreads);
 }
 
@@ -150,7 +158,7 @@ cop_kernel(CDesign d, FftTables<T> tb, const typename Cplx<T>::type *__restrict_
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
 camp_kernel(CDesign d, FftTables<T> tb, CParams p, const typename Cplx<T>::type *__restrict__ y_all,
             const int32_t *__restrict__ idx0, COut o, typename Cplx<T>::type *__restrict__ scratch,
             long long n_frames, unsigned long long *__restrict__ queue, int gbuf)
