@@ -19,7 +19,8 @@
  * otherwise; lsb_last_error() gives a thread-local message.  Nothing throws
  * across this boundary.  All device work is issued on the CURRENT CUDA device
  * (the host side sets it, e.g. torch.cuda.set_device(local_rank)); a handle
- * must be used on the device it was created on.
+ * must be used on the device it was created on.  An empty batch (zero frames)
+ * is valid with any pointer values and returns 0 without touching the device.
  *
  * LLR sign convention (as the reference): positive = bit 0 more likely.
  */
