@@ -78,6 +78,30 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     bits, idx, T, _, _ = out
+    # end to end through the public call with host buffers: pinned y in, decided sections + t_final out
+    e2e = None
+    if args.config == "c1":
+        h_y = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        h_y.copy_(y)
+        h_idx = torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
+        h_T = torch.empty(T.shape, dtype=T.dtype).pin_memory()
+
+        def e2e_step():
+            yd = h_y.to("cuda", non_blocking=True)
+            o = sparc.sparc_decode(yd, cp, dp, 1.0, [1, 2], None, Ab, Az, precision=args.precision)
+            h_idx.copy_(o[1], non_blocking=True)
+            h_T.copy_(o[2], non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        import time
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / args.steps
+        assert torch.equal(h_idx.cuda(), idx)
+        e2e = {"value": F * L_ * logM / dt, "unit": "info bits/s", "h2d_bytes_per_step": h_y.numel() * 4,
+               "d2h_bytes_per_step": h_idx.numel() * 4 + h_T.numel() * 4, "ms_per_step": dt * 1e3}
     its = T.double().mean().item()
     frame_iters = float(T.sum().item())
     peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -88,7 +112,7 @@ def main():
                     % (args.config, L_, M_, n, dp["t_max"], F),
         "precision": args.precision, "atol": dp.get("atol", 2e-15), "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
         "info_bits_per_s": F * L_ * logM / (ms * 1e-3), "mean_iterations": its,
-        "section_error_rate": float((idx != idx0).float().mean().item()),
+        "section_error_rate": float((idx != idx0).float().mean().item()), "e2e": e2e,
         "roofline": {"bound": "hbm (state-streaming model; really shared-memory/FFT bound, DESIGN.md)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
     }))
