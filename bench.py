@@ -402,9 +402,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         # secondary workloads of BASELINE.json (parity-test configs, reported for context; not the headline)
         out["extra_workloads"] = {}
-        for key, cmd in (("sparc_amp_config1", ["tools/bench_amp.py", "--frames", "4096", "--steps", "2", "--warmup", "1"]),
+        for key, cmd in (("sparc_amp_config1", ["tools/bench_amp.py", "--frames", "16384", "--steps", "2", "--warmup", "1"]),
                          # same decode with the early-stop atol at the fp32 noise floor instead of the reference's 2e-15
-                         ("sparc_amp_config1_atol_1e-7", ["tools/bench_amp.py", "--frames", "4096", "--steps", "2",
+                         ("sparc_amp_config1_atol_1e-7", ["tools/bench_amp.py", "--frames", "16384", "--steps", "2",
                                                           "--warmup", "1", "--atol", "1e-7"]),
                          ("sparc_amp_config4_sc_wave", ["tools/bench_amp.py", "--config", "c4", "--frames", "592",
                                                         "--steps", "1", "--warmup", "0"]),
