@@ -157,7 +157,8 @@ def sim(standard, rate, z, ptype='A', N_MEASUREMENTS=24, C_AWGN_OFFSET=1.0, P_ST
             nbiterrors += int(be[:take].sum())
             nit_total += int(it[:take].sum())
             rnd += 1
-        output = (standard, rate, z, float(SNR), nblocks, nblockerrors, nblocks * K, nbiterrors, nit_total)
+        output = (standard, rate, z, float(SNR), int(nblocks), int(nblockerrors), int(nblocks) * int(K), int(nbiterrors),
+                  int(nit_total))                      # plain ints: the line format of data/results.txt
         res.append(output)
         if results_path is not None and rank == 0:
             with open(results_path, 'a') as f:

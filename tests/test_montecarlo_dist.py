@@ -95,6 +95,7 @@ def test_campaign_driver_two_ranks_gloo(tmp_path):
         assert p.exitcode == 0
     lines = open(path).read().strip().splitlines()
     assert len(lines) == 2 and eval(lines[1]) == res[1]
+    assert "np." not in lines[0] and lines[0].startswith("('802.11n', '1/2', 27, ")     # plain literals, as data/results.txt
     for std, rate, z, snr, nblocks, nerr, nbits, nbiterr, nit in res:
         assert nerr == 50 and nbits == nblocks * 324 and nit == 3 * nblocks      # uncoded stub: every block errs
         assert nblocks == 50
