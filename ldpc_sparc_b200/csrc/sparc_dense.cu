@@ -234,9 +234,18 @@ __global__ void section_to_bit_kernel(const T *__restrict__ beta, T *__restrict_
     for (int j = 0; j < M; ++j)
         if (((j >> shift) & 1) == 0) p += bs[j] / (T)sqrt_nPl;
     if (probs) probs[i] = p;
-    if (llr) {   // clip and logs in fp64: 1 - 1e-15 is not representable in fp32
-        const double pc = fmin(fmax((double)p, 1e-15), 1.0 - 1e-15);
-        llr[i] = (T)(log(pc) - log(1.0 - pc));
+    if (llr) {
+        if (sizeof(T) == 8) {
+            const double pc = fmin(fmax((double)p, 1e-15), 1.0 - 1e-15);
+            llr[i] = (T)(log(pc) - log(1.0 - pc));
+        } else {
+            // 1 - 1e-15 is not an fp32 number, so the clip is applied to the result instead: for p inside
+            // [1e-15, 1 - 1e-15] nothing changes, outside it the reference's LLR is +-log((1 - 1e-15) / 1e-15);
+            // 1 - p is exact in fp32 for p >= 1/2.  (Was two fp64 logs per bit: 135 -> ~45 us at config 5.)
+            const float lim = 34.538776f;
+            const float v = logf((float)p) - logf(1.0f - (float)p);
+            llr[i] = (T)fminf(fmaxf(v, -lim), lim);
+        }
     }
 }
 
@@ -252,8 +261,8 @@ bit_to_section_kernel(const T *__restrict__ app, T *__restrict__ probs, T *__res
     double part = 0.0;
     for (int e = threadIdx.x; e < L * M; e += kThreads) {
     const long long i = (long long)f * L * M + e;
-    const long long sec = i / M;
-    const int idx = (int)(i % M);
+    const long long sec = (long long)f * L + (e >> logM);       // M = 2^logM
+    const int idx = e & (M - 1);
     T prod = (T)1;
     for (int j = 0; j < logM; ++j) {
         const T a = app[sec * logM + j];
