@@ -128,3 +128,26 @@ def test_config1_error_statistics_match_oracle():
             assert abs(out["t_final"] - ref["mean_t_final"]) < 4 * sig_t, (out["t_final"], ref["mean_t_final"])
         else:
             assert ref["mean_t_final"] - 0.5 < out["t_final"] <= ref["t_max"] - 1
+
+
+def test_campaign_cli(tmp_path, capsys):
+    """python -m ldpc_sparc_b200.campaign: the three campaigns on tiny budgets."""
+    from ldpc_sparc_b200 import campaign
+    res = str(tmp_path / "results.txt")
+    campaign.main(["ldpc", "--z", "27", "--points", "2", "--min-errors", "20", "--max-blocks", "4000", "--max-it", "30",
+                   "--results", res])
+    lines = open(res).read().strip().splitlines()
+    assert len(lines) == 2 and "np." not in lines[0]
+    std, rate, z, snr, nblocks, nerr, nbits, nbiterr, nit = eval(lines[0])
+    assert (std, rate, z) == ("802.11n", "1/2", 27) and nerr == 20 and nbits == nblocks * 324
+    capsys.readouterr()
+    campaign.main(["sparc", "--L", "128", "--M", "16", "--R", "1.2", "--frames", "256", "--pa", "4", "0.9"])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert out["frames"] == 256 and 0 <= out["ser"] < 0.05
+    campaign.main(["sparc", "--L", "128", "--M", "16", "--R", "2.0", "--frames", "128", "--K", "4", "--complex"])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert out["frames"] == 128 and out["n"] == int(round(128 * 6 / 2.0))
+    npz = str(tmp_path / "Test_0.npz")
+    campaign.main(["ldpc_sparc", "--mults", "1", "--frames", "32", "--snr", "2", "6", "2", "--npz", npz])
+    saved = np.load(npz)
+    assert saved["ber_store_averages"].shape == (4, 2) and np.all(saved["ber_store_averages"][1:, 1] == 0)
