@@ -120,6 +120,17 @@ __device__ __forceinline__ void scatter_scaled(T *bf, const uint16_t *__restrict
     }
 }
 
+// bf[0 .. count) = 0 with 16-byte stores (count is a multiple of 16 / sizeof(T): the buffer holds 2H >= 4 entries)
+template <typename T>
+__device__ __forceinline__ void zero_fill(T *bf, int count, int tid)
+{
+    constexpr int V = 16 / sizeof(T);
+    uint4 *p = reinterpret_cast<uint4 *>(bf);
+    const int n16 = count / V;
+    for (int i = tid; i < n16; i += kThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = n16 * V + tid; i < count; i += kThreads) bf[i] = (T)0;
+}
+
 // ---- A_rc x : scatter a column block into the FFT buffer, DCT-II, leave Y in buf
 template <typename T, int LOGH = 0>
 __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &tb, const BlockDev &b,
@@ -127,7 +138,7 @@ __device__ void block_forward(typename Cplx<T>::type *buf, const FftTables<T> &t
                               int Mc, int H, int tid, typename Cplx<T>::type *tile = nullptr)
 {
     T *bf = reinterpret_cast<T *>(buf);
-    for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
+    zero_fill(bf, 2 * H, tid);
     __syncthreads();
     if (x) {
         scatter_scaled<T>(bf, b.ab_scatter, x, (T)1, Mc, tid);
@@ -146,7 +157,7 @@ __device__ void block_transpose(typename Cplx<T>::type *buf, const FftTables<T> 
                                 typename Cplx<T>::type *tile = nullptr)
 {
     T *bf = reinterpret_cast<T *>(buf);
-    for (int i = tid; i < 2 * H; i += kThreads) bf[i] = (T)0;
+    zero_fill(bf, 2 * H, tid);
     __syncthreads();
     scatter_scaled<T>(bf, b.az_scatter, y, yscale, Mr, tid);
     __syncthreads();
@@ -353,10 +364,12 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                                 const T v = pv[u] + sc * bf[id[u]];
                                 if (live) s_c[j] = v;
                                 T mx = live ? v : -INFINITY;
-                                for (int off = d.M >> 1; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                                if (d.M == 32) mx = warp_max(mx);                 // unrolled full-warp butterfly
+                                else for (int off = d.M >> 1; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
                                 const T e = live ? exp((v - mx) * inv_tau) : (T)0;
                                 T sum = e;
-                                for (int off = d.M >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                                if (d.M == 32) sum = warp_sum(sum);
+                                else for (int off = d.M >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
                                 if (live) {
                                     const T inv = (T)1 / sum;
                                     const T bta = e * inv;
