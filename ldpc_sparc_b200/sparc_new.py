@@ -292,7 +292,17 @@ def _drive(eng, yd, make_gen):
                         results[i], live[i] = e.value, False
     for st in eng._streams:
         cur.wait_stream(st)
+    for r in results:                                      # the halves' outputs are read on the caller's stream from here on
+        _record_stream(t, r, cur)
     return _join(t, results[0], results[1])
+
+
+def _record_stream(t, x, stream):
+    if isinstance(x, tuple):
+        for y in x:
+            _record_stream(t, y, stream)
+    elif isinstance(x, t.Tensor) and x.is_cuda:
+        x.record_stream(stream)
 
 
 def _join(t, a, b):

@@ -228,3 +228,41 @@ def test_config3_full_size_tensor_core_amp_vs_oracle():
         assert np.max(np.abs(beta[f] - ref_beta)) < 1e-4 * sq
         dec, ref_dec = s[f].reshape(L, M).argmax(1), ref_s.reshape(L, M).argmax(1)
         assert np.array_equal(dec, ref_dec) and np.mean(dec != idx0[f]) < 0.01
+
+
+def test_two_stream_drive_equals_one_stream(gold, monkeypatch):
+    """Large tensor-core batches run as two half-batches on two CUDA streams (sparc_new._drive).
+    Frames are independent and every kernel is deterministic, so the result must be bit-identical
+    to decoding the same two half-batches one after the other on one stream.  (Against the
+    undivided batch only the K-split of the GEMMs, i.e. the fp32 summation order, differs: tau^2
+    agrees to 1e-5 and the frame error count is the same.)"""
+    g, meta = gold
+    m = meta["z54_m2_hi"]
+    pre, c, sp, dp, y, A = setup_case(g, m, "z54_m2_hi", 0)
+    lp = dict(standard=m["standard"], rate=m["rate"], z=m["z"])
+    lengths = dict(k_ldpc=c.K * m["mults"], mults=m["mults"], L_unprotected=0)
+    rng = np.random.RandomState(2)
+    F = 300
+    ys = np.stack([g[pre + "x"] + np.sqrt(sp["P"] / 5.0) * rng.randn(len(y)) for _ in range(F)])
+    cut = (F // 2 + 127) // 128 * 128                      # as sparc_new._drive cuts
+
+    def all_decoders(batch):
+        return dict(
+            amp=sparc_new.sparc_amp(batch, sp, dp, A, precision="tc", return_trace=True),
+            sep=sparc_new.sparc_ldpc_decode(batch, sp, lp, dp, True, lengths, A, precision="tc"),
+            naive=sparc_new.naively_integrated_decoder(batch, sp, lp, dp, A, precision="tc"),
+            integ=sparc_new.integrated_decoder(batch, sp, lp, dp, A, precision="tc", return_trace=True))
+
+    monkeypatch.setattr(sparc_new, "TWO_STREAM_MIN_FRAMES", 64)
+    two = all_decoders(ys)
+    monkeypatch.setattr(sparc_new, "TWO_STREAM_MIN_FRAMES", 10 ** 9)
+    a, b, whole = all_decoders(ys[:cut]), all_decoders(ys[cut:]), all_decoders(ys)
+    for k in ("sep", "naive"):
+        assert np.array_equal(two[k], np.concatenate([a[k], b[k]]))
+    for k, parts in (("amp", 3), ("integ", 3)):
+        for i in range(parts):
+            assert np.array_equal(two[k][i], np.concatenate([a[k][i], b[k][i]])), (k, i)
+    truth = g[pre + "user_bits"]
+    assert np.allclose(two["amp"][2], whole["amp"][2], rtol=1e-5)
+    for k in ("sep", "naive"):
+        assert (two[k] != truth).any(axis=1).sum() == (whole[k] != truth).any(axis=1).sum()
