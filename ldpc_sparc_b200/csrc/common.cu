@@ -2,6 +2,9 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace lsb {
 
@@ -38,6 +41,21 @@ int max_smem_optin()
 {
     static int cache[64] = {0};
     return cached_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, cache);
+}
+
+cudaError_t ensure_dynamic_smem(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = granted[std::make_pair(kernel, dev)];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
 }
 
 }  // namespace lsb

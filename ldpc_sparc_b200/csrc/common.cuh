@@ -19,6 +19,15 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 int sm_count();
 int max_smem_optin();
 
+// Raise -- never lower -- the dynamic shared-memory limit of `kernel` on the current device.  The
+// attribute belongs to the (kernel, device) pair, not to a code / design handle: two handles of
+// different size sharing one template instantiation must not shrink it under each other.
+cudaError_t ensure_dynamic_smem(const void *kernel, size_t bytes);
+template <typename K> inline cudaError_t ensure_dynamic_smem(K kernel, size_t bytes)
+{
+    return ensure_dynamic_smem(reinterpret_cast<const void *>(kernel), bytes);
+}
+
 }  // namespace lsb
 
 #define LSB_CUDA(call)                                                          \

@@ -450,11 +450,7 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     int rc = make_map(&mx_hi, sg.x_hi, (uint64_t)F, (uint64_t)W.K);
     if (!rc) rc = make_map(&mx_lo, sg.x_lo, (uint64_t)F, (uint64_t)W.K);
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
-        LSB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
-    }
+    LSB_CUDA(lsb::ensure_dynamic_smem(tc_gemm_kernel, kSmemBytes));      // tracked per device
     const int n_row_tiles = (int)((W.rows + kTileRows - 1) / kTileRows), n_f_tiles = (int)((F + kTileN - 1) / kTileN);
     const int n_tiles = n_row_tiles * n_f_tiles, sms = lsb::sm_count();
     const int num_kb = (int)((W.K + kBlockK - 1) / kBlockK);

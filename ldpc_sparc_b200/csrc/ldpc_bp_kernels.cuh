@@ -460,8 +460,8 @@ int launch_qc_bucket(const QcLaunch<T> &a)
 {
     auto kern = bp_qc_kernel<T, ALGO, MAXDC, APG>;
     const size_t smem = APG ? a.smem_apg : a.smem;
+    LSB_CUDA(lsb::ensure_dynamic_smem(kern, smem));       // per (kernel, device), raise-only: other codes share kern
     if (*a.cached_grid == 0) {
-        LSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
         if (per_sm < 1) per_sm = 1;

@@ -18,8 +18,10 @@
 // and finally the MAP decision argmax_section(s) (:997).
 #include "common.cuh"
 #include "sparc_dct.cuh"
+#include "sparc_pair.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -570,6 +572,8 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     }
 }
 
+#include "sparc_amp_pair.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------ host side
@@ -586,6 +590,10 @@ struct lsb_sparc_design {
     size_t scratch_bytes = 0;
     cudaEvent_t scratch_event = nullptr;
     int amp_grid[2] = {0, 0};
+    // pair kernels (fp32, w = 2048 / 4096 / 8192): tables with their own swizzle, see sparc_pair.cuh
+    bool has_pair = false, full_columns = true;
+    PairDev pair{};
+    int amp_grid_pair = 0;
 };
 
 namespace {
@@ -670,6 +678,124 @@ template <typename T> const FftTables<T> &tables(const lsb_sparc_design *g);
 template <> const FftTables<float> &tables<float>(const lsb_sparc_design *g) { return g->tb32; }
 template <> const FftTables<double> &tables<double>(const lsb_sparc_design *g) { return g->tb64; }
 
+// LSB_AMP_PAIR=0 in the environment forces the one-frame kernels (A/B runs, tests of the generic path)
+bool pair_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("LSB_AMP_PAIR");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+bool pair_fits(const lsb_sparc_design *g)
+{
+    return g->has_pair && pair_enabled() &&
+           pair_amp_dyn_smem(g->dev.h, g->dev.n) + 12288 <= (size_t)lsb::max_smem_optin();
+}
+
+// Host-side tables of one non-zero block for the pair kernels (index conventions in sparc_pair.cuh).
+int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t *o0, const uint32_t *o1, PairBlock *pb)
+{
+    const int H = 1 << h, N = 2 * H, Hh = H / 2;
+    std::vector<int> inv0(N + 1, -1), inv1(N + 1, -1);
+    for (int i = 0; i < Mr; ++i) inv0[o0[i]] = i;
+    for (int j = 0; j < Mc; ++j) inv1[o1[j]] = j;
+    auto ent = [](int v) -> uint16_t { return v < 0 ? pairfft::kNone : (uint16_t)v; };
+    auto makhoul = [&](int p) -> int { return (p & 1) ? N - 1 - (p - 1) / 2 : p / 2; };
+    // forward, first radix-8 pass: butterfly q holds complex elements e = q + m H/8, packed z[e] = v[2e] + i v[2e+1],
+    // v the Makhoul permutation of the zero-padded column block
+    std::vector<uint16_t> fsrc((size_t)(H / 8) * 16);
+    for (int q = 0; q < H / 8; ++q)
+        for (int m = 0; m < 8; ++m)
+            for (int comp = 0; comp < 2; ++comp) {
+                const int mpos = 2 * (q + m * (H / 8)) + comp;
+                const int pidx = mpos < N / 2 ? 2 * mpos : 2 * (N - 1 - mpos) + 1;
+                fsrc[(size_t)q * 16 + 2 * m + comp] = ent(inv1[pidx]);
+            }
+    // forward gather: after post(), slot brev(k) holds (Y[k], Y[N-k]), slot 0 holds (Y[0], Y[H])
+    std::vector<uint16_t> fgat(Mr);
+    for (int i = 0; i < Mr; ++i) {
+        const int K = (int)o0[i];
+        int slot, comp;
+        if (K < H) { slot = K; comp = 0; }
+        else if (K == H) { slot = 0; comp = 1; }
+        else { slot = N - K; comp = 1; }
+        fgat[i] = (uint16_t)(2 * pairfft::pswz_rt(h, brev_host(slot, h)) + comp);
+    }
+    // transposed sources: pair k needs c[k], c[N-k] (slot k) and c[H-k], c[H+k] (slot H-k); slot 0 is (c[0], c[H])
+    std::vector<uint16_t> tsrc((size_t)(Hh + 1) * 4);
+    for (int k = 0; k <= Hh; ++k) {
+        tsrc[(size_t)k * 4 + 0] = ent(inv0[k]);
+        tsrc[(size_t)k * 4 + 1] = ent(k == 0 ? inv0[H] : inv0[N - k]);
+        tsrc[(size_t)k * 4 + 2] = ent(inv0[H - k]);
+        tsrc[(size_t)k * 4 + 3] = ent(inv0[H + k]);
+    }
+    std::vector<uint16_t> tgat(Mc);
+    for (int j = 0; j < Mc; ++j) {
+        const int m = makhoul((int)o1[j]);
+        tgat[j] = (uint16_t)(2 * pairfft::pswz_rt(h, brev_host(m >> 1, h)) + (m & 1));
+    }
+    int rc;
+    if ((rc = dev_upload(g, &pb->fsrc, fsrc))) return rc;
+    if ((rc = dev_upload(g, &pb->fgat, fgat))) return rc;
+    if ((rc = dev_upload(g, &pb->tsrc, tsrc))) return rc;
+    return dev_upload(g, &pb->tgat, tgat);
+}
+
+// Per-size tables of the pair kernels: real-FFT twiddles (0.5 pt[k], pt[k]^4) in natural and in
+// bit-reversed pair order, and the swizzled slots of the post-processing pairs.
+int build_pair_tables(lsb_sparc_design *g, int h)
+{
+    const int H = 1 << h, Hh = H / 2;
+    const double N = 2.0 * H, PI = 3.14159265358979323846;
+    auto entry = [&](int k) {
+        const double a = PI * k / (2 * N), b = 2 * PI * k / N;
+        return float4{(float)(0.5 * cos(a)), (float)(-0.5 * sin(a)), (float)cos(b), (float)-sin(b)};
+    };
+    std::vector<float4> pre(Hh + 1), post(Hh + 1);
+    std::vector<uint32_t> slot(Hh + 1);
+    for (int k = 0; k <= Hh; ++k) pre[k] = entry(k);
+    for (int t = 0; t <= Hh; ++t) {
+        const int k = t == Hh ? Hh : brev_host(t, h - 1);
+        post[t] = entry(k);
+        const int pa = pairfft::pswz_rt(h, brev_host(k, h)), pb = pairfft::pswz_rt(h, brev_host((H - k) & (H - 1), h));
+        slot[t] = (uint32_t)pa | ((uint32_t)pb << 16);
+    }
+    g->pair.tb.tw = g->tb32.tw;
+    int rc;
+    if ((rc = dev_upload(g, &g->pair.tb.pre, pre))) return rc;
+    if ((rc = dev_upload(g, &g->pair.tb.post, post))) return rc;
+    return dev_upload(g, &g->pair.tb.post_slot, slot);
+}
+
+template <int LOGH>
+int launch_op_pair_h(lsb_sparc_design *g, bool transpose, const float *in, float *out, int64_t n_frames, cudaStream_t st)
+{
+    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n);
+    long long grid = (long long)lsb::sm_count() * 3;
+    if (grid > (n_frames + 1) / 2) grid = (n_frames + 1) / 2;
+    if (transpose) {
+        LSB_CUDA(lsb::ensure_dynamic_smem(az_pair_kernel<LOGH>, smem));
+        az_pair_kernel<LOGH><<<(unsigned)grid, kPairThreads, smem, st>>>(g->dev, g->pair, in, out, (long long)n_frames);
+    } else {
+        LSB_CUDA(lsb::ensure_dynamic_smem(ab_pair_kernel<LOGH>, smem));
+        ab_pair_kernel<LOGH><<<(unsigned)grid, kPairThreads, smem, st>>>(g->dev, g->pair, in, out, (long long)n_frames);
+    }
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+int launch_op_pair(lsb_sparc_design *g, bool transpose, const float *in, float *out, int64_t n_frames, cudaStream_t st)
+{
+    switch (g->dev.h) {
+        case 10: return launch_op_pair_h<10>(g, transpose, in, out, n_frames, st);
+        case 11: return launch_op_pair_h<11>(g, transpose, in, out, n_frames, st);
+        default: return launch_op_pair_h<12>(g, transpose, in, out, n_frames, st);
+    }
+}
+
 template <typename T, bool GBUF>
 int launch_op(lsb_sparc_design *g, bool transpose, const T *in, T *out, int64_t n_frames, long long grid,
               cudaStream_t st)
@@ -679,11 +805,11 @@ int launch_op(lsb_sparc_design *g, bool transpose, const T *in, T *out, int64_t 
                 lsb::max_smem_optin());
     T *gbuf = GBUF ? (T *)g->d_scratch : nullptr;
     if (transpose) {
-        LSB_CUDA(cudaFuncSetAttribute(az_kernel<T, GBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSB_CUDA(lsb::ensure_dynamic_smem(az_kernel<T, GBUF>, smem));
         az_kernel<T, GBUF><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out,
                                                                   (long long)n_frames, gbuf);
     } else {
-        LSB_CUDA(cudaFuncSetAttribute(ab_kernel<T, GBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LSB_CUDA(lsb::ensure_dynamic_smem(ab_kernel<T, GBUF>, smem));
         ab_kernel<T, GBUF><<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), in, out,
                                                                   (long long)n_frames, gbuf);
     }
@@ -702,6 +828,9 @@ int run_op(const lsb_sparc_design *cg, bool transpose, const T *in, T *out, int6
     if (n_frames == 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
+    if constexpr (sizeof(T) == 4) {
+        if (pair_fits(g)) return launch_op_pair(g, transpose, in, out, n_frames, st);
+    }
     long long grid = (long long)lsb::sm_count() * 4;
     if (grid > n_frames) grid = n_frames;
     if (!needs_gbuf(g->dev, sizeof(T))) return launch_op<T, false>(g, transpose, in, out, n_frames, grid, st);
@@ -734,6 +863,45 @@ AmpKernelFn<T> pick_amp_kernel(bool gbuf, int h)
     return amp_kernel<T, false, 0>;
 }
 
+template <int LOGH>
+int launch_amp_pair_h(lsb_sparc_design *g, const float *y, int64_t n_frames, const AmpParams &p, const int32_t *idx0,
+                      const AmpOut &o, cudaStream_t st)
+{
+    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n);
+    auto kernel = amp_pair_kernel<LOGH>;
+    LSB_CUDA(lsb::ensure_dynamic_smem(kernel, smem));
+    if (g->amp_grid_pair == 0) {
+        int per_sm = 0;
+        LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPairThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        g->amp_grid_pair = per_sm * lsb::sm_count();
+    }
+    const long long pairs = (n_frames + 1) / 2;
+    const long long grid = g->amp_grid_pair < pairs ? g->amp_grid_pair : pairs;
+    const size_t need = (size_t)g->amp_grid_pair * ((size_t)g->dev.L * g->dev.M + (size_t)g->dev.Mc) * sizeof(float2);
+    std::lock_guard<std::mutex> lock(g->mu);
+    int rc;
+    if ((rc = ensure_scratch(g, need, st))) return rc;
+    unsigned long long *queue = g->d_queue + (g->next_queue.fetch_add(1) % kCounters);
+    LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
+    kernel<<<(unsigned)grid, kPairThreads, smem, st>>>(g->dev, g->pair, p, y, idx0, o, (float2 *)g->d_scratch,
+                                                      (long long)n_frames, queue);
+    lsb::count_launch();
+    LSB_CUDA(cudaGetLastError());
+    LSB_CUDA(cudaEventRecord(g->scratch_event, st));
+    return LSB_OK;
+}
+
+int launch_amp_pair(lsb_sparc_design *g, const float *y, int64_t n_frames, const AmpParams &p, const int32_t *idx0,
+                    const AmpOut &o, cudaStream_t st)
+{
+    switch (g->dev.h) {
+        case 10: return launch_amp_pair_h<10>(g, y, n_frames, p, idx0, o, st);
+        case 11: return launch_amp_pair_h<11>(g, y, n_frames, p, idx0, o, st);
+        default: return launch_amp_pair_h<12>(g, y, n_frames, p, idx0, o, st);
+    }
+}
+
 template <typename T>
 int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_amp_params *pp,
             const int32_t *idx0, const lsb_sparc_amp_out *po, cudaStream_t st)
@@ -747,15 +915,24 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     if (n_frames == 0) return LSB_OK;
     int rc = check_device(g);
     if (rc) return rc;
+    LSB_REQUIRE(pp->modulation >= 0 && pp->modulation <= 2, "modulation must be 1 (none) or 2 (real 2-PSK)");
+    if constexpr (sizeof(T) == 4) {
+        // throughput path: two frames per CTA on the packed-fp32 transforms (sparc_amp_pair.cuh)
+        if (pair_fits(g) && g->full_columns && pp->modulation != 2 && g->dev.M <= 32 && !po->beta_soft && !po->s_last) {
+            AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method, 1};
+            AmpOut o{po->idx, po->t_final, po->psi, po->nmse, nullptr, nullptr, po->tau_trace, po->psi_trace};
+            return launch_amp_pair(g, y, n_frames, p, idx0, o, st);
+        }
+    }
     const bool gbuf = needs_gbuf(g->dev, sizeof(T));
     const size_t smem = amp_smem(g->dev, sizeof(T), gbuf);
     LSB_REQUIRE(smem + 8192 <= (size_t)lsb::max_smem_optin(),
                 "design needs %zu B of shared memory per CTA (n = %d): unsupported", smem, g->dev.n);
     const AmpKernelFn<T> kernel = pick_amp_kernel<T>(gbuf, g->dev.h);
     int &cached = g->amp_grid[sizeof(T) == 8];
+    LSB_CUDA(lsb::ensure_dynamic_smem(kernel, smem));      // per (kernel, device), raise-only: other designs share it
     if (cached == 0) {
         int per_sm = 0;
-        LSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
         if (per_sm < 1) per_sm = 1;
         if (gbuf) {
@@ -775,7 +952,6 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     if ((rc = ensure_scratch(g, need, st))) return rc;
     unsigned long long *queue = g->d_queue + (g->next_queue.fetch_add(1) % kCounters);
     LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
-    LSB_REQUIRE(pp->modulation >= 0 && pp->modulation <= 2, "modulation must be 1 (none) or 2 (real 2-PSK)");
     AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method, pp->modulation == 2 ? 2 : 1};
     AmpOut o{po->idx, po->t_final, po->psi, po->nmse, po->beta_soft, po->s_last, po->tau_trace, po->psi_trace};
     kernel<<<(unsigned)grid, kThreads, smem, st>>>(g->dev, tables<T>(g), p, y, idx0, o, (T *)g->d_scratch,
@@ -816,6 +992,8 @@ int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n
     }
     int rc = LSB_OK;
     std::vector<BlockDev> blocks;
+    std::vector<PairBlock> pair_blocks;
+    const bool want_pair = h >= 10 && h <= 12;
     std::vector<int> col_first(Lc + 1, 0);
     std::vector<uint16_t> t_abs(Mc), t_abg(Mr), t_azs(Mr), t_azg(Mc);
     auto slot_of_freq = [&](int K, bool reversed) -> int {   // where (Y[K]) / (c[K]) lives
@@ -859,6 +1037,14 @@ int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n
             if ((rc = dev_upload(g, &b.az_scatter, t_azs))) break;
             if ((rc = dev_upload(g, &b.az_gather, t_azg))) break;
             blocks.push_back(b);
+            if (want_pair) {
+                PairBlock pb{};
+                pb.r = r;
+                pb.c = c;
+                pb.scale = b.scale;
+                if ((rc = build_pair_block(g, h, Mr, Mc, o0, o1, &pb))) break;
+                pair_blocks.push_back(pb);
+            }
         }
     }
     col_first[Lc] = (int)blocks.size();
@@ -873,6 +1059,13 @@ int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n
     if (!rc) rc = dev_upload(g, &d.W, std::vector<double>(W, W + (size_t)Lr * Lc));
     if (!rc) rc = make_tables<float, float2>(g, &g->tb32, h);
     if (!rc) rc = make_tables<double, double2>(g, &g->tb64, h);
+    if (!rc && want_pair) {
+        rc = dev_upload(g, &g->pair.blocks, pair_blocks);
+        if (!rc) rc = build_pair_tables(g, h);
+        g->has_pair = !rc;
+        for (int c = 0; c < Lc; ++c)
+            if (col_first[c] == col_first[c + 1]) g->full_columns = false;
+    }
     if (!rc) {
         cudaError_t e = cudaMalloc((void **)&g->d_queue, kCounters * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemset(g->d_queue, 0, kCounters * sizeof(unsigned long long));

@@ -474,7 +474,7 @@ int run_cop(lsb_csparc_design *g, const void *in, void *out, int64_t n_frames, c
     const size_t smem = op_smem(g->dev, sizeof(T2), gbuf);
     LSB_REQUIRE(smem + 8192 <= (size_t)lsb::max_smem_optin(),
                 "complex design needs %zu B of shared memory per CTA (n = %d): unsupported", smem, g->dev.n);
-    LSB_CUDA(cudaFuncSetAttribute(cop_kernel<T, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSB_CUDA(lsb::ensure_dynamic_smem(cop_kernel<T, TRANS>, smem));
     long long grid = 2LL * lsb::sm_count();
     if (grid > n_frames) grid = n_frames;
     std::lock_guard<std::mutex> lock(g->mu);
@@ -507,7 +507,7 @@ int run_camp(lsb_csparc_design *g, const void *y, int64_t n_frames, const lsb_sp
     const size_t smem = op_smem(g->dev, sizeof(T2), gbuf);
     LSB_REQUIRE(smem + 8192 <= (size_t)lsb::max_smem_optin(),
                 "complex design needs %zu B of shared memory per CTA (n = %d): unsupported", smem, g->dev.n);
-    LSB_CUDA(cudaFuncSetAttribute(camp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSB_CUDA(lsb::ensure_dynamic_smem(camp_kernel<T>, smem));
     int per_sm = 0;
     LSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, camp_kernel<T>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;

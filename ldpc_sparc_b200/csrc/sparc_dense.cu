@@ -242,9 +242,16 @@ __global__ void section_to_bit_kernel(const T *__restrict__ beta, T *__restrict_
             // 1 - 1e-15 is not an fp32 number, so the clip is applied to the result instead: for p inside
             // [1e-15, 1 - 1e-15] nothing changes, outside it the reference's LLR is +-log((1 - 1e-15) / 1e-15);
             // 1 - p is exact in fp32 for p >= 1/2.  (Was two fp64 logs per bit: 135 -> ~45 us at config 5.)
+            // The fp32 sum of softmax entries can round a saturated probability to 1 + ulp (or below 0):
+            // log of a negative number is NaN and fminf/fmaxf would turn it into -lim, the wrong sign.
+            // Saturate explicitly, as the reference's clip does (p >= 1 -> +lim, p <= 0 -> -lim).
             const float lim = 34.538776f;
-            const float v = logf((float)p) - logf(1.0f - (float)p);
-            llr[i] = (T)fminf(fmaxf(v, -lim), lim);
+            const float pf = (float)p;
+            float v;
+            if (pf >= 1.0f) v = lim;
+            else if (pf <= 0.0f) v = -lim;
+            else v = fminf(fmaxf(logf(pf) - logf(1.0f - pf), -lim), lim);
+            llr[i] = (T)v;
         }
     }
 }

@@ -60,6 +60,37 @@ def test_glue_kernels_vs_oracle():
         assert np.max(np.abs(e32 - e_ref)) < 1e-5
 
 
+def test_section_to_bit_saturated_fp32_sign():
+    """fp32 section mass that sums to >= 1 (or <= 0) on one side of a bit must give the reference's clipped
+    LLR +-log((1-1e-15)/1e-15) with the right sign, never a NaN turned into -lim (sparc_new.py:1166-1169)."""
+    import torch
+    from ldpc_sparc_b200 import _lib
+    M, logM, L = 8, 3, 64
+    sq = np.float32(1.7)
+    rng = np.random.RandomState(5)
+    beta = np.zeros((L, M), dtype=np.float32)
+    for sec in range(L):
+        # all of the mass on entries whose MSB is 0, split over 2-3 entries so the fp32 sum of beta_j/sq can exceed 1
+        js = rng.choice(4, size=rng.randint(2, 4), replace=False)
+        wts = rng.dirichlet(np.ones(len(js))).astype(np.float32)
+        beta[sec, js] = np.nextafter(wts * sq, np.float32(np.inf))
+    bd = torch.from_numpy(beta.reshape(1, -1)).cuda()
+    probs = torch.empty((1, L * logM), dtype=torch.float32, device="cuda")
+    llr = torch.empty_like(probs)
+    _lib.check(_lib.lib().lsb_section_to_bit_dev_f32(bd.data_ptr(), probs.data_ptr(), llr.data_ptr(), L, M, float(sq),
+                                                     torch.cuda.current_stream().cuda_stream), "section_to_bit")
+    p = probs.cpu().numpy().reshape(L, logM)
+    v = llr.cpu().numpy().reshape(L, logM)
+    assert np.isfinite(v).all()
+    assert (p[:, 0] >= 1.0).any(), "the case must exercise a probability that rounds to >= 1"
+    lim = np.float32(34.538776)
+    assert np.all(v[:, 0] > 30.0), "MSB is certainly 0: LLR must saturate positive"
+    assert np.all(v[p >= 1.0] == lim) and np.all(v[p <= 0.0] == -lim)
+    ref = np.log(np.clip(p.astype(np.float64), 1e-15, 1 - 1e-15)) - np.log1p(-np.clip(p.astype(np.float64), 1e-15, 1 - 1e-15))
+    inside = (p > 0) & (p < 1)
+    assert np.max(np.abs(v[inside] - ref[inside]) / np.maximum(1.0, np.abs(ref[inside]))) < 1e-5
+
+
 def test_ldpc_bp_wrapper_vs_oracle():
     c = ldpc.code("802.16", "1/2", 27)
     rng = np.random.RandomState(2)
