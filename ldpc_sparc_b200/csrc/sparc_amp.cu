@@ -691,29 +691,41 @@ bool pair_enabled()
 bool pair_fits(const lsb_sparc_design *g)
 {
     return g->has_pair && pair_enabled() &&
-           pair_amp_dyn_smem(g->dev.h, g->dev.n) + 12288 <= (size_t)lsb::max_smem_optin();
+           pair_amp_dyn_smem(g->dev.h, g->dev.n, g->dev.Lr, g->dev.Lc) + 4096 <= (size_t)lsb::max_smem_optin();
+}
+
+// "chunked" layout of a per-element uint16 table (sparc_pair.cuh): element tid + 256 u sits at [u / 4][tid][u % 4]
+std::vector<uint16_t> chunked(const std::vector<uint16_t> &v)
+{
+    const int n = (int)v.size(), nc = pairfft::chunk_count(n);
+    std::vector<uint16_t> out((size_t)nc * kPairThreads * 4, pairfft::kNone);
+    for (int i = 0; i < n; ++i) {
+        const int tid = i % kPairThreads, u = i / kPairThreads;
+        out[((size_t)(u / 4) * kPairThreads + tid) * 4 + (u % 4)] = v[i];
+    }
+    return out;
 }
 
 // Host-side tables of one non-zero block for the pair kernels (index conventions in sparc_pair.cuh).
 int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t *o0, const uint32_t *o1, PairBlock *pb)
 {
-    const int H = 1 << h, N = 2 * H, Hh = H / 2;
+    const int H = 1 << h, N = 2 * H, Hh = H / 2, NB = H / 8;
     std::vector<int> inv0(N + 1, -1), inv1(N + 1, -1);
     for (int i = 0; i < Mr; ++i) inv0[o0[i]] = i;
     for (int j = 0; j < Mc; ++j) inv1[o1[j]] = j;
     auto ent = [](int v) -> uint16_t { return v < 0 ? pairfft::kNone : (uint16_t)v; };
     auto makhoul = [&](int p) -> int { return (p & 1) ? N - 1 - (p - 1) / 2 : p / 2; };
     // forward, first radix-8 pass: butterfly q holds complex elements e = q + m H/8, packed z[e] = v[2e] + i v[2e+1],
-    // v the Makhoul permutation of the zero-padded column block
-    std::vector<uint16_t> fsrc((size_t)(H / 8) * 16);
-    for (int q = 0; q < H / 8; ++q)
+    // v the Makhoul permutation of the zero-padded column block.  Layout [half][q][4 words], word = re | im << 16.
+    std::vector<uint16_t> fsrc((size_t)2 * NB * 8);
+    for (int q = 0; q < NB; ++q)
         for (int m = 0; m < 8; ++m)
             for (int comp = 0; comp < 2; ++comp) {
-                const int mpos = 2 * (q + m * (H / 8)) + comp;
+                const int mpos = 2 * (q + m * NB) + comp;
                 const int pidx = mpos < N / 2 ? 2 * mpos : 2 * (N - 1 - mpos) + 1;
-                fsrc[(size_t)q * 16 + 2 * m + comp] = ent(inv1[pidx]);
+                fsrc[((size_t)(m / 4) * NB + q) * 8 + 2 * (m % 4) + comp] = ent(inv1[pidx]);
             }
-    // forward gather: after post(), slot brev(k) holds (Y[k], Y[N-k]), slot 0 holds (Y[0], Y[H])
+    // forward gather: after the post-processing slot brev(k) holds (Y[k], Y[N-k]), slot 0 holds (Y[0], Y[H])
     std::vector<uint16_t> fgat(Mr);
     for (int i = 0; i < Mr; ++i) {
         const int K = (int)o0[i];
@@ -737,23 +749,29 @@ int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t 
         tgat[j] = (uint16_t)(2 * pairfft::pswz_rt(h, brev_host(m >> 1, h)) + (m & 1));
     }
     int rc;
-    if ((rc = dev_upload(g, &pb->fsrc, fsrc))) return rc;
-    if ((rc = dev_upload(g, &pb->fgat, fgat))) return rc;
-    if ((rc = dev_upload(g, &pb->tsrc, tsrc))) return rc;
-    return dev_upload(g, &pb->tgat, tgat);
+    const uint16_t *p16 = nullptr;
+    if ((rc = dev_upload(g, &p16, fsrc))) return rc;
+    pb->fsrc = reinterpret_cast<const uint4 *>(p16);
+    if ((rc = dev_upload(g, &p16, chunked(fgat)))) return rc;
+    pb->fgat = reinterpret_cast<const uint2 *>(p16);
+    if ((rc = dev_upload(g, &p16, tsrc))) return rc;
+    pb->tsrc = reinterpret_cast<const uint2 *>(p16);
+    if ((rc = dev_upload(g, &p16, chunked(tgat)))) return rc;
+    pb->tgat = reinterpret_cast<const uint2 *>(p16);
+    return LSB_OK;
 }
 
-// Per-size tables of the pair kernels: real-FFT twiddles (0.5 pt[k], pt[k]^4) in natural and in
-// bit-reversed pair order, and the swizzled slots of the post-processing pairs.
+// Per-size tables of the pair kernels: 0.5 pt[k] in natural and in bit-reversed pair order, and the
+// swizzled slots of the post-processing pairs.
 int build_pair_tables(lsb_sparc_design *g, int h)
 {
     const int H = 1 << h, Hh = H / 2;
     const double N = 2.0 * H, PI = 3.14159265358979323846;
     auto entry = [&](int k) {
-        const double a = PI * k / (2 * N), b = 2 * PI * k / N;
-        return float4{(float)(0.5 * cos(a)), (float)(-0.5 * sin(a)), (float)cos(b), (float)-sin(b)};
+        const double a = PI * k / (2 * N);
+        return float2{(float)(0.5 * cos(a)), (float)(-0.5 * sin(a))};
     };
-    std::vector<float4> pre(Hh + 1), post(Hh + 1);
+    std::vector<float2> pre(Hh + 1), post(Hh + 1);
     std::vector<uint32_t> slot(Hh + 1);
     for (int k = 0; k <= Hh; ++k) pre[k] = entry(k);
     for (int t = 0; t <= Hh; ++t) {
@@ -772,7 +790,7 @@ int build_pair_tables(lsb_sparc_design *g, int h)
 template <int LOGH>
 int launch_op_pair_h(lsb_sparc_design *g, bool transpose, const float *in, float *out, int64_t n_frames, cudaStream_t st)
 {
-    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n);
+    const size_t smem = pair_op_dyn_smem(LOGH, g->dev.n);
     long long grid = (long long)lsb::sm_count() * 3;
     if (grid > (n_frames + 1) / 2) grid = (n_frames + 1) / 2;
     if (transpose) {
@@ -867,7 +885,7 @@ template <int LOGH>
 int launch_amp_pair_h(lsb_sparc_design *g, const float *y, int64_t n_frames, const AmpParams &p, const int32_t *idx0,
                       const AmpOut &o, cudaStream_t st)
 {
-    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n);
+    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc);
     auto kernel = amp_pair_kernel<LOGH>;
     LSB_CUDA(lsb::ensure_dynamic_smem(kernel, smem));
     if (g->amp_grid_pair == 0) {

@@ -31,7 +31,7 @@ struct PairDev {
 
 struct SrcPair {                   // column block stored as float2 (A, B) per entry
     const float2 *p;
-    __device__ __forceinline__ P get(unsigned i) const { return p[i]; }
+    __device__ __forceinline__ P get(unsigned i) const { return __ldcg(p + i); }     // written by this CTA: L2, no L1 allocation
 };
 struct SrcTwo {                    // the two frames' column blocks in two separate arrays
     const float *a, *b;
@@ -51,27 +51,21 @@ __device__ __forceinline__ float fast_rcp(float x)
     return y;
 }
 
-// dst2[i] += sc * Y[tab[i]] for the rows of one block (Y: float2 view of the pair buffer)
-__device__ __forceinline__ void pair_gather_add(float2 *dst2, const float4 *buf, const uint16_t *__restrict__ tab, float sc,
-                                                int count, int tid)
+// per-CTA scalar state of the two frames, carved from dynamic shared memory behind the residual
+// (sized by the design's Lr / Lc, so that three CTAs leave the L1 room for the transform tables)
+struct PairScalars {
+    double *psi, *psi_prev, *tau, *nm;        // [2][Lc]
+    double *phi, *gam, *zsq;                  // [2][Lr]
+    float2 *tau_f, *itau_f;                   // [Lc] tau_c, log2(e) / tau_c          (A, B)
+    float2 *iphi_f, *coef_f;                  // [Lr] 1 / phi_r, gamma_r / phi_prev_r (A, B)
+};
+__host__ __device__ inline size_t pair_scalar_bytes(int Lr, int Lc)
 {
-    const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
-    for (int i0 = tid; i0 < count; i0 += kPairThreads * kBatch) {
-        int id[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int i = i0 + u * kPairThreads;
-            id[u] = i < count ? (int)__ldg(tab + i) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int i = i0 + u * kPairThreads;
-            if (i < count) dst2[i] = pairfft::pfmas(bf2[id[u]], sc, dst2[i]);
-        }
-    }
+    return (size_t)(4 * 2 * Lc + 3 * 2 * Lr) * sizeof(double) + (size_t)(2 * Lc + 2 * Lr) * sizeof(float2);
 }
-
-size_t pair_amp_dyn_smem(int h, int n) { return ((size_t)16 << h) + (size_t)n * sizeof(float2); }
+__host__ __device__ inline size_t pair_vec_bytes(int h, int n) { return ((size_t)16 << h) + (((size_t)n * sizeof(float2) + 15) & ~(size_t)15); }
+size_t pair_op_dyn_smem(int h, int n) { return pair_vec_bytes(h, n); }
+size_t pair_amp_dyn_smem(int h, int n, int Lr, int Lc) { return pair_vec_bytes(h, n) + pair_scalar_bytes(Lr, Lc); }
 
 // ------------------------------------------------------------------ operators
 // out[f, n] = A x[f, LM] for frame pairs (reference Ab, sparc.py:786-789,811-819,851-862)
@@ -88,12 +82,20 @@ ab_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ x, float *__re
     for (long long fA = 2LL * blockIdx.x; fA < n_frames; fA += 2LL * gridDim.x) {
         const long long fB = fA + 1 < n_frames ? fA + 1 : fA;
         for (int i = tid; i < d.n; i += kPairThreads) acc2[i] = make_float2(0.f, 0.f);
+        PairBlock b = pd.blocks[0];
+        pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid);
         for (int bi = 0; bi < d.n_blocks; ++bi) {
-            const PairBlock b = pd.blocks[bi];
             const size_t off = (size_t)b.c * d.Mc;
-            pairfft::forward<LOGH>(buf, pd.tb, b, SrcTwo{x + fA * LM + off, x + fB * LM + off}, tid);
-            pair_gather_add(acc2 + b.r * d.Mr, buf, b.fgat, b.scale, d.Mr, tid);
+            const pairfft::GatPre g =
+                pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcTwo{x + fA * LM + off, x + fB * LM + off}, fin, d.Mr, tid);
+            PairBlock bn = b;
+            if (bi + 1 < d.n_blocks) {
+                bn = pd.blocks[bi + 1];
+                fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid);
+            }
+            pairfft::gather_add(acc2 + b.r * d.Mr, buf, g, b.fgat, b.scale, d.Mr, tid);
             __syncthreads();
+            b = bn;
         }
         for (int i = tid; i < d.n; i += kPairThreads) {
             const float2 v = acc2[i];
@@ -124,17 +126,25 @@ az_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ y, float *__re
             const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
             for (int bi = b0; bi < b1; ++bi) {
                 const PairBlock b = pd.blocks[bi];
-                pairfft::transposed<LOGH>(buf, pd.tb, b, y2 + b.r * d.Mr, tid);
+                const pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid);
+                pairfft::transposed_run<LOGH>(buf, pd.tb, b, y2 + b.r * d.Mr, tin, tid, [] { return 0; });
                 const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
-                for (int j = tid; j < d.Mc; j += kPairThreads) {
-                    const float2 v = bf2[__ldg(b.tgat + j)];
-                    const float va = b.scale * v.x, vb = b.scale * v.y;
-                    if (bi == b0) {
-                        oA[j] = va;
-                        if (fB != fA) oB[j] = vb;
-                    } else {
-                        oA[j] += va;
-                        if (fB != fA) oB[j] += vb;
+                for (int ch = 0; ch < pairfft::chunk_count(d.Mc); ++ch) {
+                    const uint2 e = pairfft::ldg_na(b.tgat + ch * kPairThreads + tid);
+                    const unsigned id[4] = {e.x & 0xFFFFu, e.x >> 16, e.y & 0xFFFFu, e.y >> 16};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = tid + (4 * ch + u) * kPairThreads;
+                        if (j >= d.Mc) continue;
+                        const float2 v = bf2[id[u]];
+                        const float va = b.scale * v.x, vb = b.scale * v.y;
+                        if (bi == b0) {
+                            oA[j] = va;
+                            if (fB != fA) oB[j] = vb;
+                        } else {
+                            oA[j] += va;
+                            if (fB != fA) oB[j] += vb;
+                        }
                     }
                 }
                 __syncthreads();
@@ -150,6 +160,11 @@ az_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ y, float *__re
 }
 
 // ------------------------------------------------------------------ AMP
+struct OutPre {                    // first chunk of the gather after a transposed transform: 4 slots + the 4 addends
+    uint2 ids;
+    float2 pv[4];
+};
+
 // Requirements checked by the host: fp32, unmodulated (K = 1), M <= 32, every column block has at least
 // one non-zero base-matrix entry, no soft outputs (beta_soft / s_last), H = 2^LOGH.
 // scratch per CTA: [LM] float2 beta (A, B) then [Mc] float2 partial s of the current column.
@@ -164,10 +179,15 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
     constexpr int kWarps = kPairThreads / 32;
     float4 *buf = reinterpret_cast<float4 *>(smem);           // [H] (re_A, re_B, im_A, im_B)
     float2 *z2 = reinterpret_cast<float2 *>(buf + H);         // [n] residual of frame A / frame B
-    __shared__ double psi[2][kMaxLc], psi_prev[2][kMaxLc], tau[2][kMaxLc], nm[2][kMaxLc];
-    __shared__ double phi[2][kMaxLr], gam[2][kMaxLr], zsq[2][kMaxLr];
-    __shared__ float2 tau_f[kMaxLc], itau_f[kMaxLc];          // tau_c, log2(e) / tau_c          (A, B)
-    __shared__ float2 iphi_f[kMaxLr], coef_f[kMaxLr];         // 1 / phi_r, gamma_r / phi_prev_r (A, B)
+    PairScalars S;
+    {
+        double *dp = reinterpret_cast<double *>(smem + pair_vec_bytes(LOGH, d.n));
+        S.psi = dp; S.psi_prev = dp + 2 * d.Lc; S.tau = dp + 4 * d.Lc; S.nm = dp + 6 * d.Lc;
+        dp += 8 * d.Lc;
+        S.phi = dp; S.gam = dp + 2 * d.Lr; S.zsq = dp + 4 * d.Lr;
+        float2 *fp = reinterpret_cast<float2 *>(dp + 6 * d.Lr);
+        S.tau_f = fp; S.itau_f = fp + d.Lc; S.iphi_f = fp + 2 * d.Lc; S.coef_f = fp + 2 * d.Lc + d.Lr;
+    }
     __shared__ double part_psi[2][kWarps][2], part_nm[2][kWarps][2];   // [column parity][warp][frame]
     __shared__ double part_z[kWarps][2];
     __shared__ long long s_frame;
@@ -175,6 +195,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = (tid >> 6) & 1, ix = tid & 63;             // scalar work: threads 0..127 = (frame, index)
+    const int Lr = d.Lr, Lc = d.Lc;
     const int LM = d.L * d.M;
     float2 *beta2 = scratch + (size_t)blockIdx.x * ((size_t)LM + d.Mc);
     float2 *s2col = beta2 + LM;
@@ -183,6 +204,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
     const int M = d.M, logM = d.logM;
     const unsigned grp_base = (unsigned)lane & ~(unsigned)(M - 1);
     const unsigned grp_mask = M == 32 ? 0xffffffffu : (((1u << M) - 1u) << grp_base);
+    const int col_lines = (d.Mc * (int)sizeof(float2) + 127) / 128;     // 128-byte lines of one column block of beta
 
     for (;;) {
         if (tid == 0) s_frame = (long long)atomicAdd(queue, 2ull);
@@ -196,8 +218,8 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
 
         for (int i = tid; i < d.n; i += kPairThreads) z2[i] = make_float2(yA[i], yB[i]);      // z = y (:915)
         if (tid < 128) {
-            if (ix < d.Lc) psi[fr][ix] = 1.0;                                                 // gamma = W.1/Lc (:918,926)
-            phi[fr][ix] = 0.0;
+            if (ix < Lc) S.psi[fr * Lc + ix] = 1.0;                                           // gamma = W.1/Lc (:918,926)
+            if (ix < Lr) S.phi[fr * Lr + ix] = 0.0;
         }
         if (tid < 2) s_active[tid] = tid == 0 ? 1 : (hasB ? 1 : 0);
         __syncthreads();
@@ -206,37 +228,49 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
         for (; t < p.t_max - 1; ++t) {
             // ---- gamma_r, the Onsager coefficient gamma_r / phi_prev_r (phi still holds the previous iteration's)
             if (tid < 128) {
-                if (ix < d.Lr) {
+                if (ix < Lr) {
                     double g = 0.0;
-                    for (int c = 0; c < d.Lc; ++c) g += d.W[ix * d.Lc + c] * psi[fr][c];
-                    g /= d.Lc;
-                    gam[fr][ix] = g;
-                    reinterpret_cast<float *>(&coef_f[ix])[fr] = t > 0 ? (float)(g / phi[fr][ix]) : 0.f;
-                    zsq[fr][ix] = 0.0;
+                    for (int c = 0; c < Lc; ++c) g += d.W[ix * Lc + c] * S.psi[fr * Lc + c];
+                    g /= Lc;
+                    S.gam[fr * Lr + ix] = g;
+                    reinterpret_cast<float *>(&S.coef_f[ix])[fr] = t > 0 ? (float)(g / S.phi[fr * Lr + ix]) : 0.f;
+                    S.zsq[fr * Lr + ix] = 0.0;
                 }
-                if (ix < d.Lc) psi_prev[fr][ix] = psi[fr][ix];
+                if (ix < Lc) S.psi_prev[fr * Lc + ix] = S.psi[fr * Lc + ix];
             }
             __syncthreads();
             if (t > 0) {
                 // z = y - A beta + b z (:944-946): z <- y + b z, then every block subtracts its A_rc beta_c.
-                // Row i is owned by thread i mod 256 here and in pair_gather_add: no barrier in between.
-                if (d.Lr == 1) {
-                    const float2 cf = coef_f[0];
+                // Row i is owned by thread i mod 256 here and in gather_add: no barrier in between.
+                PairBlock b = pd.blocks[0];
+                pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid);
+                if (d.n_blocks > 1 && tid < col_lines) pairfft::prefetch_l2(beta2 + (size_t)pd.blocks[1].c * d.Mc + tid * 16);
+                if (Lr == 1) {
+                    const float2 cf = S.coef_f[0];
                     for (int i = tid; i < d.n; i += kPairThreads) z2[i] = pairfft::pfma(z2[i], cf, make_float2(yA[i], yB[i]));
                 } else {
                     for (int i = tid; i < d.n; i += kPairThreads)
-                        z2[i] = pairfft::pfma(z2[i], coef_f[i / d.Mr], make_float2(yA[i], yB[i]));
+                        z2[i] = pairfft::pfma(z2[i], S.coef_f[i / d.Mr], make_float2(yA[i], yB[i]));
                 }
                 for (int bi = 0; bi < d.n_blocks; ++bi) {
-                    const PairBlock b = pd.blocks[bi];
-                    pairfft::forward<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, tid);
-                    pair_gather_add(z2 + b.r * d.Mr, buf, b.fgat, -b.scale, d.Mr, tid);
+                    const pairfft::GatPre g =
+                        pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, fin, d.Mr, tid);
+                    PairBlock bn = b;
+                    if (bi + 1 < d.n_blocks) {
+                        bn = pd.blocks[bi + 1];
+                        fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid);
+                        // the column block after that: pull it into L2 (beta streams through DRAM between iterations)
+                        if (bi + 2 < d.n_blocks && tid < col_lines)
+                            pairfft::prefetch_l2(beta2 + (size_t)pd.blocks[bi + 2].c * d.Mc + tid * 16);
+                    }
+                    pairfft::gather_add(z2 + b.r * d.Mr, buf, g, b.fgat, -b.scale, d.Mr, tid);
                     __syncthreads();
+                    b = bn;
                 }
             }
             // ---- phi (:949-955)
             if (p.phi_method == 2) {
-                for (int r = 0; r < d.Lr; ++r) {
+                for (int r = 0; r < Lr; ++r) {
                     double pa = 0.0, pb = 0.0;
                     for (int i = tid; i < d.Mr; i += kPairThreads) {
                         const float2 v = z2[r * d.Mr + i];
@@ -250,133 +284,145 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     if (tid < 2) {
                         double a = 0.0;
                         for (int w = 0; w < kWarps; ++w) a += part_z[w][tid];
-                        zsq[tid][r] = a;
+                        S.zsq[tid * Lr + r] = a;
                     }
                     __syncthreads();
                 }
             }
-            if (tid < 128 && ix < d.Lr) {
-                const double ph = p.phi_method == 1 ? p.awgn_var + gam[fr][ix] : zsq[fr][ix] / d.Mr;
-                phi[fr][ix] = ph;
-                reinterpret_cast<float *>(&iphi_f[ix])[fr] = (float)(1.0 / ph);
+            if (tid < 128 && ix < Lr) {
+                const double ph = p.phi_method == 1 ? p.awgn_var + S.gam[fr * Lr + ix] : S.zsq[fr * Lr + ix] / d.Mr;
+                S.phi[fr * Lr + ix] = ph;
+                reinterpret_cast<float *>(&S.iphi_f[ix])[fr] = (float)(1.0 / ph);
             }
             __syncthreads();
             // ---- tau (:958-969)
-            if (tid < 128 && ix < d.Lc) {
+            if (tid < 128 && ix < Lc) {
                 double tc;
-                if (d.Lr == 1) {
-                    tc = ((double)d.L * phi[fr][0] / d.n) / d.W[ix];
+                if (Lr == 1) {
+                    tc = ((double)d.L * S.phi[fr * Lr] / d.n) / d.W[ix];
                 } else {
                     double acc_w = 0.0;
-                    for (int r = 0; r < d.Lr; ++r) acc_w += d.W[r * d.Lc + ix] / phi[fr][r];
+                    for (int r = 0; r < Lr; ++r) acc_w += d.W[r * Lc + ix] / S.phi[fr * Lr + r];
                     tc = ((double)d.L / d.Mr) / acc_w;
                 }
-                tau[fr][ix] = tc;
-                reinterpret_cast<float *>(&tau_f[ix])[fr] = (float)tc;
-                reinterpret_cast<float *>(&itau_f[ix])[fr] = (float)(1.4426950408889634 / tc);
-                if (o.tau_trace && s_active[fr]) o.tau_trace[(fsel * p.t_max + t) * d.Lc + ix] = tc;
+                S.tau[fr * Lc + ix] = tc;
+                reinterpret_cast<float *>(&S.tau_f[ix])[fr] = (float)tc;
+                reinterpret_cast<float *>(&S.itau_f[ix])[fr] = (float)(1.4426950408889634 / tc);
+                if (o.tau_trace && s_active[fr]) o.tau_trace[(fsel * p.t_max + t) * Lc + ix] = tc;
             }
             __syncthreads();
             const bool actA = s_active[0] != 0, actB = s_active[1] != 0;
             // ---- s = beta + tau * Az(z / phi) column block by column block (:972), softmax denoiser (:429-432),
             //      MAP decision argmax(s) of this iteration (:997)
-            for (int c = 0; c < d.Lc; ++c) {
-                const float2 tau2 = tau_f[c], itl = itau_f[c];
+            PairBlock b = pd.blocks[0];
+            pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid);
+            for (int c = 0; c < Lc; ++c) {
+                const float2 tau2 = S.tau_f[c], itl = S.itau_f[c];
                 float2 *beta2_c = beta2 + (size_t)c * d.Mc;
                 const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
+                if (t > 0 && c + 1 < Lc && tid < col_lines) pairfft::prefetch_l2(beta2_c + d.Mc + tid * 16);
                 double psA = 0.0, psB = 0.0, nmA = 0.0, nmB = 0.0;
                 for (int bi = b0; bi < b1; ++bi) {
-                    const PairBlock b = pd.blocks[bi];
-                    pairfft::transposed<LOGH>(buf, pd.tb, b, z2 + b.r * d.Mr, tid);
-                    const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
-                    const float2 sc2 = pairfft::pmul(pairfft::pscale(tau2, b.scale), iphi_f[b.r]);   // scale tau_c / phi_r
                     const float2 *prev = bi == b0 ? (t > 0 ? beta2_c : nullptr) : s2col;
-                    if (bi < b1 - 1) {
-                        for (int j0 = tid; j0 < d.Mc; j0 += kPairThreads * kBatch) {
-                            int id[kBatch];
-                            float2 pv[kBatch];
+                    const OutPre pre = pairfft::transposed_run<LOGH>(buf, pd.tb, b, z2 + b.r * d.Mr, tin, tid, [&] {
+                        OutPre q;
+                        q.ids = pairfft::ldg_na(b.tgat + tid);
 #pragma unroll
-                            for (int u = 0; u < kBatch; ++u) {
-                                const int j = j0 + u * kPairThreads;
-                                id[u] = j < d.Mc ? (int)__ldg(b.tgat + j) : 0;
-                                pv[u] = (prev && j < d.Mc) ? prev[j] : make_float2(0.f, 0.f);
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = tid + u * kPairThreads;
+                            q.pv[u] = (prev && j < d.Mc) ? __ldcg(prev + j) : make_float2(0.f, 0.f);
+                        }
+                        return q;
+                    });
+                    const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
+                    const float2 sc2 = pairfft::pmul(pairfft::pscale(tau2, b.scale), S.iphi_f[b.r]);   // scale tau_c / phi_r
+                    const uint2 *tgat = b.tgat;
+                    if (bi + 1 < d.n_blocks) {                   // next block (this column or the next): start its table loads
+                        b = pd.blocks[bi + 1];
+                        tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid);
+                    }
+                    const bool last = bi == b1 - 1;
+                    for (int base = 0, ch = 0; base < d.Mc; base += kPairThreads * 4, ++ch) {     // warp-uniform trip count
+                        uint2 ide = pre.ids;
+                        float2 pv[4] = {pre.pv[0], pre.pv[1], pre.pv[2], pre.pv[3]};
+                        if (ch > 0) {
+                            ide = pairfft::ldg_na(tgat + ch * kPairThreads + tid);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int j = base + tid + u * kPairThreads;
+                                pv[u] = (prev && j < d.Mc) ? __ldcg(prev + j) : make_float2(0.f, 0.f);
                             }
+                        }
+                        const unsigned id[4] = {ide.x & 0xFFFFu, ide.x >> 16, ide.y & 0xFFFFu, ide.y >> 16};
+                        if (!last) {
 #pragma unroll
-                            for (int u = 0; u < kBatch; ++u) {
-                                const int j = j0 + u * kPairThreads;
+                            for (int u = 0; u < 4; ++u) {
+                                const int j = base + tid + u * kPairThreads;
                                 if (j < d.Mc) s2col[j] = pairfft::pfma(bf2[id[u]], sc2, pv[u]);
                             }
+                            continue;
                         }
-                    } else {
                         // last block of the column: 32 consecutive j of a warp hold whole sections, the softmax
                         // runs on the gathered values in registers
-                        for (int base = 0; base < d.Mc; base += kPairThreads * kBatch) {     // warp-uniform trip count
-                            int id[kBatch];
-                            float2 pv[kBatch];
 #pragma unroll
-                            for (int u = 0; u < kBatch; ++u) {
-                                const int j = base + tid + u * kPairThreads;
-                                id[u] = j < d.Mc ? (int)__ldg(b.tgat + j) : 0;
-                                pv[u] = (prev && j < d.Mc) ? prev[j] : make_float2(0.f, 0.f);
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = base + tid + u * kPairThreads;
+                            const bool live = j < d.Mc;                       // uniform over a section's lanes
+                            const float2 v = pairfft::pfma(bf2[live ? id[u] : 0], sc2, pv[u]);
+                            float mxA = live ? v.x : -INFINITY, mxB = live ? v.y : -INFINITY;
+                            if (M == 32) {
+#pragma unroll
+                                for (int off = 16; off > 0; off >>= 1) {
+                                    mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
+                                    mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
+                                }
+                            } else {
+                                for (int off = M >> 1; off > 0; off >>= 1) {
+                                    mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
+                                    mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
+                                }
                             }
+                            // decision of this iteration: lowest index attaining the section maximum
+                            const unsigned balA = __ballot_sync(0xffffffffu, live && v.x == mxA) & grp_mask;
+                            const unsigned balB = __ballot_sync(0xffffffffu, live && v.y == mxB) & grp_mask;
+                            // e = exp((v - mx) / tau) as 2^((v - mx) log2(e) / tau)
+                            const float2 arg = pairfft::pmul(pairfft::psub(v, make_float2(mxA, mxB)), itl);
+                            const float2 e = make_float2(live ? fast_ex2(arg.x) : 0.f, live ? fast_ex2(arg.y) : 0.f);
+                            float2 sum = e;
+                            if (M == 32) {
 #pragma unroll
-                            for (int u = 0; u < kBatch; ++u) {
-                                const int j = base + tid + u * kPairThreads;
-                                const bool live = j < d.Mc;                       // uniform over a section's lanes
-                                const float2 v = pairfft::pfma(bf2[id[u]], sc2, pv[u]);
-                                float mxA = live ? v.x : -INFINITY, mxB = live ? v.y : -INFINITY;
-                                if (M == 32) {
-#pragma unroll
-                                    for (int off = 16; off > 0; off >>= 1) {
-                                        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
-                                        mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
-                                    }
-                                } else {
-                                    for (int off = M >> 1; off > 0; off >>= 1) {
-                                        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
-                                        mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
-                                    }
+                                for (int off = 16; off > 0; off >>= 1)
+                                    sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
+                                                                         __shfl_xor_sync(0xffffffffu, sum.y, off)));
+                            } else {
+                                for (int off = M >> 1; off > 0; off >>= 1)
+                                    sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
+                                                                         __shfl_xor_sync(0xffffffffu, sum.y, off)));
+                            }
+                            if (live) {
+                                const float2 inv = make_float2(fast_rcp(sum.x), fast_rcp(sum.y));
+                                const float2 bta = pairfft::pmul(e, inv);
+                                __stcg(beta2_c + j, bta);
+                                // 1 - sum beta^2 = sum beta (1 - beta), 1 - beta = (sum - e) / sum: no cancellation
+                                const float2 term = pairfft::pmul(bta, pairfft::pmul(pairfft::psub(sum, e), inv));
+                                psA += (double)term.x;
+                                psB += (double)term.y;
+                                const int sec = c * secs_per_col + (j >> logM);
+                                if (((unsigned)lane & (unsigned)(M - 1)) == 0u) {
+                                    if (actA) o.idx[fA * d.L + sec] = balA ? (int)(__ffs(balA) - 1 - (int)grp_base) : 0;
+                                    if (actB) o.idx[fB * d.L + sec] = balB ? (int)(__ffs(balB) - 1 - (int)grp_base) : 0;
                                 }
-                                // decision of this iteration: lowest index attaining the section maximum
-                                const unsigned balA = __ballot_sync(0xffffffffu, live && v.x == mxA) & grp_mask;
-                                const unsigned balB = __ballot_sync(0xffffffffu, live && v.y == mxB) & grp_mask;
-                                // e = exp((v - mx) / tau) as 2^((v - mx) log2(e) / tau)
-                                const float2 arg = pairfft::pmul(pairfft::psub(v, make_float2(mxA, mxB)), itl);
-                                float2 e = make_float2(live ? fast_ex2(arg.x) : 0.f, live ? fast_ex2(arg.y) : 0.f);
-                                float2 sum = e;
-                                if (M == 32) {
-#pragma unroll
-                                    for (int off = 16; off > 0; off >>= 1)
-                                        sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
-                                                                             __shfl_xor_sync(0xffffffffu, sum.y, off)));
-                                } else {
-                                    for (int off = M >> 1; off > 0; off >>= 1)
-                                        sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
-                                                                             __shfl_xor_sync(0xffffffffu, sum.y, off)));
-                                }
-                                if (live) {
-                                    const float2 inv = make_float2(fast_rcp(sum.x), fast_rcp(sum.y));
-                                    const float2 bta = pairfft::pmul(e, inv);
-                                    beta2_c[j] = bta;
-                                    // 1 - sum beta^2 = sum beta (1 - beta), 1 - beta = (sum - e) / sum: no cancellation
-                                    const float2 term = pairfft::pmul(bta, pairfft::pmul(pairfft::psub(sum, e), inv));
-                                    psA += (double)term.x;
-                                    psB += (double)term.y;
-                                    const int sec = c * secs_per_col + (j >> logM);
-                                    if (((unsigned)lane & (unsigned)(M - 1)) == 0u) {
-                                        if (actA) o.idx[fA * d.L + sec] = balA ? (int)(__ffs(balA) - 1 - (int)grp_base) : 0;
-                                        if (actB) o.idx[fB * d.L + sec] = balB ? (int)(__ffs(balB) - 1 - (int)grp_base) : 0;
-                                    }
-                                    if (o.nmse) {
-                                        const int k = j & (M - 1);
-                                        const float dA = bta.x - (k == idx0[fA * d.L + sec] ? 1.f : 0.f);
-                                        const float dB = bta.y - (k == idx0[fB * d.L + sec] ? 1.f : 0.f);
-                                        nmA += (double)dA * (double)dA;
-                                        nmB += (double)dB * (double)dB;
-                                    }
+                                if (o.nmse) {
+                                    const int k = j & (M - 1);
+                                    const float dA = bta.x - (k == idx0[fA * d.L + sec] ? 1.f : 0.f);
+                                    const float dB = bta.y - (k == idx0[fB * d.L + sec] ? 1.f : 0.f);
+                                    nmA += (double)dA * (double)dA;
+                                    nmB += (double)dB * (double)dB;
                                 }
                             }
                         }
+                    }
+                    if (last) {
                         psA = warp_sum(psA);
                         psB = warp_sum(psB);
                         if (o.nmse) { nmA = warp_sum(nmA); nmB = warp_sum(nmB); }
@@ -394,28 +440,29 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                 if (tid < 2) {
                     double a = 0.0, bsum = 0.0;
                     for (int w = 0; w < kWarps; ++w) { a += part_psi[c & 1][w][tid]; bsum += part_nm[c & 1][w][tid]; }
-                    psi[tid][c] = a;
-                    nm[tid][c] = bsum;
+                    S.psi[tid * Lc + c] = a;
+                    S.nm[tid * Lc + c] = bsum;
                 }
             }
             // ---- psi, nmse, early stop (:976-986), per frame
             if (tid < 2 && s_active[tid]) {
                 const long long f = tid ? fB : fA;
+                double *psi = S.psi + tid * Lc, *psi_prev = S.psi_prev + tid * Lc, *nm = S.nm + tid * Lc;
                 int stop = t > 0;
-                for (int c = 0; c < d.Lc; ++c) {
-                    const double ps = psi[tid][c] / sec_norm;
-                    psi[tid][c] = ps;
-                    if (!(fabs(ps - psi_prev[tid][c]) <= p.atol + p.rtol * fabs(psi_prev[tid][c]))) stop = 0;
-                    if (o.psi_trace) o.psi_trace[(f * p.t_max + t) * d.Lc + c] = ps;
-                    if (o.nmse) o.nmse[(f * p.t_max + t + 1) * d.Lc + c] = (float)(nm[tid][c] / sec_norm);
+                for (int c = 0; c < Lc; ++c) {
+                    const double ps = psi[c] / sec_norm;
+                    psi[c] = ps;
+                    if (!(fabs(ps - psi_prev[c]) <= p.atol + p.rtol * fabs(psi_prev[c]))) stop = 0;
+                    if (o.psi_trace) o.psi_trace[(f * p.t_max + t) * Lc + c] = ps;
+                    if (o.nmse) o.nmse[(f * p.t_max + t + 1) * Lc + c] = (float)(nm[c] / sec_norm);
                 }
                 if (stop) {
                     if (o.nmse)                                       // nmse[t:] = nmse[t]  (:985)
                         for (int tt = t + 1; tt < p.t_max; ++tt)
-                            for (int c = 0; c < d.Lc; ++c)
-                                o.nmse[(f * p.t_max + tt) * d.Lc + c] = o.nmse[(f * p.t_max + t) * d.Lc + c];
+                            for (int c = 0; c < Lc; ++c)
+                                o.nmse[(f * p.t_max + tt) * Lc + c] = o.nmse[(f * p.t_max + t) * Lc + c];
                     o.t_final[f] = t + 1;
-                    for (int c = 0; c < d.Lc; ++c) o.psi[f * d.Lc + c] = psi[tid][c];
+                    for (int c = 0; c < Lc; ++c) o.psi[f * Lc + c] = psi[c];
                     s_active[tid] = 0;
                 }
             }
@@ -426,7 +473,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
         if (tid < 2 && s_active[tid]) {
             const long long f = tid ? fB : fA;
             o.t_final[f] = p.t_max - 1;
-            for (int c = 0; c < d.Lc; ++c) o.psi[f * d.Lc + c] = psi[tid][c];
+            for (int c = 0; c < Lc; ++c) o.psi[f * Lc + c] = S.psi[tid * Lc + c];
         }
         __syncthreads();
     }

@@ -11,8 +11,14 @@
 //    straight from the column block in global memory through an inverse table (0xFFFF = zero);
 //  * the transposed transform gathers the row block from shared memory inside the real-FFT
 //    pre-processing pass (again an inverse table with a sentinel), no zero-fill / scatter;
-//  * real-FFT twiddles come from (0.5 pt, pt^4) tables, the bit-reversed pair slots of the
-//    post-processing from a slot table.
+//  * real-FFT twiddles come from a (0.5 pt) table (pt^4 by two squarings), the bit-reversed pair
+//    slots of the post-processing from a slot table;
+//  * every phase ISSUES the global table loads of the NEXT phase before it starts its own work, so
+//    their L1 / L2 latency runs under the phase and its closing barrier instead of behind it (the
+//    kernel keeps only 6 warps per scheduler: ncu showed 30 % of the stall samples on table loads);
+//    index tables are laid out so that one 64- / 128-bit load per thread fetches 4 / 8 entries and
+//    are read with L1::no_allocate, which leaves the small L1 (228 KB minus 3 CTAs of shared memory)
+//    to the twiddle and real-FFT tables that every block reuses.
 // Compile-time transform sizes H = w/2 = 2^10, 2^11, 2^12 (w = 2048, 4096, 8192).
 #pragma once
 #include "sparc_dct.cuh"
@@ -82,200 +88,391 @@ template <int LOGH> __host__ __device__ constexpr int pswz(int i)
 }
 inline int pswz_rt(int logh, int i) { return logh == 12 ? pswz<12>(i) : logh == 11 ? pswz<11>(i) : pswz<10>(i); }
 
-// One radix-8 / radix-4 DIF pass over sub-transforms of size 2^LOGS on the pair buffer.
-// GATHER: first pass of the forward transform -- inputs come from the column block in global
-// memory (x.get(i): entry i of frame A / frame B) through src[q][2R] (uint16, kNone = zero).
-struct NoSrc {
-    __device__ __forceinline__ P get(unsigned) const { return make_float2(0.f, 0.f); }
-};
-template <int LOGH, int LOGS, int LOGR, bool INV, bool GATHER, typename Src = NoSrc>
-__device__ __forceinline__ void pass(float4 *buf, const float2 *__restrict__ tw, int tid,
-                                     const uint16_t *__restrict__ src = nullptr, const Src x = Src())
+// ---- global loads that do not allocate in L1 (index tables: read once per block)
+__device__ __forceinline__ uint4 ldg_na(const uint4 *p)
 {
-    constexpr int H = 1 << LOGH, R = 1 << LOGR, LOGQ = LOGS - LOGR;
-    constexpr int NB = H >> LOGR;
-    constexpr int TW_STEP = H >> LOGS;
-    static_assert(!GATHER || (LOGS == LOGH && LOGR == 3), "the gathering pass is the first, radix-8 one");
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_na(const uint2 *p)
+{
+    uint2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- pass plan: radix of sparc_dct.cuh's pass_logr; 4 passes for LOGH = 10 (8,8,4,4), 11 (8,8,8,4), 12 (8,8,8,8)
+template <int LOGH> __host__ __device__ constexpr int plan_logs(int i)
+{
+    int s = LOGH;
+    for (int k = 0; k < i; ++k) s -= pass_logr(s);
+    return s;
+}
+template <int LOGH, int I>
+struct PassInfo {
+    static constexpr int LOGS = plan_logs<LOGH>(I), LOGR = pass_logr(LOGS), LOGQ = LOGS - LOGR;
+    static constexpr int NB = (1 << LOGH) >> LOGR;                          // butterflies of the pass
+    static constexpr int NQ = NB > kPairThreads ? NB / kPairThreads : 1;    // per thread
+    static constexpr int TW_STEP = (1 << LOGH) >> LOGS;
+};
+
+template <int NQ> struct TwPre { float2 w1[NQ], w2[NQ], w4[NQ]; };
+
+// issue the twiddle loads of pass I (nothing for the last pass: stride 1, no twiddles)
+template <int LOGH, int I, bool INV>
+__device__ __forceinline__ TwPre<PassInfo<LOGH, I>::NQ> tw_issue(const float2 *__restrict__ tw, int tid)
+{
+    typedef PassInfo<LOGH, I> PI;
+    TwPre<PI::NQ> t;
 #pragma unroll
-    for (int q0 = 0; q0 < NB; q0 += kPairThreads) {
-        const int q = q0 + tid;
-        if (NB % kPairThreads != 0 && q >= NB) break;
-        const int j = q & ((1 << LOGQ) - 1);
-        const int sb = pswz<LOGH>(((q >> LOGQ) << LOGS) | j);
-        float2 w1 = {1.f, 0.f}, w2 = w1, w4 = w1;
-        if (LOGQ > 0) {
-            w1 = __ldg(tw + j * TW_STEP);
-            w2 = __ldg(tw + 2 * j * TW_STEP);
-            if (LOGR == 3) w4 = __ldg(tw + 4 * j * TW_STEP);
-            if (INV) { w1.y = -w1.y; w2.y = -w2.y; w4.y = -w4.y; }
+    for (int i = 0; i < PI::NQ; ++i) {
+        t.w1[i] = t.w2[i] = t.w4[i] = make_float2(1.f, 0.f);
+        const int q = tid + i * kPairThreads;
+        if (PI::LOGQ > 0 && q < PI::NB) {
+            const int j = q & ((1 << PI::LOGQ) - 1);
+            t.w1[i] = __ldg(tw + j * PI::TW_STEP);
+            t.w2[i] = __ldg(tw + 2 * j * PI::TW_STEP);
+            if (PI::LOGR == 3) t.w4[i] = __ldg(tw + 4 * j * PI::TW_STEP);
+            if (INV) { t.w1[i].y = -t.w1[i].y; t.w2[i].y = -t.w2[i].y; t.w4[i].y = -t.w4[i].y; }
         }
-        CP v[R];
-        if (GATHER) {
-            const uint4 *tp = reinterpret_cast<const uint4 *>(src) + 2 * q;
-            const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
-            const unsigned e[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const unsigned ir = e[m] & 0xFFFFu, ii = e[m] >> 16;
-                v[m].re = ir != kNone ? x.get(ir) : make_float2(0.f, 0.f);
-                v[m].im = ii != kNone ? x.get(ii) : make_float2(0.f, 0.f);
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < R; ++m) v[m] = ld(buf, sb ^ pswz<LOGH>(m << LOGQ));
-        }
-        if (LOGR == 2) {
-            bfly1(v[0], v[2]);
-            bfly1(v[1], v[3]);
-            v[3] = mul_mi<INV>(v[3]);
-            bfly1(v[0], v[1]);
-            bfly1(v[2], v[3]);
-        } else {
-            bfly1(v[0], v[4]);
-            bfly1(v[1], v[5]);
-            bfly1(v[2], v[6]);
-            bfly1(v[3], v[7]);
-            v[5] = mul_w8<INV>(v[5]);
-            v[6] = mul_mi<INV>(v[6]);
-            v[7] = mul_mi<INV>(mul_w8<INV>(v[7]));
-            bfly1(v[0], v[2]);
-            bfly1(v[1], v[3]);
-            bfly1(v[4], v[6]);
-            bfly1(v[5], v[7]);
-            v[3] = mul_mi<INV>(v[3]);
-            v[7] = mul_mi<INV>(v[7]);
-            bfly1(v[0], v[1]);
-            bfly1(v[2], v[3]);
-            bfly1(v[4], v[5]);
-            bfly1(v[6], v[7]);
-        }
-        if (LOGQ > 0) {     // output m holds frequency brev(m) of the radix-R DFT: times w_S^(j brev(m))
-            if (LOGR == 2) {
-                v[1] = cmulw(v[1], w2);
-                v[2] = cmulw(v[2], w1);
-                v[3] = cmulw(v[3], cmul_s(w1, w2));
-            } else {
-                const float2 w3 = cmul_s(w1, w2);
-                v[1] = cmulw(v[1], w4);
-                v[2] = cmulw(v[2], w2);
-                v[3] = cmulw(v[3], cmul_s(w2, w4));
-                v[4] = cmulw(v[4], w1);
-                v[5] = cmulw(v[5], cmul_s(w1, w4));
-                v[6] = cmulw(v[6], w3);
-                v[7] = cmulw(v[7], cmul_s(w3, w4));
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < R; ++m) st(buf, sb ^ pswz<LOGH>(m << LOGQ), v[m]);
+    }
+    return t;
+}
+
+template <int LOGR, bool INV> __device__ __forceinline__ void radix_dft(CP *v)
+{
+    if (LOGR == 2) {
+        bfly1(v[0], v[2]);
+        bfly1(v[1], v[3]);
+        v[3] = mul_mi<INV>(v[3]);
+        bfly1(v[0], v[1]);
+        bfly1(v[2], v[3]);
+    } else {
+        bfly1(v[0], v[4]);
+        bfly1(v[1], v[5]);
+        bfly1(v[2], v[6]);
+        bfly1(v[3], v[7]);
+        v[5] = mul_w8<INV>(v[5]);
+        v[6] = mul_mi<INV>(v[6]);
+        v[7] = mul_mi<INV>(mul_w8<INV>(v[7]));
+        bfly1(v[0], v[2]);
+        bfly1(v[1], v[3]);
+        bfly1(v[4], v[6]);
+        bfly1(v[5], v[7]);
+        v[3] = mul_mi<INV>(v[3]);
+        v[7] = mul_mi<INV>(v[7]);
+        bfly1(v[0], v[1]);
+        bfly1(v[2], v[3]);
+        bfly1(v[4], v[5]);
+        bfly1(v[6], v[7]);
+    }
+}
+// output m of the radix-R DFT holds frequency brev(m): times w_S^(j brev(m))
+template <int LOGR> __device__ __forceinline__ void radix_twiddle(CP *v, float2 w1, float2 w2, float2 w4)
+{
+    if (LOGR == 2) {
+        v[1] = cmulw(v[1], w2);
+        v[2] = cmulw(v[2], w1);
+        v[3] = cmulw(v[3], cmul_s(w1, w2));
+    } else {
+        const float2 w3 = cmul_s(w1, w2);
+        v[1] = cmulw(v[1], w4);
+        v[2] = cmulw(v[2], w2);
+        v[3] = cmulw(v[3], cmul_s(w2, w4));
+        v[4] = cmulw(v[4], w1);
+        v[5] = cmulw(v[5], cmul_s(w1, w4));
+        v[6] = cmulw(v[6], w3);
+        v[7] = cmulw(v[7], cmul_s(w3, w4));
     }
 }
 
-// passes from sub-transform size 2^LOGS down (radix plan of sparc_dct.cuh: pass_logr); a barrier after each
-template <int LOGH, int LOGS, bool INV>
-__device__ __forceinline__ void passes_from(float4 *buf, const float2 *tw, int tid)
+// One in-place DIF pass (pass I of the plan) on the pair buffer with its twiddles already in registers.
+template <int LOGH, int I, bool INV>
+__device__ __forceinline__ void pass_run(float4 *buf, const TwPre<PassInfo<LOGH, I>::NQ> &t, int tid)
 {
-    if constexpr (LOGS > 0) {
-        constexpr int LOGR = pass_logr(LOGS);
-        pass<LOGH, LOGS, LOGR, INV, false>(buf, tw, tid);
-        __syncthreads();
-        passes_from<LOGH, LOGS - LOGR, INV>(buf, tw, tid);
+    typedef PassInfo<LOGH, I> PI;
+    constexpr int R = 1 << PI::LOGR;
+#pragma unroll
+    for (int i = 0; i < PI::NQ; ++i) {
+        const int q = tid + i * kPairThreads;
+        if (PI::NB < kPairThreads && q >= PI::NB) break;
+        const int j = q & ((1 << PI::LOGQ) - 1);
+        const int sb = pswz<LOGH>(((q >> PI::LOGQ) << PI::LOGS) | j);
+        CP v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = ld(buf, sb ^ pswz<LOGH>(m << PI::LOGQ));
+        radix_dft<PI::LOGR, INV>(v);
+        if (PI::LOGQ > 0) radix_twiddle<PI::LOGR>(v, t.w1[i], t.w2[i], t.w4[i]);
+#pragma unroll
+        for (int m = 0; m < R; ++m) st(buf, sb ^ pswz<LOGH>(m << PI::LOGQ), v[m]);
     }
 }
 
 // Tables of one transform size for the pair kernels (device pointers).
 struct PairTables {
     const float2 *tw;          // exp(-2 pi i k / H), k < H
-    const float4 *pre;         // [H/2 + 1] natural k:        (0.5 pt[k], pt[k]^4)
-    const float4 *post;        // [H/2 + 1] bit-reversed t:   (0.5 pt[k], pt[k]^4), k = brev_{h-1}(t), last = H/2
+    const float2 *pre;         // [H/2 + 1] natural k:       0.5 pt[k],  pt[k] = exp(-i pi k / (2N))
+    const float2 *post;        // [H/2 + 1] bit-reversed t:  0.5 pt[k],  k = brev_{h-1}(t), last entry k = H/2
     const uint32_t *post_slot; // [H/2 + 1] slot of Z[k] | slot of Z[H-k] << 16 (swizzled, after the FFT)
 };
 
-// One non-zero block of the design for the pair kernels.
+// One non-zero block of the design for the pair kernels.  "Chunked" tables hold the entries of
+// element tid + 256 u (u = 4 c .. 4 c + 3) as one uint2 at [c][tid], padded with kNone.
 struct PairBlock {
     int r, c;
     float scale;                   // sqrt(2 W[r,c] / L)
-    const uint16_t *fsrc;          // [H/8][16]  forward first-pass sources (index into the column block)
-    const uint16_t *fgat;          // [Mr]       float2-view slot of Y[o0[i]] after post()
-    const uint16_t *tsrc;          // [H/2+1][4] transposed sources: c[k], c[N-k], c[H-k], c[H+k] (index into the row block)
-    const uint16_t *tgat;          // [Mc]       float2-view slot of X[o1[j]] after the inverse FFT
+    const uint4 *fsrc;             // [2][H/8]     forward first-pass sources of butterfly q: elements m = 0..3 | 4..7, (re | im << 16)
+    const uint2 *fgat;             // chunked [Mr] float2-view slot of Y[o0[i]] after the post-processing
+    const uint2 *tsrc;             // [H/2+1]      transposed sources of pair k: c[k], c[N-k], c[H-k], c[H+k] (rows of the block)
+    const uint2 *tgat;             // chunked [Mc] float2-view slot of X[o1[j]] after the inverse FFT
 };
+__host__ __device__ constexpr int chunk_count(int n) { return (n + 4 * kPairThreads - 1) / (4 * kPairThreads); }
 
-// (0.5 pt[H-k]) from (0.5 pt[k]): pt[H-k] = e^{-i pi/4} conj(pt[k])
+// 0.5 pt[H-k] from 0.5 pt[k]: pt[H-k] = e^{-i pi/4} conj(pt[k]);  q = pt^4 = 16 (0.5 pt)^4
 __device__ __forceinline__ float2 half_pt_mirror(float2 hp)
 {
     const float kR = 0.70710678118654752440f;
     return {kR * (hp.x - hp.y), -kR * (hp.x + hp.y)};
 }
+__device__ __forceinline__ float2 q_from_half_pt(float2 hp)
+{
+    const float2 s1 = {hp.x * hp.x - hp.y * hp.y, 2.f * hp.x * hp.y};
+    return {16.f * (s1.x * s1.x - s1.y * s1.y), 32.f * s1.x * s1.y};
+}
 
-// ---- forward: buf <- DCT-II spectrum of the column block x2 (both frames); slot brev(k) ends up
-// holding (Y[k], Y[N-k]).  Starts by overwriting buf: the caller makes sure nobody still reads it.
-// Ends with __syncthreads().
+#ifndef LSB_PAIR_PREPF
+#define LSB_PAIR_PREPF 5
+#endif
+#ifndef LSB_PAIR_GATPF
+#define LSB_PAIR_GATPF 4
+#endif
+constexpr int kPrePF = LSB_PAIR_PREPF;      // pairs per thread whose tables are prefetched (H/2 + 1 = 1025 pairs at H = 2048)
+constexpr int kGatPF = LSB_PAIR_GATPF;      // gather-id chunks (4 ids each) prefetched
+
+// ------------------------------------------------------------------ forward
+template <int LOGH> struct FwdIn {                       // what the gathering first pass needs
+    typedef PassInfo<LOGH, 0> PI;
+    uint4 ta[PI::NQ], tb[PI::NQ];
+    TwPre<PI::NQ> tw;
+};
+template <int LOGH>
+__device__ __forceinline__ FwdIn<LOGH> forward_issue(const PairTables &tb, const PairBlock &b, int tid)
+{
+    typedef PassInfo<LOGH, 0> PI;
+    FwdIn<LOGH> in;
+#pragma unroll
+    for (int i = 0; i < PI::NQ; ++i) {
+        const int q = tid + i * kPairThreads;
+        if (q < PI::NB) {
+            in.ta[i] = ldg_na(b.fsrc + q);
+            in.tb[i] = ldg_na(b.fsrc + PI::NB + q);
+        } else {
+            in.ta[i] = in.tb[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        }
+    }
+    in.tw = tw_issue<LOGH, 0, false>(tb.tw, tid);
+    return in;
+}
+
+struct PostPre { uint32_t slot[kPrePF]; float2 hp[kPrePF]; };
+template <int LOGH> __device__ __forceinline__ PostPre post_issue(const PairTables &tb, int tid)
+{
+    constexpr int Hh = 1 << (LOGH - 1);
+    PostPre p;
+#pragma unroll
+    for (int i = 0; i < kPrePF; ++i) {
+        const int t = tid + i * kPairThreads;
+        p.slot[i] = t <= Hh ? __ldg(tb.post_slot + t) : 0u;
+        p.hp[i] = t <= Hh ? __ldg(tb.post + t) : make_float2(0.f, 0.f);
+    }
+    return p;
+}
+__device__ __forceinline__ void post_pair(float4 *buf, uint32_t sl, float2 hp)
+{
+    const int pa = (int)(sl & 0xFFFFu), pb = (int)(sl >> 16);
+    const CP za = ld(buf, pa), zb = ld(buf, pb);
+    const float2 q = q_from_half_pt(hp);
+    // E2 = za + conj(zb), O2 = -i (za - conj(zb))  (twice the even / odd spectra; the 1/2 is in hp)
+    const CP E2 = {padd(za.re, zb.re), psub(za.im, zb.im)};
+    const CP O2 = {padd(za.im, zb.im), psub(zb.re, za.re)};
+    const CP qO = cmulw(O2, q);
+    const CP Vk = cadd(E2, qO);                              // 2 V[k]
+    const CP ta = cmulw(Vk, hp);
+    st(buf, pa, CP{ta.re, pneg(ta.im)});
+    if (pb != pa) {
+        const CP Vm = {psub(E2.re, qO.re), psub(qO.im, E2.im)};   // 2 V[H-k] = conj(E2 - qO)
+        const CP t2 = cmulw(Vm, half_pt_mirror(hp));
+        st(buf, pb, CP{t2.re, pneg(t2.im)});
+    }
+}
+
+struct GatPre { uint2 c[kGatPF]; };
+__device__ __forceinline__ GatPre gather_issue(const uint2 *__restrict__ tab, int count, int tid)
+{
+    GatPre g;
+    const int nc = chunk_count(count);
+#pragma unroll
+    for (int c = 0; c < kGatPF; ++c) g.c[c] = c < nc ? ldg_na(tab + c * kPairThreads + tid) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    return g;
+}
+
+// buf <- DCT-II spectrum of the column block x (both frames): slot brev(k) ends up holding (Y[k], Y[N-k]).
+// `in` was issued by forward_issue() for this block.  Overwrites buf from the start (the caller makes sure
+// nobody still reads it), ends after the barrier that closes the post-processing and returns the first
+// gather ids of the block's rows (issued under the post-processing).
 template <int LOGH, typename Src>
-__device__ __forceinline__ void forward(float4 *buf, const PairTables &tb, const PairBlock &b, const Src x, int tid)
+__device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb, const PairBlock &b, const Src x,
+                                              const FwdIn<LOGH> &in, int n_rows, int tid)
 {
     constexpr int H = 1 << LOGH, Hh = H >> 1;
-    pass<LOGH, LOGH, 3, false, true, Src>(buf, tb.tw, tid, b.fsrc, x);
+    typedef PassInfo<LOGH, 0> P0;
+    static_assert(P0::LOGR == 3 && PassInfo<LOGH, 3>::LOGQ == 0, "plan: radix-8 first pass, 4 passes");
+    const auto t1 = tw_issue<LOGH, 1, false>(tb.tw, tid);
+    // pass 0 gathers its inputs from the column block: packed z[e] = v[2e] + i v[2e+1], v = Makhoul permutation
+#pragma unroll
+    for (int i = 0; i < P0::NQ; ++i) {
+        const int q = tid + i * kPairThreads;
+        if (P0::NB < kPairThreads && q >= P0::NB) break;
+        const unsigned e[8] = {in.ta[i].x, in.ta[i].y, in.ta[i].z, in.ta[i].w, in.tb[i].x, in.tb[i].y, in.tb[i].z, in.tb[i].w};
+        CP v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const unsigned ir = e[m] & 0xFFFFu, ii = e[m] >> 16;
+            v[m].re = ir != kNone ? x.get(ir) : make_float2(0.f, 0.f);
+            v[m].im = ii != kNone ? x.get(ii) : make_float2(0.f, 0.f);
+        }
+        radix_dft<3, false>(v);
+        radix_twiddle<3>(v, in.tw.w1[i], in.tw.w2[i], in.tw.w4[i]);
+        const int sb = pswz<LOGH>(q);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) st(buf, sb ^ pswz<LOGH>(m << P0::LOGQ), v[m]);
+    }
     __syncthreads();
-    passes_from<LOGH, LOGH - 3, false>(buf, tb.tw, tid);
+    const auto t2 = tw_issue<LOGH, 2, false>(tb.tw, tid);
+    pass_run<LOGH, 1, false>(buf, t1, tid);
+    __syncthreads();
+    pass_run<LOGH, 2, false>(buf, t2, tid);
+    __syncthreads();
+    const PostPre pp = post_issue<LOGH>(tb, tid);
+    pass_run<LOGH, 3, false>(buf, TwPre<PassInfo<LOGH, 3>::NQ>(), tid);
+    __syncthreads();
+    const GatPre g = gather_issue(b.fgat, n_rows, tid);
     // real-FFT split + DCT phase, pairs visited in bit-reversed order (consecutive lanes, consecutive slots)
-    for (int t = tid; t <= Hh; t += kPairThreads) {
+#pragma unroll
+    for (int i = 0; i < kPrePF; ++i) {
+        const int t = tid + i * kPairThreads;
+        if (t > Hh) break;
         if (t == 0) {
             const CP z = ld(buf, 0);
             st(buf, 0, CP{padd(z.re, z.im), pscale(psub(z.re, z.im), 0.70710678118654752440f)});
-            continue;
-        }
-        const uint32_t sl = __ldg(tb.post_slot + t);
-        const float4 tq = __ldg(tb.post + t);
-        const int pa = (int)(sl & 0xFFFFu), pb = (int)(sl >> 16);
-        const CP za = ld(buf, pa), zb = ld(buf, pb);
-        const float2 hp = {tq.x, tq.y}, q = {tq.z, tq.w};
-        // E2 = za + conj(zb), O2 = -i (za - conj(zb))  (twice the even / odd spectra; the 1/2 is in hp)
-        const CP E2 = {padd(za.re, zb.re), psub(za.im, zb.im)};
-        const CP O2 = {padd(za.im, zb.im), psub(zb.re, za.re)};
-        const CP qO = cmulw(O2, q);
-        const CP Vk = cadd(E2, qO);                              // 2 V[k]
-        const CP ta = cmulw(Vk, hp);
-        st(buf, pa, CP{ta.re, pneg(ta.im)});
-        if (pb != pa) {
-            const CP Vm = {psub(E2.re, qO.re), psub(qO.im, E2.im)};   // 2 V[H-k] = conj(E2 - qO)
-            const CP t2 = cmulw(Vm, half_pt_mirror(hp));
-            st(buf, pb, CP{t2.re, pneg(t2.im)});
+        } else {
+            post_pair(buf, pp.slot[i], pp.hp[i]);
         }
     }
+    for (int t = tid + kPrePF * kPairThreads; t <= Hh; t += kPairThreads) post_pair(buf, __ldg(tb.post_slot + t), __ldg(tb.post + t));
     __syncthreads();
+    return g;
 }
 
-// ---- transposed: buf <- DCT-III of the row block y2 (shared memory, float2 per entry) scattered to
-// its rows; the inverse FFT leaves X in bit-reversed slots (tgat knows them).
-// Starts by overwriting buf.  Ends with __syncthreads().
+// dst2[i] += sc * Y[id(i)] for the rows of one block (Y: float2 view of the pair buffer); row tid + 256 u
+// is handled by thread tid, so successive blocks update a row from the same thread (no barrier needed).
+__device__ __forceinline__ void gather_add(float2 *dst2, const float4 *buf, const GatPre &g, const uint2 *__restrict__ tab,
+                                           float sc, int count, int tid)
+{
+    const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
+    const int nc = chunk_count(count);
+#pragma unroll
+    for (int c = 0; c < kGatPF; ++c) {
+        if (c >= nc) break;
+        const unsigned id[4] = {g.c[c].x & 0xFFFFu, g.c[c].x >> 16, g.c[c].y & 0xFFFFu, g.c[c].y >> 16};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = tid + (4 * c + u) * kPairThreads;
+            if (i < count) dst2[i] = pfmas(bf2[id[u]], sc, dst2[i]);
+        }
+    }
+    for (int c = kGatPF; c < nc; ++c) {
+        const uint2 e = ldg_na(tab + c * kPairThreads + tid);
+        const unsigned id[4] = {e.x & 0xFFFFu, e.x >> 16, e.y & 0xFFFFu, e.y >> 16};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = tid + (4 * c + u) * kPairThreads;
+            if (i < count) dst2[i] = pfmas(bf2[id[u]], sc, dst2[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ transposed
+struct TrIn { uint2 src[kPrePF]; float2 hp[kPrePF]; };
 template <int LOGH>
-__device__ __forceinline__ void transposed(float4 *buf, const PairTables &tb, const PairBlock &b, const float2 *y2, int tid)
+__device__ __forceinline__ TrIn transposed_issue(const PairTables &tb, const PairBlock &b, int tid)
+{
+    constexpr int Hh = 1 << (LOGH - 1);
+    TrIn in;
+#pragma unroll
+    for (int i = 0; i < kPrePF; ++i) {
+        const int k = tid + i * kPairThreads;
+        in.src[i] = k <= Hh ? ldg_na(b.tsrc + k) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        in.hp[i] = k <= Hh ? __ldg(tb.pre + k) : make_float2(0.f, 0.f);
+    }
+    return in;
+}
+
+template <int LOGH>
+__device__ __forceinline__ void pre_pair(float4 *buf, const float2 *y2, int k, uint2 e, float2 hp)
 {
     constexpr int H = 1 << LOGH, Hh = H >> 1;
-    const uint2 *src = reinterpret_cast<const uint2 *>(b.tsrc);
-    for (int k = tid; k <= Hh; k += kPairThreads) {
-        const uint2 e = __ldg(src + k);
-        const unsigned a0 = e.x & 0xFFFFu, a1 = e.x >> 16, b0 = e.y & 0xFFFFu, b1 = e.y >> 16;
-        const P zero = make_float2(0.f, 0.f);
-        const CP ca = {a0 != kNone ? y2[a0] : zero, a1 != kNone ? y2[a1] : zero};     // (c[k], c[N-k])
-        if (k == 0) {
-            const P wH = pscale(ca.im, 0.70710678118654752440f);
-            st(buf, 0, CP{padd(ca.re, wH), psub(ca.re, wH)});
-            continue;
-        }
-        const CP cb = {b0 != kNone ? y2[b0] : zero, b1 != kNone ? y2[b1] : zero};     // (c[H-k], c[H+k])
-        const float4 tq = __ldg(tb.pre + k);
-        const float2 hp = {tq.x, tq.y}, q = {tq.z, tq.w};
-        // W[k] = conj(pt[k]) (c[k] - i c[N-k]) / 2 = conj(hp * ca); A = W[k] + conj(W[H-k]), B = (W[k] - conj(W[H-k])) conj(q)
-        const CP U = cmulw(ca, hp), V = cmulw(cb, half_pt_mirror(hp));
-        const CP A = {padd(U.re, V.re), psub(V.im, U.im)};
-        const CP D = {psub(U.re, V.re), pneg(padd(U.im, V.im))};
-        const CP B = cmulw(D, make_float2(q.x, -q.y));
-        st(buf, pswz<LOGH>(k), CP{psub(A.re, B.im), padd(A.im, B.re)});                 // A + iB
-        if (k != Hh) st(buf, pswz<LOGH>(H - k), CP{padd(A.re, B.im), psub(B.re, A.im)});   // conj(A) + i conj(B)
+    const unsigned a0 = e.x & 0xFFFFu, a1 = e.x >> 16, b0 = e.y & 0xFFFFu, b1 = e.y >> 16;
+    const P zero = make_float2(0.f, 0.f);
+    const CP ca = {a0 != kNone ? y2[a0] : zero, a1 != kNone ? y2[a1] : zero};     // (c[k], c[N-k])
+    if (k == 0) {
+        const P wH = pscale(ca.im, 0.70710678118654752440f);
+        st(buf, 0, CP{padd(ca.re, wH), psub(ca.re, wH)});
+        return;
     }
+    const CP cb = {b0 != kNone ? y2[b0] : zero, b1 != kNone ? y2[b1] : zero};     // (c[H-k], c[H+k])
+    const float2 q = q_from_half_pt(hp);
+    // W[k] = conj(pt[k]) (c[k] - i c[N-k]) / 2 = conj(hp * ca); A = W[k] + conj(W[H-k]), B = (W[k] - conj(W[H-k])) conj(q)
+    const CP U = cmulw(ca, hp), V = cmulw(cb, half_pt_mirror(hp));
+    const CP A = {padd(U.re, V.re), psub(V.im, U.im)};
+    const CP D = {psub(U.re, V.re), pneg(padd(U.im, V.im))};
+    const CP B = cmulw(D, make_float2(q.x, -q.y));
+    st(buf, pswz<LOGH>(k), CP{psub(A.re, B.im), padd(A.im, B.re)});                 // A + iB
+    if (k != Hh) st(buf, pswz<LOGH>(H - k), CP{padd(A.re, B.im), psub(B.re, A.im)});   // conj(A) + i conj(B)
+}
+
+// buf <- DCT-III of the row block y2 (shared memory, float2 per entry) scattered to its rows; the inverse
+// FFT leaves X in bit-reversed slots (tgat knows them).  `in` was issued by transposed_issue() for this
+// block.  Overwrites buf from the start; issue_out() is called before the last pass so the caller's loads
+// for the gather that follows run under it; ends with a barrier and returns issue_out()'s result.
+template <int LOGH, typename IssueOut>
+__device__ __forceinline__ auto transposed_run(float4 *buf, const PairTables &tb, const PairBlock &b, const float2 *y2,
+                                               const TrIn &in, int tid, IssueOut issue_out) -> decltype(issue_out())
+{
+    constexpr int Hh = 1 << (LOGH - 1);
+    const auto t0 = tw_issue<LOGH, 0, true>(tb.tw, tid);
+#pragma unroll
+    for (int i = 0; i < kPrePF; ++i) {
+        const int k = tid + i * kPairThreads;
+        if (k > Hh) break;
+        pre_pair<LOGH>(buf, y2, k, in.src[i], in.hp[i]);
+    }
+    for (int k = tid + kPrePF * kPairThreads; k <= Hh; k += kPairThreads) pre_pair<LOGH>(buf, y2, k, ldg_na(b.tsrc + k), __ldg(tb.pre + k));
     __syncthreads();
-    passes_from<LOGH, LOGH, true>(buf, tb.tw, tid);
+    const auto t1 = tw_issue<LOGH, 1, true>(tb.tw, tid);
+    pass_run<LOGH, 0, true>(buf, t0, tid);
+    __syncthreads();
+    const auto t2 = tw_issue<LOGH, 2, true>(tb.tw, tid);
+    pass_run<LOGH, 1, true>(buf, t1, tid);
+    __syncthreads();
+    pass_run<LOGH, 2, true>(buf, t2, tid);
+    __syncthreads();
+    const auto out = issue_out();
+    pass_run<LOGH, 3, true>(buf, TwPre<PassInfo<LOGH, 3>::NQ>(), tid);
+    __syncthreads();
+    return out;
 }
 
 }  // namespace pairfft
