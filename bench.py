@@ -32,6 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 N_FRAMES = 65536
 MAX_IT = 50
@@ -52,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fp64 re-decode of the batch after the timed region")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary workloads (SPARC AMP config 1, dense-design AMP config 3)")
     return ap.parse_args()
@@ -154,51 +156,6 @@ def run_reference(args, rank, world):
     }))
 
 
-# ------------------------------------------------------------------- clocks
-class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-
-    def __init__(self, index):
-        self.index, self.rows, self.stop, self.thread = index, [], threading.Event(), None
-
-    def _loop(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([t.strip() for t in out.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
-
-    def __enter__(self):
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
-        return self
-
-    def __exit__(self, *a):
-        self.stop.set()
-        self.thread.join(timeout=6)
-
-    def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
-
-
 # ---------------------------------------------------------------------- main
 def bind_to_gpu_numa(torch, local_rank):
     """Multi-rank runs: keep this process (and so its pinned host buffers, first-touched by it) on the
@@ -229,6 +186,8 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import workloads
+    from workloads import ClockSampler
     from ldpc_sparc_b200 import _lib, ldpc
 
     torch.cuda.set_device(local_rank)
@@ -329,6 +288,34 @@ def main():
                         "mean_iterations": it_sum / max(frames, 1), "mean_executed_iterations": exec_sum / max(frames, 1)},
     }
 
+    # parity at bench scale (outside the timed region): the same frames through the fp64 kernel, whose iteration
+    # counts and decisions are the reference's (tests/test_ldpc_gpu.py: exact against c_ldpc.c)
+    if not args.no_parity:
+        llr64 = llr.double()
+        app64 = torch.empty_like(llr64)
+        it64 = torch.empty(F, dtype=torch.int32, device=dev)
+        _lib.check(L.lsb_ldpc_decode_dev_f64(g, llr64.data_ptr(), app64.data_ptr(), None, it64.data_ptr(), F,
+                                             args.max_it, 0, 1.0, stream), "decode f64")
+        torch.cuda.synchronize()
+        hard64, hard32 = app64 < 0, app < 0
+        err64, err32 = (hard64 != truth).any(1), hard_err.any(1)
+        par = torch.stack([err32.sum(), err64.sum(), (err32 != err64).sum(), (hard64 != hard32).any(1).sum(),
+                           (it64 != iters).sum(), ((hard64 != hard32).any(1) & (it64 < args.max_it)).sum(),
+                           (hard64 != truth).sum()]).to(torch.int64)
+        if world > 1:
+            dist.all_reduce(par, op=dist.ReduceOp.SUM)
+        fe32, fe64, d_status, d_dec, d_it, d_dec_conv, be64 = (int(v) for v in par.tolist())
+        out["parity_at_bench_scale"] = {
+            "frames": frames, "frame_errors_fp32": fe32, "frame_errors_fp64": fe64, "bit_errors_fp32": bit_errs,
+            "bit_errors_fp64": be64, "frames_with_different_error_status": d_status,
+            "frames_with_different_hard_decisions": d_dec, "of_which_fp64_converged": d_dec_conv,
+            "frames_with_different_iteration_counts": d_it,
+            "note": "fp64 kernel = the reference's arithmetic (bit-exact iteration counts and decisions against c_ldpc.c in "
+                    "the tests); fp32 differences are confined to frames the reference does not converge on within max_it",
+        }
+        del llr64, app64, hard64
+        torch.cuda.empty_cache()
+
     # end to end through the C-ABI host-pointer call (pinned host buffers)
     if not args.no_e2e:
         h_llr = torch.empty((F, N), dtype=torch.float32).pin_memory()
@@ -399,28 +386,31 @@ def main():
                                     "ncu reports the XU pipe 83 % busy (profiles/r1_bp_qc_f32_v3_ncu_full.csv)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(code, args, args.cpu_seconds)
-    if rank == 0 and world == 1 and not args.no_extras:
-        # secondary workloads of BASELINE.json (parity-test configs, reported for context; not the headline)
+    if not args.no_extras:
+        # the other BASELINE.json workloads (AMP half of the metric: configs 1, 3, 4, 5), on EVERY rank with the
+        # headline's timing rules (tools/workloads.py): >= 5 steps / 2 warm-ups, barriers, max over ranks, clocks
+        ctx = workloads.Ctx(rank, local_rank, world)
         out["extra_workloads"] = {}
-        for key, cmd in (("sparc_amp_config1", ["tools/bench_amp.py", "--frames", "16384", "--steps", "2", "--warmup", "1"]),
-                         # same decode with the early-stop atol at the fp32 noise floor instead of the reference's 2e-15
-                         ("sparc_amp_config1_atol_1e-7", ["tools/bench_amp.py", "--frames", "16384", "--steps", "2",
-                                                          "--warmup", "1", "--atol", "1e-7"]),
-                         ("sparc_amp_config4_sc_wave", ["tools/bench_amp.py", "--config", "c4", "--frames", "592",
-                                                        "--steps", "1", "--warmup", "0"]),
-                         ("dense_amp_config3_tcgen05", ["tools/bench_dense.py", "--precision", "tc", "--frames", "1024",
-                                                        "--steps", "2", "--warmup", "1"]),
-                         ("ldpc_sparc_config5", ["tools/bench_c5.py", "--frames", "1024", "--chunk", "1024", "--sims",
-                                                 "SPARC+LDPC", "Integrated_decoder"])):
+        k = max(5, min(args.steps, 5))
+        plan = (
+            ("sparc_amp_config1", lambda: workloads.amp_workload(ctx, "c1", 16384, k, 2)),
+            # same decode with the early-stop atol at the fp32 noise floor instead of the reference's 2e-15
+            ("sparc_amp_config1_atol_1e-7", lambda: workloads.amp_workload(ctx, "c1", 16384, k, 2, atol=1e-7, e2e=False)),
+            ("sparc_amp_config4_sc_wave", lambda: workloads.amp_workload(ctx, "c4", 592, 2 if args.steps < 20 else 5, 1)),
+            ("dense_amp_config3_tcgen05", lambda: workloads.dense_workload(ctx, 1024, k, 2)),
+            ("ldpc_sparc_config5", lambda: workloads.c5_workload(ctx, 256, k, 2)),
+        )
+        for key, fn in plan:
             try:
-                r = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], capture_output=True,
-                                   text=True, timeout=240, cwd=ROOT)
-                out["extra_workloads"][key] = json.loads(r.stdout.strip().splitlines()[-1])
+                out["extra_workloads"][key] = fn()
             except Exception as e:   # the headline line must still be printed
-                out["extra_workloads"][key] = {"error": repr(e)[:200]}
-        # CPU baselines of the two SPARC configs: the numpy oracle (a port of the reference, kind "port")
-        # timed on the host cores over a bounded sample -- the cpu_baseline leg is allowed to execute oracle/
-        if not args.no_cpu_baseline:
+                out["extra_workloads"][key] = {"error": repr(e)[:300]}
+                if world > 1:
+                    raise
+            torch.cuda.empty_cache()
+        # CPU baselines of the SPARC configs: the numpy oracle (a port of the reference, kind "port") timed on the
+        # host cores over a bounded sample -- the cpu_baseline leg is allowed to execute oracle/
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             for key, cmd in (("sparc_amp_config1", ["c1", "--frames", str(4 * cores), "--procs", str(cores)]),
                              ("dense_amp_config3_tcgen05", ["c3", "--frames", "4"]),

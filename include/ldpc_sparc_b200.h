@@ -211,6 +211,16 @@ int lsb_sparc_amp_dev_f64(lsb_sparc_design *g, const double *y, int64_t n_frames
                           const lsb_sparc_amp_params *p, const int32_t *idx0,
                           const lsb_sparc_amp_out *out, void *stream);
 
+/* Host-pointer form of the batched decode: what a loop over the reference's
+ * sparc_decode (sparc_public/sparc.py:55-74, called per frame by sparc_sim.py:21-24)
+ * takes and returns.  y [F, n] received words in host memory (pinned memory makes the
+ * copies asynchronous); out: idx [F, L] MAP section decisions, t_final [F], psi
+ * [F, Lc] final psi (optional, NULL to skip; expect_err of the reference is
+ * mean(psi) >= 1e-3).  Returns when the outputs are in host memory. */
+int lsb_sparc_amp_host_f32(lsb_sparc_design *g, const float *y, int64_t n_frames,
+                           const lsb_sparc_amp_params *p, int32_t *idx, int32_t *t_final,
+                           double *psi);
+
 /* ----------------------------- (4) SPARC, dense Gaussian design (sparc_sophie)
  * Replaces, for batches of frames that share one design matrix A [n x ML]
  * (sparc_new.py:1284-1294), the NumPy steps of sparc_amp / sparc_amp_single_it

@@ -93,8 +93,6 @@ struct lsb_ldpc_graph {
     std::mutex ws_mu;
     void *d_ws = nullptr;
     size_t ws_bytes = 0;
-    void *d_ap = nullptr;      // APP scratch rows of the APP-in-global QC kernel (hard-only calls)
-    size_t ap_bytes = 0;
     cudaEvent_t ws_event = nullptr;
     // cached launch geometry per [fp64?][algo]
     int qc_grid[2][3] = {{0, 0, 0}, {0, 0, 0}};
@@ -179,23 +177,7 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
         a.scale = (T)scale;
         a.queue = queue;
         a.smem = qc_smem_bytes(g, sizeof(T));
-        a.smem_apg = a.smem - (size_t)g->nv * sizeof(T);
-        a.ap_scratch = nullptr;
         a.cached_grid = &g->qc_grid[sizeof(T) == 8][algo];
-        if (qc_uses_global_app<T>(g->max_dc, algo) && !app) {
-            // hard-decision-only call: the kernel needs a row per CTA to keep the APP values
-            std::lock_guard<std::mutex> lock(g->ws_mu);
-            const size_t need = (size_t)lsb::sm_count() * 8 * (size_t)g->nv * sizeof(float);
-            if (g->ap_bytes < need) {
-                LSB_CUDA(cudaDeviceSynchronize());
-                cudaFree(g->d_ap);
-                g->d_ap = nullptr;
-                g->ap_bytes = 0;
-                LSB_CUDA(cudaMalloc(&g->d_ap, need));
-                g->ap_bytes = need;
-            }
-            a.ap_scratch = (T *)g->d_ap;
-        }
         a.stream = st;
         return launch_qc<T>(a);
     }
@@ -536,7 +518,6 @@ void lsb_ldpc_graph_destroy(lsb_ldpc_graph *g)
     cudaFree(g->d_proto);
     cudaFree(g->d_queue);
     cudaFree(g->d_ws);
-    cudaFree(g->d_ap);
     if (g->ws_event) cudaEventDestroy(g->ws_event);
     delete g;
 }

@@ -32,9 +32,7 @@ struct QcLaunch {
     int max_it, algo, max_dc;
     T scale;
     unsigned long long *queue;
-    size_t smem;        // dynamic shared memory with / without the APP vector
-    size_t smem_apg;
-    T *ap_scratch;      // [grid, nv] rows for the APP-in-global variant when app == NULL
+    size_t smem;        // dynamic shared memory of one CTA
     int *cached_grid;   // per (handle, precision, algo) launch geometry cache
     cudaStream_t stream;
 };
@@ -55,14 +53,6 @@ struct GenericLaunch {
     long long grid;
     cudaStream_t stream;
 };
-
-#ifndef LSB_BP_APG
-#define LSB_BP_APG 0   // 1: fp32 sumprod2, degree <= 8: APP vector in global memory (6 CTAs/SM at 40 regs); measured 1.6 % slower than 5 CTAs/SM with APP in shared memory
-#endif
-template <typename T> inline bool qc_uses_global_app(int max_dc, int algo)
-{
-    return LSB_BP_APG && sizeof(T) == 4 && max_dc <= 8 && algo == LSB_BP_SUMPROD2;
-}
 
 // defined in ldpc_bp_f32.cu / ldpc_bp_f64.cu
 template <typename T> int launch_qc(const QcLaunch<T> &a);

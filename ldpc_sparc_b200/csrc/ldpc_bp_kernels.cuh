@@ -32,12 +32,6 @@
 #pragma once
 #include "ldpc_bp_host.h"
 
-// Which fp32 Lxor calls use the 3-MUFU series form of the correction instead of
-// the 4-MUFU lg2 form (see Num<float>::add_corr): bit 0 = backward chain,
-// bit 1 = forward chain, bit 2 = combine step.  Tuned on B200.
-#ifndef LSB_BP_SERIES_MASK
-#define LSB_BP_SERIES_MASK 0
-#endif
 // 1: fp32 sumprod2 takes the stop-rule syndrome from the sign/min rule (same sign
 // and zero as the corrected value, saves one Lxor per check)
 #ifndef LSB_BP_CHEAP_SYNDROME
@@ -68,28 +62,14 @@ struct Num<float> {
     // so nothing else changes, and Lxor becomes
     //   sign*min + lg2(1 + 2^-|a+b|) - lg2(1 + 2^-|a-b|)
     // with no multiplies: 4 MUFU (2 EX2 + 2 LG2) and 9 other instructions.
-    // (LSB_BP_CORR_LG2 = 0 selects the 3-MUFU variant instead: lg2((1+u)/(1+v)) =
-    // 2 log2(e) atanh(w), w = (u-v)/(2+u+v), |w| <= 1/3, one MUFU.RCP and an odd
-    // series through w^13; it measured slower on B200 because the kernel is bound
-    // by issue slots, not by the MUFU pipe -- see DESIGN.md.)
+    // (A 3-MUFU form, lg2((1+u)/(1+v)) = 2 log2(e) atanh(w) with one MUFU.RCP and an odd series, measured
+    // 1.4-5.5 % slower on B200: its extra FP32 instructions cost more issue slots than the MUFU saves.)
     // Abs. error of the correction ~2e-7; parity bound 1e-4 relative.
-    template <bool SERIES>
     static __device__ __forceinline__ float add_corr(float out, float a, float b)
     {
         const float u = ex2(-fabsf(a + b));
         const float v = ex2(-fabsf(a - b));
-        if (!SERIES) return out + (__log2f(1.0f + u) - __log2f(1.0f + v));
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((u + v) + 2.0f));
-        const float w = (u - v) * r;
-        const float w2 = w * w;
-        float p = fmaf(w2, 1.0f / 13.0f, 1.0f / 11.0f);
-        p = fmaf(p, w2, 1.0f / 9.0f);
-        p = fmaf(p, w2, 1.0f / 7.0f);
-        p = fmaf(p, w2, 1.0f / 5.0f);
-        p = fmaf(p, w2, 1.0f / 3.0f);
-        p = fmaf(p, w2, 1.0f);
-        return fmaf(2.0f * 1.4426950408889634f, w * p, out);
+        return out + (__log2f(1.0f + u) - __log2f(1.0f + v));
     }
     static __device__ __forceinline__ float with_sign_of_product(float mag, float a, float b)
     {
@@ -105,7 +85,6 @@ struct Num<double> {
     // Same expression and evaluation order as the reference (c_ldpc.c:246-247).
     // Not inlined: the fp64 path is the parity mode, and inlining libdevice
     // exp/log into every unrolled trellis costs minutes of compile time.
-    template <bool SERIES>
     static __device__ __noinline__ double add_corr(double out, double a, double b)
     {
         out += log(1 + exp(-fabs(a + b)));
@@ -136,11 +115,11 @@ struct Domain<float, LSB_BP_SUMPROD2> {
 
 // LLR of the XOR of two bits (c_ldpc.c:234-251).  mag >= 0, so OR-ing the sign
 // bit in reproduces "sign(a)sign(b) * min(|a|,|b|)" including signed zeros.
-template <typename T, bool CORR, bool SERIES = false>
+template <typename T, bool CORR>
 __device__ __forceinline__ T lxor(T a, T b)
 {
     T out = Num<T>::with_sign_of_product(fmin(fabs(a), fabs(b)), a, b);
-    if (CORR) out = Num<T>::template add_corr<SERIES>(out, a, b);
+    if (CORR) out = Num<T>::add_corr(out, a, b);
     return out;
 }
 
@@ -166,21 +145,19 @@ __device__ __forceinline__ T check_node(T (&L)[DC], T scale)
     } else {
         constexpr bool CORR = (ALGO == LSB_BP_SUMPROD2);
         constexpr bool F32 = sizeof(T) == 4;
-        constexpr bool S_BWD = F32 && (LSB_BP_SERIES_MASK & 1), S_FWD = F32 && (LSB_BP_SERIES_MASK & 2),
-                       S_CMB = F32 && (LSB_BP_SERIES_MASK & 4);
         T b[DC];
         b[DC - 1] = L[DC - 1];
 #pragma unroll
-        for (int i = DC - 2; i >= 1; --i) b[i] = lxor<T, CORR, S_BWD>(b[i + 1], L[i]);
+        for (int i = DC - 2; i >= 1; --i) b[i] = lxor<T, CORR>(b[i + 1], L[i]);
         // b[0] only feeds the stopping rule "<= 0": the uncorrected value has the
         // same sign and the same zeros (|correction| < min(|a|,|b|))
-        b[0] = (F32 && LSB_BP_CHEAP_SYNDROME) ? lxor<T, false>(b[1], L[0]) : lxor<T, CORR, S_BWD>(b[1], L[0]);
+        b[0] = (F32 && LSB_BP_CHEAP_SYNDROME) ? lxor<T, false>(b[1], L[0]) : lxor<T, CORR>(b[1], L[0]);
         T f = L[0];
         L[0] = b[1];
 #pragma unroll
         for (int i = 1; i < DC - 1; ++i) {
-            T out = lxor<T, CORR, S_CMB>(f, b[i + 1]);
-            f = lxor<T, CORR, S_FWD>(f, L[i]);
+            T out = lxor<T, CORR>(f, b[i + 1]);
+            f = lxor<T, CORR>(f, L[i]);
             L[i] = out;
         }
         L[DC - 1] = f;
@@ -309,21 +286,16 @@ __device__ __forceinline__ T variable_node_any(T *msg, const int2 *entry, int dv
 }
 
 // ------------------------------------------------------------------ QC kernel
-template <int MAXDC, int ELEM, bool APG>
+template <int MAXDC, int ELEM>
 struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
-    static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? (APG ? 6 : LSB_BP_OCC8) : (MAXDC <= 16 ? 4 : 3));
+    static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? LSB_BP_OCC8 : (MAXDC <= 16 ? 4 : 3));
 };
 
-// APG: the APP vector is not kept in shared memory but written straight to its
-// output row (or, when the caller wants hard decisions only, to a per-CTA scratch row)
-// at every variable-node pass.  The stores cost the same instructions, stay in L2 and
-// free 4*nv bytes of shared memory per CTA: 6 instead of 5 resident CTAs per SM for the
-// n = 1944 code (40 registers, no spills).
-template <typename T, int ALGO, int MAXDC, bool APG>
-__global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T), APG>::value)
+template <typename T, int ALGO, int MAXDC>
+__global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T)>::value)
 bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *__restrict__ app,
              uint8_t *__restrict__ hard, int32_t *__restrict__ iters, long long n_frames,
-             int max_it, T scale, unsigned long long *__restrict__ queue, T *__restrict__ ap_scratch)
+             int max_it, T scale, unsigned long long *__restrict__ queue)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QcTables tabs;
@@ -339,14 +311,13 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
     const unsigned magic = tabs.magic;
     T *msg = reinterpret_cast<T *>(smem_raw);   // [n_edges][z]
     T *ch = msg + n_msg;                        // [nv]
-    T *ap = ch + nv;                            // [nv] (shared-memory variant)
+    T *ap = ch + nv;                            // [nv]
 
     for (;;) {
         if (tid == 0) s_frame = (long long)atomicAdd(queue, 1ull);
         __syncthreads();
         const long long f = s_frame;
         if (f >= n_frames) break;
-        if (APG) ap = app ? app + f * nv : ap_scratch + (size_t)blockIdx.x * nv;
 
         const T *frame_llr = llr + f * nv;
         for (int v = tid; v < nv; v += kThreads) {
@@ -364,7 +335,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
                 const int j = v - c * z;
                 const int t0 = tabs.col_ptr[c];
                 const T total = variable_node_any<T>(msg, tabs.col_entry + t0, tabs.col_ptr[c + 1] - t0, j, z, ch[v]);
-                ap[v] = APG ? Domain<T, ALGO>::out(total) : total;
+                ap[v] = total;
             }
             __syncthreads();
             // ---- check nodes: lane = consecutive checks of a (degree-sorted) row
@@ -382,11 +353,11 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
         }
 
         if (tid == 0) iters[f] = it;
-        if (!APG && app) {
+        if (app) {
             T *o = app + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = Domain<T, ALGO>::out(ap[v]);
         }
-        if (hard) {   // (APG: every thread reads back only what it wrote itself)
+        if (hard) {
             uint8_t *o = hard + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
         }
@@ -455,11 +426,11 @@ bp_generic_kernel(const int *__restrict__ voff, const int *__restrict__ coff,
 }
 
 // ------------------------------------------------------------------ launchers
-template <typename T, int ALGO, int MAXDC, bool APG>
+template <typename T, int ALGO, int MAXDC>
 int launch_qc_bucket(const QcLaunch<T> &a)
 {
-    auto kern = bp_qc_kernel<T, ALGO, MAXDC, APG>;
-    const size_t smem = APG ? a.smem_apg : a.smem;
+    auto kern = bp_qc_kernel<T, ALGO, MAXDC>;
+    const size_t smem = a.smem;
     LSB_CUDA(lsb::ensure_dynamic_smem(kern, smem));       // per (kernel, device), raise-only: other codes share kern
     if (*a.cached_grid == 0) {
         int per_sm = 0;
@@ -470,7 +441,7 @@ int launch_qc_bucket(const QcLaunch<T> &a)
     long long grid = *a.cached_grid;
     if (grid > a.n_frames) grid = a.n_frames;
     kern<<<(unsigned)grid, kThreads, smem, a.stream>>>(a.tabs, a.llr, a.app, a.hard, a.iters, a.n_frames,
-                                                      a.max_it, a.scale, a.queue, a.ap_scratch);
+                                                      a.max_it, a.scale, a.queue);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     return LSB_OK;
@@ -479,13 +450,9 @@ int launch_qc_bucket(const QcLaunch<T> &a)
 template <typename T, int ALGO>
 int launch_qc_algo(const QcLaunch<T> &a)
 {
-    // APP-in-global variant: fp32 sumprod2 on degree <= 8 codes (the throughput path)
-    if (a.max_dc <= 8) {
-        if (qc_uses_global_app<T>(a.max_dc, ALGO)) return launch_qc_bucket<T, ALGO, 8, true>(a);
-        return launch_qc_bucket<T, ALGO, 8, false>(a);
-    }
-    if (a.max_dc <= 16) return launch_qc_bucket<T, ALGO, 16, false>(a);
-    return launch_qc_bucket<T, ALGO, 24, false>(a);
+    if (a.max_dc <= 8) return launch_qc_bucket<T, ALGO, 8>(a);
+    if (a.max_dc <= 16) return launch_qc_bucket<T, ALGO, 16>(a);
+    return launch_qc_bucket<T, ALGO, 24>(a);
 }
 
 template <typename T>

@@ -254,6 +254,9 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
     T2 *tile = (GBUF && d.h == 15) ? reinterpret_cast<T2 *>(smem + staged_tile_offset(d.n, sizeof(T))) : nullptr;
     __shared__ double psi[kMaxLc], psi_prev[kMaxLc], tau[kMaxLc], nm[kMaxLc];
     __shared__ double phi[kMaxLr], phi_prev[kMaxLr], gam[kMaxLr], zsq[kMaxLr];
+    // per-warp partial sums, added in fixed warp order by one thread: results are bit-reproducible run to run
+    // (slots of column parity c & 1 are rewritten two columns, i.e. several barriers, after they were read)
+    __shared__ double part_psi[2][kThreads / 32], part_nm[2][kThreads / 32], part_z[kThreads / 32];
     __shared__ long long s_frame;
     __shared__ int s_stop;
 
@@ -310,9 +313,15 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                     double part = 0.0;
                     for (int i = tid; i < d.Mr; i += kThreads) { const double v = (double)z[r * d.Mr + i]; part += v * v; }
                     part = warp_sum(part);
-                    if (lane == 0) atomicAdd(&zsq[r], part);
+                    if (lane == 0) part_z[warp] = part;
+                    __syncthreads();
+                    if (tid == 0) {
+                        double a = 0.0;
+                        for (int w = 0; w < kThreads / 32; ++w) a += part_z[w];
+                        zsq[r] = a;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             if (tid < d.Lr) phi[tid] = p.phi_method == 1 ? p.awgn_var + gam[tid] : zsq[tid] / d.Mr;
             __syncthreads();
@@ -391,8 +400,8 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                         psi_part = warp_sum(psi_part);
                         nm_part = warp_sum(nm_part);
                         if (lane == 0) {
-                            atomicAdd(&psi[c], psi_part);
-                            atomicAdd(&nm[c], nm_part);
+                            part_psi[c & 1][warp] = psi_part;
+                            part_nm[c & 1][warp] = nm_part;
                         }
                     } else {
                         for (int j0 = tid; j0 < d.Mc; j0 += kThreads * kBatch) {
@@ -413,7 +422,15 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                     }
                     __syncthreads();
                 }
-                if (fuse_denoiser && b1 > b0) continue;      // beta, psi, nmse of this column are done
+                if (fuse_denoiser && b1 > b0) {              // beta, psi, nmse of this column are done
+                    if (tid == 0) {
+                        double a = 0.0, bsum = 0.0;
+                        for (int w = 0; w < kThreads / 32; ++w) { a += part_psi[c & 1][w]; bsum += part_nm[c & 1][w]; }
+                        psi[c] = a;
+                        nm[c] = bsum;
+                    }
+                    continue;
+                }
                 // denoiser: sections of M entries, beta = softmax(s / tau) (:429-432)
                 double psi_part = 0.0, nm_part = 0.0;
                 const T inv_tau = (T)1 / tau_c;
@@ -514,10 +531,16 @@ amp_kernel(DesignDev d, FftTables<T> tb, AmpParams p, const T *__restrict__ y_al
                 psi_part = warp_sum(psi_part);
                 nm_part = warp_sum(nm_part);
                 if (lane == 0) {
-                    atomicAdd(&psi[c], psi_part);
-                    atomicAdd(&nm[c], nm_part);
+                    part_psi[c & 1][warp] = psi_part;
+                    part_nm[c & 1][warp] = nm_part;
                 }
                 __syncthreads();
+                if (tid == 0) {
+                    double a = 0.0, bsum = 0.0;
+                    for (int w = 0; w < kThreads / 32; ++w) { a += part_psi[c & 1][w]; bsum += part_nm[c & 1][w]; }
+                    psi[c] = a;
+                    nm[c] = bsum;
+                }
             }
             // ---- psi, nmse, early stop (:976-986)
             if (tid == 0) {
@@ -594,6 +617,11 @@ struct lsb_sparc_design {
     bool has_pair = false, full_columns = true;
     PairDev pair{};
     int amp_grid_pair = 0;
+    // host-pointer API staging (lazily sized), one host call at a time per handle
+    std::mutex stage_mu;
+    cudaStream_t stage_stream = nullptr;
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
 };
 
 namespace {
@@ -1104,6 +1132,8 @@ void lsb_sparc_design_destroy(lsb_sparc_design *g)
     for (void *p : g->allocs) cudaFree(p);
     cudaFree(g->d_queue);
     cudaFree(g->d_scratch);
+    cudaFree(g->stage);
+    if (g->stage_stream) cudaStreamDestroy(g->stage_stream);
     if (g->scratch_event) cudaEventDestroy(g->scratch_event);
     delete g;
 }
@@ -1143,6 +1173,58 @@ int lsb_sparc_amp_dev_f64(lsb_sparc_design *g, const double *y, int64_t n_frames
                           const int32_t *idx0, const lsb_sparc_amp_out *out, void *stream)
 {
     return run_amp<double>(g, y, n_frames, p, idx0, out, (cudaStream_t)stream);
+}
+
+// Host-pointer decode of a batch (what a loop over the reference's sparc_decode, sparc.py:55-74, consumes and
+// returns): y in, section decisions + iteration counts + final psi out.  The copies are a few per cent of the
+// decode (13.6 KB in and 4 KB out per frame against ~17 us of kernel time at config 1), so a batch goes up in
+// one piece per 65 536 frames rather than in small overlapped chunks, which would leave a partial last wave
+// of CTAs per chunk.
+int lsb_sparc_amp_host_f32(lsb_sparc_design *g, const float *y, int64_t n_frames, const lsb_sparc_amp_params *p,
+                           int32_t *idx, int32_t *t_final, double *psi)
+{
+    if (n_frames == 0) return LSB_OK;
+    LSB_REQUIRE(g && y && p && idx && t_final, "null pointer");
+    LSB_REQUIRE(n_frames >= 0, "negative frame count");
+    int rc = check_device(g);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g->stage_mu);
+    const DesignDev &d = g->dev;
+    const int64_t chunk = n_frames < 65536 ? n_frames : 65536;
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };       // every staging segment starts 256-byte aligned
+    const size_t y_b = pad((size_t)chunk * d.n * sizeof(float)), idx_b = pad((size_t)chunk * d.L * sizeof(int32_t));
+    const size_t t_b = pad((size_t)chunk * sizeof(int32_t)), psi_b = pad((size_t)chunk * d.Lc * sizeof(double));
+    const size_t need = y_b + idx_b + t_b + psi_b;
+    if (!g->stage_stream) LSB_CUDA(cudaStreamCreateWithFlags(&g->stage_stream, cudaStreamNonBlocking));
+    if (g->stage_bytes < need) {
+        LSB_CUDA(cudaStreamSynchronize(g->stage_stream));
+        cudaFree(g->stage);
+        g->stage = nullptr;
+        g->stage_bytes = 0;
+        LSB_CUDA(cudaMalloc(&g->stage, need));
+        g->stage_bytes = need;
+    }
+    char *base = (char *)g->stage;
+    float *d_y = (float *)base;
+    double *d_psi = (double *)(base + y_b);
+    int32_t *d_idx = (int32_t *)(base + y_b + psi_b);
+    int32_t *d_t = (int32_t *)(base + y_b + psi_b + idx_b);
+    const cudaStream_t st = g->stage_stream;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int64_t nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        LSB_CUDA(cudaMemcpyAsync(d_y, y + (size_t)f0 * d.n, (size_t)nf * d.n * sizeof(float), cudaMemcpyHostToDevice, st));
+        lsb_sparc_amp_out o{};
+        o.idx = d_idx;
+        o.t_final = d_t;
+        o.psi = d_psi;
+        if ((rc = run_amp<float>(g, d_y, nf, p, nullptr, &o, st))) return rc;
+        LSB_CUDA(cudaMemcpyAsync(idx + (size_t)f0 * d.L, d_idx, (size_t)nf * d.L * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        LSB_CUDA(cudaMemcpyAsync(t_final + f0, d_t, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (psi)
+            LSB_CUDA(cudaMemcpyAsync(psi + (size_t)f0 * d.Lc, d_psi, (size_t)nf * d.Lc * sizeof(double), cudaMemcpyDeviceToHost, st));
+        LSB_CUDA(cudaStreamSynchronize(st));
+    }
+    return LSB_OK;
 }
 
 }  // extern "C"

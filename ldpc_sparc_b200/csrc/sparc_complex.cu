@@ -173,6 +173,8 @@ camp_kernel(CDesign d, FftTables<T> tb, CParams p, const typename Cplx<T>::type 
     T2 *z = gbuf ? reinterpret_cast<T2 *>(smem) : buf + d.w;       // [n]
     __shared__ double psi[kMaxLc], psi_prev[kMaxLc], tau[kMaxLc], nm[kMaxLc];
     __shared__ double phi[kMaxLr], phi_prev[kMaxLr], gam[kMaxLr], zsq[kMaxLr];
+    // per-warp partial sums added in fixed warp order by one thread (bit-reproducible run to run)
+    __shared__ double part_psi[2][kThreads / 32], part_nm[2][kThreads / 32], part_z[kThreads / 32];
     __shared__ T2 con[kMaxK];                  // constellation
     __shared__ long long s_frame;
     __shared__ int s_stop;
@@ -240,9 +242,15 @@ camp_kernel(CDesign d, FftTables<T> tb, CParams p, const typename Cplx<T>::type 
                         part += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
                     }
                     part = warp_sum(part);
-                    if (lane == 0) atomicAdd(&zsq[r], part);
+                    if (lane == 0) part_z[warp] = part;
+                    __syncthreads();
+                    if (tid == 0) {
+                        double a = 0.0;
+                        for (int w = 0; w < kThreads / 32; ++w) a += part_z[w];
+                        zsq[r] = a;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             if (tid < d.Lr) phi[tid] = p.phi_method == 1 ? p.awgn_var + gam[tid] : zsq[tid] / d.Mr;
             __syncthreads();
@@ -323,10 +331,16 @@ camp_kernel(CDesign d, FftTables<T> tb, CParams p, const typename Cplx<T>::type 
                 psi_part = warp_sum(psi_part);
                 nm_part = warp_sum(nm_part);
                 if (lane == 0) {
-                    atomicAdd(&psi[c], psi_part);
-                    atomicAdd(&nm[c], nm_part);
+                    part_psi[c & 1][warp] = psi_part;
+                    part_nm[c & 1][warp] = nm_part;
                 }
                 __syncthreads();
+                if (tid == 0) {         // slots of parity c & 1 are rewritten two columns (several barriers) later
+                    double a = 0.0, bsum = 0.0;
+                    for (int w = 0; w < kThreads / 32; ++w) { a += part_psi[c & 1][w]; bsum += part_nm[c & 1][w]; }
+                    psi[c] = a;
+                    nm[c] = bsum;
+                }
             }
             if (tid == 0) {                     // psi, nmse, early stop (:976-986)
                 int stop = t > 0;

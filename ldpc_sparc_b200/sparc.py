@@ -615,6 +615,39 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     return res + (extra,) if extra else res
 
 
+def sparc_decode_host(y, code_params, decode_params, awgn_var, Ab, out=None):
+    """Batched fp32 AMP decode through the host-pointer C-ABI entry ``lsb_sparc_amp_host_f32``: the call a
+    Monte-Carlo loop over the reference's ``sparc_decode`` (sparc.py:55-74, sparc_sim.py:21-24) makes, for
+    ``F`` frames at once.  ``y``: float32 ``[F, n]`` in host memory (a numpy array, or a pinned CPU torch
+    tensor for asynchronous copies).  Returns ``(idx [F, L] int32, t_final [F] int32, psi [F, Lc] float64)``
+    as numpy arrays (or fills the pinned torch tensors passed in ``out``); ``expect_err = psi.mean(1) >= 1e-3``."""
+    import torch
+    check_decode_params(decode_params)
+    _require_real_unmodulated(code_params)
+    if not isinstance(Ab, _Operator) or Ab.design.csparc:
+        raise TypeError("Ab must come from this module's sparc_transforms / sparc_encode (real design)")
+    design = Ab.design
+    L, n, Lc = code_params['L'], code_params['n'], design.Lc
+    if isinstance(y, torch.Tensor):
+        assert y.device.type == "cpu" and y.dtype == torch.float32 and y.is_contiguous()
+        F, y_ptr = y.reshape(-1, n).shape[0], y.data_ptr()
+    else:
+        y = np.ascontiguousarray(y, dtype=np.float32).reshape(-1, n)
+        F, y_ptr = y.shape[0], y.ctypes.data
+    _lib.require_device()
+    if out is None:
+        idx, t_final, psi = np.empty((F, L), np.int32), np.empty(F, np.int32), np.empty((F, Lc), np.float64)
+        ptrs = (idx.ctypes.data, t_final.ctypes.data, psi.ctypes.data)
+    else:
+        idx, t_final, psi = out
+        ptrs = (idx.data_ptr(), t_final.data_ptr(), psi.data_ptr() if psi is not None else None)
+    t_max, rtol, phi_est_method = map(decode_params.get, ['t_max', 'rtol', 'phi_est_method'])
+    atol = float(decode_params.get('atol', 2 * np.finfo(float).resolution))
+    params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method), int(_modulation(code_params)), 0)
+    _lib.check(_lib.lib().lsb_sparc_amp_host_f32(design.handle(), y_ptr, F, ct.byref(params), *ptrs), "lsb_sparc_amp_host_f32")
+    return idx, t_final, psi
+
+
 def sparc_decode(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None, Az=None, precision=None):
     """Decode SPARC codeword(s) (reference sparc.py:55-74).  Returns
     ``bits_out, beta, t_final, nmse, expect_err``."""

@@ -182,6 +182,95 @@ def test_batched_decode_vs_oracle():
     assert np.array_equal(bits_t.cpu().numpy(), bits)
 
 
+def _c1_batch(F, seed=0):
+    cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
+    dp = dict(t_max=25)
+    sparc.check_code_params(cp)
+    sparc.check_decode_params(dp)
+    W = sparc.create_base_matrix(**dict(cp, awgn_var=1.0))
+    cp["n"] = 3413
+    Ab, Az = sparc.sparc_transforms(W, 1024, 32, 3413, [1, 2])
+    rng = np.random.RandomState(seed)
+    idx0 = rng.randint(0, 32, (F, 1024))
+    beta0 = np.zeros((F, 1024 * 32), dtype=np.float32)
+    beta0[np.arange(F)[:, None], np.arange(1024)[None, :] * 32 + idx0] = 1
+    y = (Ab(beta0, precision="fp32") + rng.randn(F, 3413)).astype(np.float32)
+    return cp, dp, Ab, Az, idx0, y
+
+
+def test_host_entry_equals_device_path_and_is_reproducible():
+    """lsb_sparc_amp_host_f32 (host buffers in / out) returns exactly what the device-pointer call returns;
+    two runs of the same batch are bit-identical (t_final, decisions, psi): the psi / nmse sums are taken in
+    a fixed order, no atomics (scheduling-dependent early stop)."""
+    import torch
+    cp, dp, Ab, Az, idx0, y = _c1_batch(37)                  # odd frame count: the last CTA holds one frame only
+    yt = torch.from_numpy(y).cuda()
+    outs = []
+    for _ in range(2):
+        idx_d, T_d, _, psi_d = sparc.sparc_amp(yt, cp, dp, 1.0, [1, 2], None, Ab, Az, precision="fp32")
+        outs.append((idx_d.cpu().numpy().copy(), T_d.cpu().numpy().copy(), psi_d.cpu().numpy().copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2]), "psi differs between two runs of the same batch"
+    idx_h, T_h, psi_h = sparc.sparc_decode_host(y, cp, dp, 1.0, Ab)
+    assert np.array_equal(idx_h, outs[0][0]) and np.array_equal(T_h, outs[0][1]) and np.array_equal(psi_h, outs[0][2])
+    assert (idx_h != idx0).mean() < 5e-3
+    # a frame decoded alone, or next to a different neighbour, gives the same result as inside the batch
+    perm = np.arange(37)[::-1].copy()
+    idx_p, T_p, psi_p = sparc.sparc_decode_host(y[perm], cp, dp, 1.0, Ab)
+    assert np.array_equal(idx_p, idx_h[perm]) and np.array_equal(T_p, T_h[perm]) and np.array_equal(psi_p, psi_h[perm])
+    idx_1, T_1, psi_1 = sparc.sparc_decode_host(y[5:6], cp, dp, 1.0, Ab)
+    assert np.array_equal(idx_1[0], idx_h[5]) and T_1[0] == T_h[5] and np.array_equal(psi_1[0], psi_h[5])
+
+
+def test_pair_kernel_against_one_frame_kernel(tmp_path):
+    """The two-frames-per-CTA fp32 kernel against the one-frame fp32 kernel (LSB_AMP_PAIR=0; the switch is read
+    once per process, so the one-frame numbers come from a subprocess fed the same received words)."""
+    import subprocess
+    import sys
+    cp, dp, Ab, Az, idx0, y = _c1_batch(16, seed=3)
+    idx_h, T_h, psi_h = sparc.sparc_decode_host(y, cp, dp, 1.0, Ab)
+    np.save(tmp_path / "y.npy", y)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from ldpc_sparc_b200 import sparc\n"
+        "cp = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9); dp = dict(t_max=25)\n"
+        "sparc.check_code_params(cp); sparc.check_decode_params(dp)\n"
+        "W = sparc.create_base_matrix(**dict(cp, awgn_var=1.0)); cp['n'] = 3413\n"
+        "Ab, Az = sparc.sparc_transforms(W, 1024, 32, 3413, [1, 2])\n"
+        "idx, T, psi = sparc.sparc_decode_host(np.load(%r), cp, dp, 1.0, Ab)\n"
+        "np.savez(%r, idx=idx, T=T, psi=psi)\n"
+    ) % (root, str(tmp_path / "y.npy"), str(tmp_path / "one.npz"))
+    env = dict(os.environ, LSB_AMP_PAIR="0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    one = np.load(tmp_path / "one.npz")
+    assert np.array_equal(one["idx"], idx_h), "decisions of the two fp32 kernels differ"
+    # fp32 iterates differ in the last bits, so t_final may differ by the stop rule's noise; psi agrees to fp32 accuracy
+    assert np.max(np.abs(one["T"].astype(int) - T_h.astype(int))) <= 3
+    assert np.allclose(one["psi"], psi_h, rtol=0, atol=1e-6)
+
+
+def test_alternating_designs_keep_their_shared_memory_opt_in():
+    """Two designs of different size share the kernels' template instantiations; the dynamic shared-memory
+    opt-in is per (kernel, device) and must never shrink (second design lowered it, the first then
+    failed to launch)."""
+    big = dict(P=15.0, R=1.5, L=1024, M=32, power_allocated=True, B=32, R_PA_ratio=0.9)
+    small = dict(P=15.0, R=1.0, L=64, M=32)
+    res = {}
+    for rep in range(2):
+        for name, cp in (("big", big), ("small", small)):
+            cp = dict(cp)
+            bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, 1.0, [7, 8])
+            y = x + np.random.RandomState(1).randn(cp["n"])
+            for prec in ("fp64", "fp32"):
+                out = sparc.sparc_decode(y, cp, dict(t_max=10), 1.0, [7, 8], beta0, Ab, Az, precision=prec)
+                key = (name, prec)
+                if key in res:
+                    assert np.array_equal(res[key], out[0])
+                res[key] = out[0]
+
+
 def test_config4_sc_wave_matches_reference_golden(gold):
     """BASELINE config 4 (sparc_demo_sc_decode_wave.ipynb: L=2048, M=512, R=1.5, omega=6,
     Lambda=32, t_max=40 -> Lr=37, Lc=32, n=12284, transform size 65536, 192 blocks).  The FFT
