@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-mc", action="store_true", help="skip the fused generate-decode-count Monte-Carlo leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp64 re-decode of the batch after the timed region")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary workloads (SPARC AMP config 1, dense-design AMP config 3)")
@@ -287,6 +288,28 @@ def main():
         "monte_carlo": {"frames": frames, "frame_errors": frame_errs, "bit_errors": bit_errs,
                         "mean_iterations": it_sum / max(frames, 1), "mean_executed_iterations": exec_sum / max(frames, 1)},
     }
+
+    # the same step with the frames GENERATED inside the kernel (lsb_ldpc_mc_dev_f32: Philox noise + BPSK + LLR scaling in
+    # the load phase, error counting in the epilogue): what a Monte-Carlo sweep runs, no 510 MB LLR batch in HBM
+    if not args.no_mc:
+        cw_pool = (sgn < 0).to(torch.uint8).contiguous()
+        mc_counters = torch.zeros(4, dtype=torch.int64, device=dev)
+
+        def mc_step(i=[0]):
+            i[0] += 1
+            code.mc_decode(cw_pool, F, s2, seed=4242, frame0=(i[0] * world + rank) * F, max_itcount=args.max_it,
+                           counters=mc_counters)
+
+        mc_ms, _ = workloads.timed(workloads.Ctx(rank, local_rank, world), mc_step, args.steps, 2)
+        mc = mc_counters.clone()
+        if world > 1:
+            dist.all_reduce(mc, op=dist.ReduceOp.SUM)
+        mcl = [int(v) for v in mc.tolist()]
+        out["monte_carlo_fused"] = {
+            "value": world * F * K * args.steps / (mc_ms * 1e-3), "unit": "info bits/s", "ms_per_step": mc_ms / args.steps,
+            "frames_per_s": world * F * args.steps / (mc_ms * 1e-3), "frames": mcl[2], "frame_errors": mcl[1],
+            "bit_errors": mcl[0], "mean_iterations": mcl[3] / max(mcl[2], 1),
+            "api": "lsb_ldpc_mc_dev_f32 (generate -> decode -> count in one kernel; warm-up steps included in the counters)"}
 
     # parity at bench scale (outside the timed region): the same frames through the fp64 kernel, whose iteration
     # counts and decisions are the reference's (tests/test_ldpc_gpu.py: exact against c_ldpc.c)

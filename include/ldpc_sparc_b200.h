@@ -121,6 +121,21 @@ int lsb_ldpc_decode_dev_f64(const lsb_ldpc_graph *g, const double *llr,
                             int64_t n_frames, int max_it, int algo,
                             double scale, void *stream);
 
+/* Fused Monte-Carlo step (replaces the body of the reference's simulation loop,
+ * ldpc_jossy/py/ldpc_awgn.py:88-107: bpsk -> awgn -> ch2llr -> decode -> count) for QC
+ * graphs.  Frame f of the call carries codeword (frame0 + f) mod n_codewords of the device
+ * array codewords [n_codewords, N] (0 / 1, e.g. from lsb_ldpc_encode_dev), BPSK-modulated,
+ * plus N(0, sigma2) noise from Philox4x32-10 keyed by (seed, frame0 + f): the noise of a
+ * frame depends on its global index only, so results do not change with the batch split
+ * or the number of GPUs.  Nothing but the codeword pool is read from HBM and nothing but
+ * the requested outputs is written: bit_errors [F] wrong hard decisions over all N code
+ * bits (:99), iters [F], llr_out [F, N] the generated channel LLRs (tests), counters [4]
+ * += {bit errors, frame errors, frames, iterations} (each optional, device pointers). */
+int lsb_ldpc_mc_dev_f32(const lsb_ldpc_graph *g, const uint8_t *codewords, int64_t n_codewords,
+                        double sigma2, uint64_t seed, uint64_t frame0, int64_t n_frames,
+                        int max_it, int algo, double scale, int32_t *bit_errors, int32_t *iters,
+                        float *llr_out, uint64_t *counters, void *stream);
+
 /* Host-pointer decode: the call copies llr host->device, decodes and copies
  * the requested outputs back, in chunks pipelined over internal streams, and
  * returns when the outputs are complete.  Buffers may be pageable or pinned

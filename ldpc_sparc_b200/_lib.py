@@ -57,6 +57,9 @@ SIGNATURES = {
     "lsb_ldpc_graph_create": (ct.c_int, [c_i64p, c_i64p, c_i64p, ct.c_int64, ct.c_int64, ct.c_int64, ct.POINTER(ct.c_void_p)]),
     "lsb_ldpc_graph_destroy": (None, [ct.c_void_p]),
     "lsb_ldpc_graph_info": (ct.c_int, [ct.c_void_p, c_i64p]),
+    "lsb_ldpc_mc_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_double, ct.c_uint64, ct.c_uint64, ct.c_int64,
+                                       ct.c_int, ct.c_int, ct.c_double, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p,
+                                       ct.c_void_p]),
     "lsb_ldpc_encode_dev": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_ldpc_decode_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_void_p]),
     "lsb_ldpc_decode_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_void_p]),

@@ -147,11 +147,11 @@ size_t qc_smem_bytes(const lsb_ldpc_graph *g, size_t elem)
 
 template <typename T>
 int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, int32_t *iters,
-               int64_t n_frames, int max_it, int algo, double scale, cudaStream_t st)
+               int64_t n_frames, int max_it, int algo, double scale, cudaStream_t st, const McParams *mc = nullptr)
 {
     lsb_ldpc_graph *g = const_cast<lsb_ldpc_graph *>(cg);
     if (n_frames == 0) return LSB_OK;                  // an empty batch is valid with any pointers
-    LSB_REQUIRE(g && llr && iters, "null graph / llr / iters pointer");
+    LSB_REQUIRE(g && (mc || (llr && iters)), "null graph / llr / iters pointer");
     LSB_REQUIRE(n_frames >= 0 && max_it >= 0, "negative n_frames or max_it");
     LSB_REQUIRE(algo >= 0 && algo <= 2, "unknown algo %d", algo);
     int rc = check_device(g);
@@ -179,8 +179,10 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
         a.smem = qc_smem_bytes(g, sizeof(T));
         a.cached_grid = &g->qc_grid[sizeof(T) == 8][algo];
         a.stream = st;
+        if (mc) a.mc = *mc;
         return launch_qc<T>(a);
     }
+    LSB_REQUIRE(!mc, "the fused Monte-Carlo front end needs a QC graph within the QC kernel's limits");
     // generic path: one message workspace per handle, so launches are chained
     // through ws_event (they may sit on different streams)
     int &cached = g->gen_grid[sizeof(T) == 8][0];
@@ -324,6 +326,28 @@ int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, i
 }  // namespace
 
 extern "C" {
+
+int lsb_ldpc_mc_dev_f32(const lsb_ldpc_graph *g, const uint8_t *codewords, int64_t n_codewords, double sigma2,
+                        uint64_t seed, uint64_t frame0, int64_t n_frames, int max_it, int algo, double scale,
+                        int32_t *bit_errors, int32_t *iters, float *llr_out, uint64_t *counters, void *stream)
+{
+    if (n_frames == 0) return LSB_OK;
+    LSB_REQUIRE(g && codewords && n_codewords > 0, "null graph / codewords");
+    LSB_REQUIRE(sigma2 > 0.0, "sigma2 must be positive");
+    LSB_REQUIRE(n_frames >= 0 && max_it >= 0, "negative n_frames or max_it");
+    LSB_REQUIRE(algo >= 0 && algo <= 2, "unknown algo %d", algo);
+    McParams mc;
+    mc.cw = codewords;
+    mc.n_cw = n_codewords;
+    mc.llr_scale = (float)(2.0 / sigma2);
+    mc.sigma = (float)std::sqrt(sigma2);
+    mc.seed = seed;
+    mc.frame0 = frame0;
+    mc.bit_errors = bit_errors;
+    mc.llr_out = llr_out;
+    mc.counters = (unsigned long long *)counters;
+    return decode_dev<float>(g, nullptr, nullptr, nullptr, iters, n_frames, max_it, algo, scale, (cudaStream_t)stream, &mc);
+}
 
 int lsb_ldpc_graph_create(const int64_t *vdeg, const int64_t *cdeg, const int64_t *intrlv,
                           int64_t nv, int64_t nc, int64_t nmsg, lsb_ldpc_graph **out)

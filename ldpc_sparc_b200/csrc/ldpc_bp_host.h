@@ -21,6 +21,21 @@ struct QcTables {
     int2 col_entry[kMaxEdges];       // per column-list entry: (edge*z - shift, shift mod z)
 };
 
+// Fused Monte-Carlo front end of the QC kernel (reference loop: ldpc_jossy/py/ldpc_awgn.py:88-107).  With
+// cw != nullptr the kernel does not read LLRs: frame f carries codeword (frame0 + f) mod n_cw, BPSK-modulated
+// (1 - 2 x, :55-56), plus sigma * N(0, 1) noise from Philox4x32-10 keyed by (seed, frame0 + f) -- the noise of a
+// frame depends on its GLOBAL index only, not on the launch geometry or the number of GPUs -- scaled to LLRs by
+// 2 / sigma^2 (:51-53); after the decode it counts the wrong hard decisions over all N code bits (:99).
+struct McParams {
+    const uint8_t *cw = nullptr;       // [n_cw, N] code bits (0 / 1), device
+    long long n_cw = 0;
+    float llr_scale = 0.f, sigma = 0.f;
+    unsigned long long seed = 0, frame0 = 0;
+    int32_t *bit_errors = nullptr;     // [F] wrong bits of the frame (optional)
+    float *llr_out = nullptr;          // [F, N] the channel LLRs that were generated (optional; tests)
+    unsigned long long *counters = nullptr;   // [4] += bit errors, frame errors, frames, iterations (optional)
+};
+
 template <typename T>
 struct QcLaunch {
     const QcTables *tabs;
@@ -35,6 +50,7 @@ struct QcLaunch {
     size_t smem;        // dynamic shared memory of one CTA
     int *cached_grid;   // per (handle, precision, algo) launch geometry cache
     cudaStream_t stream;
+    McParams mc;
 };
 
 template <typename T>

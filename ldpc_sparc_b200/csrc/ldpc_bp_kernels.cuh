@@ -285,6 +285,38 @@ __device__ __forceinline__ T variable_node_any(T *msg, const int2 *entry, int dv
     return sum;
 }
 
+// ------------------------------------------------------------------ Monte-Carlo front end
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0, k1) -> 4 x 32 random bits.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// two standard normals from two 32-bit words (Box-Muller; u1 in (0, 1], |n| <= 6.66)
+__device__ __forceinline__ float2 box_muller(unsigned a, unsigned b)
+{
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;        // (a + 1) / 2^32; a = 2^32 - 1 rounds to 1.0
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf((float)b * 1.4629180792671596e-9f, &sn, &cs);               // 2 pi b / 2^32
+    return make_float2(r * cs, r * sn);
+}
+// the 4 noise samples of code bits 4 q .. 4 q + 3 of the frame with global index gf
+__device__ __forceinline__ float4 mc_noise4(unsigned long long seed, unsigned long long gf, unsigned q)
+{
+    const uint4 r = philox4x32_10(make_uint4(q, 0u, (unsigned)gf, (unsigned)(gf >> 32)),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 // ------------------------------------------------------------------ QC kernel
 template <int MAXDC, int ELEM>
 struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
@@ -295,11 +327,13 @@ template <typename T, int ALGO, int MAXDC>
 __global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T)>::value)
 bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *__restrict__ app,
              uint8_t *__restrict__ hard, int32_t *__restrict__ iters, long long n_frames,
-             int max_it, T scale, unsigned long long *__restrict__ queue)
+             int max_it, T scale, unsigned long long *__restrict__ queue, McParams mc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QcTables tabs;
     __shared__ long long s_frame;
+    __shared__ int s_err[kThreads / 32];
+    unsigned long long tot_bit = 0, tot_frame = 0, tot_n = 0, tot_it = 0;     // thread 0: this CTA's Monte-Carlo counters
 
     const int tid = threadIdx.x;
     for (int i = tid; i < (int)(sizeof(QcTables) / sizeof(int)); i += kThreads)
@@ -319,10 +353,31 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
         const long long f = s_frame;
         if (f >= n_frames) break;
 
-        const T *frame_llr = llr + f * nv;
-        for (int v = tid; v < nv; v += kThreads) {
-            ch[v] = Domain<T, ALGO>::in(frame_llr[v]);
-            ap[v] = (T)0;
+        const uint8_t *frame_cw = nullptr;
+        if (mc.cw) {
+            // generate the frame instead of reading it: LLR = 2/sigma^2 ((1 - 2 x) + sigma n)  (ldpc_awgn.py:45-56)
+            const unsigned long long gf = mc.frame0 + (unsigned long long)f;
+            frame_cw = mc.cw + (long long)(gf % (unsigned long long)mc.n_cw) * nv;
+            for (int q = tid; 4 * q < nv; q += kThreads) {
+                const float4 nz = mc_noise4(mc.seed, gf, (unsigned)q);
+                const float nn[4] = {nz.x, nz.y, nz.z, nz.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = 4 * q + u;
+                    if (v < nv) {
+                        const float l = mc.llr_scale * ((1.0f - 2.0f * (float)frame_cw[v]) + mc.sigma * nn[u]);
+                        if (mc.llr_out) mc.llr_out[f * nv + v] = l;
+                        ch[v] = Domain<T, ALGO>::in((T)l);
+                        ap[v] = (T)0;
+                    }
+                }
+            }
+        } else {
+            const T *frame_llr = llr + f * nv;
+            for (int v = tid; v < nv; v += kThreads) {
+                ch[v] = Domain<T, ALGO>::in(frame_llr[v]);
+                ap[v] = (T)0;
+            }
         }
         for (int i = tid; i < n_msg; i += kThreads) msg[i] = (T)0;
         __syncthreads();
@@ -352,7 +407,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
             if (!__syncthreads_or(unsatisfied)) break;
         }
 
-        if (tid == 0) iters[f] = it;
+        if (tid == 0 && iters) iters[f] = it;
         if (app) {
             T *o = app + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = Domain<T, ALGO>::out(ap[v]);
@@ -361,6 +416,30 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
             uint8_t *o = hard + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
         }
+        if (mc.cw) {
+            // wrong hard decisions over all N code bits (ldpc_awgn.py:97-103), summed in a fixed order
+            int wrong = 0;
+            for (int v = tid; v < nv; v += kThreads) wrong += (int)(ap[v] < (T)0) != (int)frame_cw[v];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wrong += __shfl_xor_sync(0xffffffffu, wrong, o);
+            if ((tid & 31) == 0) s_err[tid >> 5] = wrong;
+            __syncthreads();
+            if (tid == 0) {
+                int total = 0;
+                for (int w = 0; w < kThreads / 32; ++w) total += s_err[w];
+                if (mc.bit_errors) mc.bit_errors[f] = total;
+                tot_bit += (unsigned long long)total;
+                tot_frame += total != 0;
+                tot_n += 1;
+                tot_it += (unsigned long long)it;
+            }
+        }
+    }
+    if (mc.cw && mc.counters && tid == 0 && tot_n) {
+        atomicAdd(mc.counters + 0, tot_bit);
+        atomicAdd(mc.counters + 1, tot_frame);
+        atomicAdd(mc.counters + 2, tot_n);
+        atomicAdd(mc.counters + 3, tot_it);
     }
 }
 
@@ -441,7 +520,7 @@ int launch_qc_bucket(const QcLaunch<T> &a)
     long long grid = *a.cached_grid;
     if (grid > a.n_frames) grid = a.n_frames;
     kern<<<(unsigned)grid, kThreads, smem, a.stream>>>(a.tabs, a.llr, a.app, a.hard, a.iters, a.n_frames,
-                                                      a.max_it, a.scale, a.queue);
+                                                      a.max_it, a.scale, a.queue, a.mc);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     return LSB_OK;

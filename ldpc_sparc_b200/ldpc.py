@@ -263,6 +263,10 @@ class code:
         [F, N], it int32 [F])`` out, nothing else written.  (New API; the
         reference computes ``app < 0`` on the host, ldpc_awgn.py:97.)"""
         import torch
+        if dectype not in _lib.ALGO:
+            raise NameError('Decoder type unknown')                 # same conditions as decode (ldpc.py:470,489)
+        if llr.dim() != 2 or llr.shape[1] != self.Nv:
+            raise NameError('Channel inputs not consistent with variable degrees')
         precision = precision or DEFAULT_PRECISION
         want = torch.float64 if precision == "fp64" else torch.float32
         if llr.dtype != want or not llr.is_contiguous():
@@ -280,6 +284,33 @@ class code:
                     _lib.ALGO[dectype], float(corr_factor), torch.cuda.current_stream().cuda_stream)
             _lib.check(rc, "lsb_ldpc_decode_dev")
         return hard, iters
+
+    def mc_decode(self, codewords, n_frames, sigma2, seed=0, frame0=0, max_itcount=200, dectype="sumprod2",
+                  corr_factor=0.7, counters=None, want_llr=False):
+        """Fused Monte-Carlo step on the GPU (``lsb_ldpc_mc_dev_f32``): BPSK + AWGN(sigma2) + LLR scaling are
+        generated inside the decoder kernel (Philox keyed by ``(seed, frame0 + f)``), the decode runs, and the
+        wrong hard decisions over all N code bits are counted in its epilogue -- the body of the reference's loop
+        (ldpc_awgn.py:88-107) without an LLR batch in HBM.  ``codewords``: CUDA uint8 ``[n_cw, N]`` pool; frame f
+        carries codeword ``(frame0 + f) % n_cw``.  Returns ``(bit_errors int32 [F], iters int32 [F])`` (+ the
+        generated LLRs ``[F, N]`` with ``want_llr``); ``counters`` (CUDA int64 [4], optional) accumulates
+        bit errors, frame errors, frames, iterations."""
+        import torch
+        if not codewords.is_cuda or codewords.dtype != torch.uint8 or codewords.shape[-1] != self.N:
+            raise TypeError("codewords must be a CUDA uint8 tensor [n_cw, N]")
+        cw = codewords.reshape(-1, self.N).contiguous()
+        F = int(n_frames)
+        with torch.cuda.device(cw.device):
+            g = self._handle()
+            be = torch.empty(F, dtype=torch.int32, device=cw.device)
+            it = torch.empty(F, dtype=torch.int32, device=cw.device)
+            llr = torch.empty((F, self.N), dtype=torch.float32, device=cw.device) if want_llr else None
+            rc = _lib.lib().lsb_ldpc_mc_dev_f32(g, cw.data_ptr(), cw.shape[0], float(sigma2), int(seed) & (2 ** 64 - 1),
+                                                int(frame0), F, int(max_itcount), _lib.ALGO[dectype], float(corr_factor),
+                                                be.data_ptr(), it.data_ptr(), llr.data_ptr() if want_llr else None,
+                                                counters.data_ptr() if counters is not None else None,
+                                                torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "lsb_ldpc_mc_dev_f32")
+        return (be, it, llr) if want_llr else (be, it)
 
     def encode_device(self, info):
         """Systematic encoding on the GPU: CUDA tensor ``info [F, K]`` (any integer / bool

@@ -68,6 +68,7 @@ def ldpc_awgn_sweep(code, snr_db_points, frames_per_point, max_itcount=200, seed
     rank, world = _rank_world()
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    fused = decode_fn is None            # the CUDA path: noise, LLRs, decode and error counts in one kernel
     if decode_fn is None:
         decode_fn = lambda llr, it: code.decode_hard(llr, it)
     rng = np.random.RandomState(seed)
@@ -78,6 +79,19 @@ def ldpc_awgn_sweep(code, snr_db_points, frames_per_point, max_itcount=200, seed
     counters = torch.zeros((len(snr_db_points), len(COUNTER_FIELDS)), dtype=torch.int64, device=device)
     for p, snr_db in enumerate(snr_db_points):
         sigma2 = 10.0 ** (-float(snr_db) / 10.0)                       # ldpc_awgn.py:45-49
+        if fused:
+            # lsb_ldpc_mc_dev_f32: frame f of the point = codeword f mod n_codewords + Philox noise keyed by
+            # (seed of the point, f); ranks take contiguous chunk ranges, totals do not depend on the world size
+            mc = torch.zeros(4, dtype=torch.int64, device=device)
+            for c in shard_chunks(len(ranges), rank, world):
+                f0, nf = ranges[c]
+                code.mc_decode(truth, nf, sigma2, seed=chunk_seed(seed, p, 0), frame0=f0, max_itcount=max_itcount,
+                               counters=mc)
+            counters[p, 0] += mc[0]
+            counters[p, 1] += mc[1]
+            counters[p, 3] += mc[2]
+            counters[p, 4] += mc[3]
+            continue
         for c in shard_chunks(len(ranges), rank, world):
             f0, nf = ranges[c]
             gen = torch.Generator(device=device).manual_seed(chunk_seed(seed, p, c))
@@ -125,6 +139,7 @@ def sim(standard, rate, z, ptype='A', N_MEASUREMENTS=24, C_AWGN_OFFSET=1.0, P_ST
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     mycode = _code(standard, rate, z, ptype)
     K, N = mycode.K, mycode.N
+    fused = decode_fn is None            # CUDA path: channel, LLRs, decode and per-frame error counts in one kernel
     if decode_fn is None:
         decode_fn = lambda llr, it: mycode.decode_hard(llr, it)
     if encode_fn is None:
@@ -139,9 +154,13 @@ def sim(standard, rate, z, ptype='A', N_MEASUREMENTS=24, C_AWGN_OFFSET=1.0, P_ST
             gen = torch.Generator(device=device).manual_seed(chunk_seed(seed, datapoint, rnd * world + rank))
             u = torch.randint(0, 2, (batch, K), device=device, generator=gen, dtype=torch.uint8)
             x = encode_fn(u)
-            y = (1.0 - 2.0 * x.float()) + (sigma2 ** 0.5) * torch.randn((batch, N), device=device, generator=gen)
-            hard, iters = decode_fn((2.0 / sigma2) * y, max_itcount)
-            biterr = (hard.to(torch.uint8) != x).sum(dim=1).to(torch.int32)          # over all N code bits (:99)
+            if fused:       # one codeword per frame; noise keyed by (seed of the round, global frame index)
+                biterr, iters = mycode.mc_decode(x, batch, sigma2, seed=chunk_seed(seed, datapoint, rnd),
+                                                 frame0=rank * batch, max_itcount=max_itcount)
+            else:
+                y = (1.0 - 2.0 * x.float()) + (sigma2 ** 0.5) * torch.randn((batch, N), device=device, generator=gen)
+                hard, iters = decode_fn((2.0 / sigma2) * y, max_itcount)
+                biterr = (hard.to(torch.uint8) != x).sum(dim=1).to(torch.int32)      # over all N code bits (:99)
             stats = torch.stack([biterr, iters.to(torch.int32)])                      # [2, batch]
             if world > 1:
                 parts = [torch.empty_like(stats) for _ in range(world)]

@@ -144,9 +144,41 @@ def test_batch_vs_oracle_c2(snr_db):
     assert np.array_equal((app32 < 0)[sel], (app_ref < 0)[sel])
     assert_llr_close(app32[sel], app_ref[sel], RTOL32)
     # frame / bit error counts of the whole batch are identical
-    fe_ref = ((app_ref < 0) != x.astype(bool)).any(1).sum()
-    fe_32 = ((app32 < 0) != x.astype(bool)).any(1).sum()
-    assert fe_ref == fe_32
+    fe_ref = ((app_ref < 0) != x.astype(bool)).any(1)
+    fe_32 = ((app32 < 0) != x.astype(bool)).any(1)
+    assert fe_ref.sum() == fe_32.sum()
+    # ... and so is the error STATUS of every frame, converged or not, and "did not converge" itself
+    assert np.array_equal(fe_ref, fe_32)
+    assert np.array_equal(it32 == 50, it_ref == 50)
+
+
+def test_bench_scale_fp32_against_fp64_kernel():
+    """The bench workload's batch shape (Es/N0 1.2 dB, <= 50 its), 16 384 frames: the fp32 throughput kernel against
+    the fp64 kernel (= the reference's arithmetic, pinned above against c_ldpc.c).  Frame-error status and
+    non-convergence identical on every frame, hard decisions identical on every frame the reference converges on,
+    iteration counts identical on >= 99.9 % of the frames."""
+    import torch
+    c = ldpc.code("802.11n", "1/2", 81)
+    rng = np.random.RandomState(77)
+    x = c.encode(rng.randint(0, 2, (256, c.K)))
+    F, s2 = 16384, 10 ** (-1.2 / 10)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sgn = torch.from_numpy(1.0 - 2.0 * x).float().cuda()
+    which = torch.arange(F, device="cuda") % 256
+    llr = (2 / s2) * (sgn[which] + (s2 ** 0.5) * torch.randn((F, c.N), device="cuda", generator=gen))
+    truth = sgn[which] < 0
+    app32, it32 = c.decode(llr, 50, precision="fp32")
+    app64, it64 = c.decode(llr.double(), 50, precision="fp64")
+    h32, h64 = app32 < 0, app64 < 0
+    e32, e64 = (h32 != truth).any(1), (h64 != truth).any(1)
+    assert torch.equal(e32, e64), "frame-error status differs on %d frames" % int((e32 != e64).sum())
+    assert int(e64.sum()) > 500                                   # the operating point has non-converging frames
+    assert torch.equal(it32 == 50, it64 == 50)
+    conv = it64 < 50
+    assert torch.equal(h32[conv], h64[conv])
+    assert float((it32 == it64).float().mean()) >= 0.999
+    rel = ((app32[conv].double() - app64[conv]).abs() / app64[conv].abs().clamp(min=1.0)).max()
+    assert float(rel) < 1e-3      # APP LLRs of converged frames (per-frame 1e-4 is asserted on the oracle batches above)
 
 
 def test_other_codes_vs_oracle():
@@ -325,3 +357,51 @@ def test_campaign_driver_matches_reference_semantics(tmp_path):
     assert abs(res[1][3] - (snr0 + 1.0)) < 1e-12                             # step sqrt(100/100) = 1 dB
     # third point (-0.83 dB) is still below threshold in the recorded campaign (results.txt:252: 100/100)
     assert res[2][5] >= 100 and res[2][4] <= 110
+
+
+def test_fused_monte_carlo_front_end():
+    """lsb_ldpc_mc_dev_f32: channel + LLR scaling generated inside the BP kernel (Philox keyed by the global frame
+    index), errors counted in its epilogue (reference loop ldpc_awgn.py:88-107).  Checked: (i) the noise is
+    N(0, sigma2) on the right codeword; (ii) decoding the LLRs it reports with the plain decoder gives the same
+    iteration counts and bit errors, and the C oracle agrees on converged frames; (iii) results depend on the global
+    frame index only -- any split of the batch, any frame0 -- and the counters equal the per-frame sums."""
+    import torch
+    c = ldpc.code("802.11n", "1/2", 81)
+    rng = np.random.RandomState(4)
+    x = c.encode(rng.randint(0, 2, (8, c.K))).astype(np.uint8)
+    cw = torch.from_numpy(x).cuda()
+    F, sigma2, seed = 512, 10 ** (-1.6 / 10), 1234567
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    be, it, llr = c.mc_decode(cw, F, sigma2, seed=seed, max_itcount=50, counters=counters, want_llr=True)
+    be_h, it_h, llr_h = be.cpu().numpy(), it.cpu().numpy(), llr.cpu().numpy().astype(np.float64)
+    # (i) channel statistics
+    noise = llr_h * sigma2 / 2 - (1.0 - 2.0 * x[np.arange(F) % 8])
+    assert abs(noise.mean()) < 4 * np.sqrt(sigma2 / noise.size)
+    assert abs(noise.var() / sigma2 - 1) < 0.01
+    z = noise / np.sqrt(sigma2)
+    assert abs((z ** 4).mean() - 3) < 0.05 and abs((z ** 3).mean()) < 0.02 and np.abs(z).max() < 6.7
+    assert abs(np.corrcoef(z[0], z[1])[0, 1]) < 0.1 and not np.array_equal(z[0], z[8])
+    # (ii) same decode as the plain entry on those LLRs; oracle on converged frames
+    hard, it2 = c.decode_hard(llr, 50)
+    assert np.array_equal(it2.cpu().numpy(), it_h)
+    assert np.array_equal((hard.cpu().numpy() != x[np.arange(F) % 8]).sum(1), be_h)
+    g = orc.Graph(c.vdeg, c.cdeg, c.intrlv)
+    app_ref, it_ref = orc.decode_batch(g, llr_h[:48], 50)
+    conv = it_ref < 50
+    assert conv.sum() > 30 and np.array_equal(it_h[:48][conv], it_ref[conv])
+    assert np.array_equal(((app_ref < 0) != x[np.arange(48) % 8]).sum(1)[conv], be_h[:48][conv])
+    # (iii) global-index keyed, split-independent; counters = sums
+    assert counters.tolist() == [int(be_h.sum()), int((be_h > 0).sum()), F, int(it_h.sum())]
+    be_a, it_a = c.mc_decode(cw, 200, sigma2, seed=seed, max_itcount=50)
+    be_b, it_b = c.mc_decode(cw, F - 200, sigma2, seed=seed, frame0=200, max_itcount=50)
+    assert np.array_equal(np.concatenate([be_a.cpu().numpy(), be_b.cpu().numpy()]), be_h)
+    assert np.array_equal(np.concatenate([it_a.cpu().numpy(), it_b.cpu().numpy()]), it_h)
+    be_c, _ = c.mc_decode(cw, 64, sigma2, seed=seed + 1, max_itcount=50)
+    assert not np.array_equal(be_c.cpu().numpy(), be_h[:64]) or be_h[:64].sum() == 0
+    # the sweep driver on the fused path: totals do not depend on the chunking
+    from ldpc_sparc_b200 import montecarlo
+    r1 = montecarlo.ldpc_awgn_sweep(c, [1.4], 3000, max_itcount=50, seed=9, chunk=3000)
+    r2 = montecarlo.ldpc_awgn_sweep(c, [1.4], 3000, max_itcount=50, seed=9, chunk=512)
+    for k in montecarlo.COUNTER_FIELDS:
+        assert np.array_equal(r1[k], r2[k]), k
+    assert r1["frames"][0] == 3000 and 0 < r1["frame_errors"][0] < 1500
