@@ -96,8 +96,15 @@ BATCH_FIELDS = ("bit_errors", "frame_errors", "section_errors", "frames", "itera
 
 
 def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1, 2), seed=0, chunk=2048,
-                    precision="fp32", device=None):
-    """``n_frames`` independent frames over one design drawn from ``rand_seed``.
+                    precision="fp32", device=None, n_designs=1):
+    """``n_frames`` independent frames over a pool of ``n_designs`` designs.
+
+    The reference draws a NEW design for every trial (sparc_sim.py:15-24 calls sparc_encode with the trial's
+    ``rand_seed``, sparc.py:48,752), so its error rates average over the design ensemble as well as over messages
+    and noise.  Here design ``d`` is drawn from ``rand_seed + d`` (element-wise) and block ``c`` of ``chunk`` frames
+    runs on design ``c mod n_designs``: ``n_designs = 1`` is the fixed-design experiment (one design for all frames,
+    the throughput configuration), larger pools approach the reference's ensemble average at the cost of
+    ``n_designs`` sets of index tables (568 KB each at BASELINE config 1) and one kernel launch per block.
 
     Every rank handles its share of the ``chunk``-frame blocks (montecarlo.shard_chunks);
     the message and noise streams of a block are seeded by (seed, block index), so the totals
@@ -120,7 +127,14 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
     if W.ndim == 2:
         n = int(round(n / W.shape[0])) * W.shape[0]
     code_params.update({'n': n, 'R_actual': bit_len / n})
-    Ab, Az = sparc.sparc_transforms(W, L, M, n, list(rand_seed), code_params['complex'])
+    assert n_designs >= 1
+    design_seeds = [[int(v) + d for v in rand_seed] for d in range(n_designs)]
+    designs = {}
+
+    def design(d):                       # built on first use: a rank only uploads the designs of its own blocks
+        if d not in designs:
+            designs[d] = sparc.sparc_transforms(W, L, M, n, design_seeds[d], code_params['complex'])
+        return designs[d]
 
     rank, world = montecarlo._rank_world()
     if device is None:
@@ -138,6 +152,8 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
 
     for c in montecarlo.shard_chunks(len(ranges), rank, world):
         _, nf = ranges[c]
+        Ab, Az = design(c % n_designs)
+        rand_seed = design_seeds[c % n_designs]
         gen = torch.Generator(device=device).manual_seed(montecarlo.chunk_seed(seed, 0, c))
         idx0 = torch.randint(0, K * M, (nf, L), device=device, generator=gen, dtype=torch.int32)   # location + M * k
         beta0 = torch.zeros((nf, L * M), dtype=dt, device=device)
@@ -165,6 +181,6 @@ def sparc_sim_batch(code_params, decode_params, awgn_var, n_frames, rand_seed=(1
     frames = max(cnt["frames"], 1)
     out = {'ber': cnt["bit_errors"] / (frames * bit_len), 'cer': cnt["frame_errors"] / frames,
            'ser': cnt["section_errors"] / (frames * L), 't_final': cnt["iterations"] / frames,
-           'detect': cnt["detected"] / frames, 'n': n, 'R_actual': bit_len / n}
+           'detect': cnt["detected"] / frames, 'n': n, 'R_actual': bit_len / n, 'n_designs': n_designs}
     out.update(cnt)
     return out

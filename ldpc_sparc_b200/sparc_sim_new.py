@@ -52,10 +52,10 @@ def sparc_ldpc_integrated_sim(sparc_params, ldpc_params, lengths, ldpc_bool, dec
 _sweep_engines = {}     # (L, M, n, design_seed, precision) -> device-resident design (generation takes seconds)
 
 
-def _sweep_engine(L, M, n, design_seed, precision):
+def _sweep_engine(L, M, n, design_seed, precision, keep=2):
     key = (L, M, n, design_seed, precision)
     if key not in _sweep_engines:
-        if len(_sweep_engines) >= 2:
+        if len(_sweep_engines) >= max(2, keep):
             _sweep_engines.clear()
         _sweep_engines[key] = _engine(create_design_matrix(L, M, n, design_seed), precision)
     return _sweep_engines[key]
@@ -88,9 +88,14 @@ def _frames(eng, c, sparc_params, lengths, ldpc_bool, nf, gen):
 
 def performance_sweep(sparc_params, sparc_ldpc_params, ldpc_params, lengths, decode_params, snr_store,
                       frames_per_point, sims=SIMS, seed=0, design_seed=0, chunk=1024, precision="tc", save_path=None,
-                      decode_params_integrated=None):
+                      decode_params_integrated=None, n_designs=1):
     """BER of the four schemes of performance_plots_general.py:101-118 at every SNR of
     ``snr_store`` (linear, ``awgn_var = P / snr``), ``frames_per_point`` frames each.
+
+    The reference draws a new design matrix for every run (sparc_new.py:48,1290 seeded per run by
+    performance_plots_general.py:101-118), i.e. its BER curves average over the design ensemble.  ``n_designs`` > 1
+    keeps a pool of that many device-resident designs (seeds ``design_seed + d``; 4 bf16 copies of A each, 3.3 GB at
+    BASELINE config 5) and runs chunk ``c`` on design ``c mod n_designs``; 1 (default) is the fixed-design experiment.
 
     Returns a dict with ``snr_store``, ``ber_store_averages [len(sims), n_snr]``,
     ``ber_store_max`` / ``ber_store_min`` (extreme per-frame BERs, the reference's error
@@ -115,13 +120,17 @@ def performance_sweep(sparc_params, sparc_ldpc_params, ldpc_params, lengths, dec
                                lambda y, A: integrated_decoder(y, sparc_ldpc_params, ldpc_params,
                                                                decode_params_integrated, A, precision)),
     }
-    engines = {}
+    assert n_designs >= 1
+    shapes = {}
     for ldpc_bool, sp in ((False, sparc_params), (True, sparc_ldpc_params)):
         if any(runs[s][1] == ldpc_bool for s in sims):
             L, M = sp['L'], sp['M']
-            n = int(L * int(np.log2(M)) / sp['R'])
-            engines[ldpc_bool] = _sweep_engine(L, M, n, design_seed, precision)
-    dev = next(iter(engines.values())).dev
+            shapes[ldpc_bool] = (L, M, int(L * int(np.log2(M)) / sp['R']))
+
+    def engine_of(ldpc_bool, ci):
+        return _sweep_engine(*shapes[ldpc_bool], design_seed + ci % n_designs, precision, keep=len(shapes) * n_designs)
+
+    dev = engine_of(next(iter(shapes)), 0).dev
     ranges = montecarlo.chunk_ranges(frames_per_point, chunk)
     mine = montecarlo.shard_chunks(len(ranges), rank, world)
     n_s, n_v = len(sims), len(snr_store)
@@ -134,7 +143,7 @@ def performance_sweep(sparc_params, sparc_ldpc_params, ldpc_params, lengths, dec
             made = {}
             for si, name in enumerate(sims):
                 sp, ldpc_bool, dec = runs[name]
-                eng = engines[ldpc_bool]
+                eng = engine_of(ldpc_bool, ci)
                 if ldpc_bool not in made:                                          # schemes on one design see the same frames
                     gen = torch.Generator(device=dev).manual_seed(montecarlo.chunk_seed(seed, v, ci))
                     user, x = _frames(eng, c, sp, lengths, ldpc_bool, nf, gen)

@@ -63,6 +63,38 @@ def test_sparc_sim_batch_counts_and_determinism():
     assert abs(lo32['ser'] - lo64['ser']) <= 0.02 * lo64['ser'] + 1e-4
 
 
+def test_design_ensemble_pool():
+    """n_designs: the reference draws a new design per trial (sparc_sim.py:15-24, performance_plots_general.py:101-118);
+    a pool of D designs per batch averages over designs as well.  D = 1 reproduces the fixed-design counters; with D > 1
+    every block of frames runs on its own design (first block = the fixed design's first block) and the totals stay
+    deterministic; a block decoded on design d equals a single-design run on rand_seed + d."""
+    from ldpc_sparc_b200 import sparc_sim, sparc_sim_new
+    cp = dict(P=15.0, R=1.3, L=256, M=32)
+    dp = dict(t_max=25)
+    fixed = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 768, rand_seed=(1, 2), seed=3, chunk=256)
+    d1 = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 768, rand_seed=(1, 2), seed=3, chunk=256, n_designs=1)
+    assert {k: v for k, v in d1.items() if k != 'n_designs'} == {k: v for k, v in fixed.items() if k != 'n_designs'}
+    d3 = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 768, rand_seed=(1, 2), seed=3, chunk=256, n_designs=3)
+    assert d3 == sparc_sim.sparc_sim_batch(cp, dp, 2.0, 768, rand_seed=(1, 2), seed=3, chunk=256, n_designs=3)
+    assert d3['frames'] == 768 and d3['n_designs'] == 3
+    assert d3['section_errors'] != fixed['section_errors'] and abs(d3['ser'] - fixed['ser']) < 0.5 * fixed['ser'] + 1e-3
+    # block 1 of the pool run is block 1 of a fixed-design run on the second design: same messages, noise and design
+    only_b = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 512, rand_seed=(2, 3), seed=3, chunk=256)        # blocks 0, 1 on design 1
+    two = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 512, rand_seed=(1, 2), seed=3, chunk=256, n_designs=2)  # block 1 on design 1
+    first = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 256, rand_seed=(1, 2), seed=3, chunk=256)          # block 0 on design 0
+    first_b = sparc_sim.sparc_sim_batch(cp, dp, 2.0, 256, rand_seed=(2, 3), seed=3, chunk=256)        # block 0 on design 1
+    assert two['section_errors'] == first['section_errors'] + (only_b['section_errors'] - first_b['section_errors'])
+    # dense-design sweep: pool of 2 designs, deterministic, D = 1 equals the default
+    sp, spl, lp, lengths = _config5_small()
+    kw = dict(sims=('SPARC+LDPC',), chunk=16, seed=5, precision="tc")
+    a = sparc_sim_new.performance_sweep(sp, spl, lp, lengths, {'t_max': 25}, [2.0], 32, **kw)
+    b = sparc_sim_new.performance_sweep(sp, spl, lp, lengths, {'t_max': 25}, [2.0], 32, n_designs=1, **kw)
+    assert np.array_equal(a['bit_errors'], b['bit_errors'])
+    c2 = sparc_sim_new.performance_sweep(sp, spl, lp, lengths, {'t_max': 25}, [2.0], 32, n_designs=2, **kw)
+    c3 = sparc_sim_new.performance_sweep(sp, spl, lp, lengths, {'t_max': 25}, [2.0], 32, n_designs=2, **kw)
+    assert np.array_equal(c2['bit_errors'], c3['bit_errors']) and np.all(c2['bits'] == a['bits'])
+
+
 def _config5_small():
     from ldpc_sparc_b200.param_calc import param_calc
     mults, logM, standard, rate, int_rate, z = 1, 1, '802.16', '1/2', 1 / 2, 150

@@ -233,6 +233,35 @@ def test_config5_small_variant_vs_oracle():
                                   sph.naively_integrated_decoder(y, sp, oc, dp, A))
 
 
+def test_config5_full_size_vs_oracle():
+    """BASELINE config 5 at FULL size (performance_plots_general.py:21-47): 802.16 r1/2 z=150, mults=4, M=2, R=1 ->
+    L = n = 14 400, A = 14 400 x 28 800 (3.3 GB in fp64), P = 19.44, t_max = 25, four LDPC blocks per frame.  The
+    tensor-core mode -- the one the bench times -- against the numpy oracle on the same A and y: identical user bits
+    for the separate and the integrated decoder, tau^2 trace of the plain AMP within 1e-4."""
+    c = ldpc.code("802.16", "1/2", 150)
+    oc = sph.Code(c)
+    mults, L, M, n = 4, 14400, 2, 14400
+    sp = dict(P=19.44, R=1.0, L=L, M=M)
+    lp = dict(standard="802.16", rate="1/2", z=150)
+    lengths = dict(k_ldpc=c.K * mults, mults=mults, L_unprotected=0)
+    dp = dict(t_max=25)
+    ub, tb, beta0, x, A = sph.encode(sp, oc, mults, 21, c.encode)
+    assert A.shape == (n, L * M) and ub.size == 4 * c.K
+    rng = np.random.RandomState(21)
+    y = x + np.sqrt(sp["P"] / 6.0) * rng.randn(n)
+    trace = []
+    ref_beta, ref_s = sph.sparc_amp(y, sp, dp, A, trace)
+    beta, s_, tau = sparc_new.sparc_amp(y, sp, dp, A, precision="tc", return_trace=True)
+    ref_tau = np.array([t["tau_sqr"] for t in trace])
+    assert np.max(np.abs(tau - ref_tau) / ref_tau) < 1e-4
+    assert np.array_equal(s_.reshape(L, M).argmax(1), ref_s.reshape(L, M).argmax(1))
+    ref_sep = sph.sparc_ldpc_decode(y, sp, oc, dp, True, lengths, A)
+    ref_int = sph.integrated_decoder(y, sp, oc, dp, A)
+    assert np.array_equal(sparc_new.sparc_ldpc_decode(y, sp, lp, dp, True, lengths, A, precision="tc"), ref_sep)
+    assert np.array_equal(sparc_new.integrated_decoder(y, sp, lp, dp, A, precision="tc"), ref_int)
+    assert np.array_equal(ref_int, ub)                              # SNR 6: the top of the reference's sweep decodes cleanly
+
+
 def test_config3_full_size_tensor_core_amp_vs_oracle():
     """BASELINE config 3 at full size (L = 512, M = 64, n = 3072: A 3072 x 32768, P = 19.44,
     t_max = 25): the tcgen05 AMP path against the numpy oracle on the same A and y --

@@ -301,6 +301,38 @@ def test_config4_sc_wave_matches_reference_golden(gold):
             assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < 1e-4
 
 
+def test_config4_fp32_against_fp64_on_a_batch(gold):
+    """Config 4, four fresh frames (messages and noise) on the reference design: the fp32 throughput kernel against
+    the fp64 kernel, which the test above pins to the reference's golden run -- identical section decisions on every
+    frame, tau trace within 1e-4 over the iterations both ran, t_final within the fp32 stop rule's slack."""
+    g, meta = gold
+    m = meta["c4_sc_wave"]
+    cp, dp = dict(m["code_params"]), dict(m["decode_params"])
+    seed = m["seeds"][0]
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, m["awgn_var"], seed)
+    sparc.check_decode_params(dp)
+    L, M, n = cp["L"], cp["M"], cp["n"]
+    rng = np.random.RandomState(42)
+    F = 4
+    idx0 = rng.randint(0, M, (F, L))
+    b0 = np.zeros((F, L * M))
+    b0[np.arange(F)[:, None], np.arange(L)[None, :] * M + idx0] = 1
+    y = Ab(b0) + np.sqrt(m["awgn_var"]) * rng.randn(F, n)
+    out = {}
+    for prec in ("fp64", "fp32"):
+        out[prec] = sparc.sparc_amp(y, cp, dp, m["awgn_var"], seed, idx0, Ab, Az, precision=prec, return_trace=True)
+    idx64, T64, _, _, ex64 = out["fp64"]
+    idx32, T32, _, _, ex32 = out["fp32"]
+    idx64, idx32, T64, T32 = (np.asarray(v.cpu() if hasattr(v, "cpu") else v) for v in (idx64, idx32, T64, T32))
+    assert np.array_equal(idx64, idx32)
+    assert (idx64 != idx0).mean() < 5e-3
+    tau64, tau32 = (np.asarray(e["tau"].cpu() if hasattr(e["tau"], "cpu") else e["tau"]) for e in (ex64, ex32))
+    for f in range(F):
+        assert T64[f] - 1 <= T32[f] <= dp["t_max"] - 1
+        Tc = int(min(T64[f], T32[f]))
+        assert rel_err(tau32[f, :Tc], tau64[f, :Tc]) < 1e-4
+
+
 # ---------------------------------------------------------------- real 2-PSK modulation
 @pytest.fixture(scope="module")
 def gold_mod():
