@@ -19,360 +19,12 @@
 //   warps 4..7       : epilogue      - tcgen05.ld 32x32b.x32, transposed store C[f, r]
 //                      (lanes = consecutive r: coalesced); drains accumulator j & 1 while
 //                      the MMAs of the CTA's next item fill the other one
-#include "common.cuh"
-
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "tc_gemm.cuh"
 
 #include <map>
 #include <mutex>
 #include <new>
 
-namespace {
-
-constexpr int kStages = 3;
-constexpr int kTileRows = 128;   // UMMA M: rows of W per tile
-constexpr int kTileN = 128;      // UMMA N: frames per tile
-constexpr int kBlockK = 64;      // bf16 elements per 128-byte swizzle row
-constexpr int kTileBytes = 128 * 128;                 // one operand tile: 128 rows x 128 B
-constexpr int kStageBytes = 4 * kTileBytes;           // W_hi, W_lo, X_hi, X_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024;   // + slack for 1024 B alignment
-constexpr int kThreadsTc = 256;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Persistent: CTA b works on items b, b + gridDim.x, ...; an item is one 128 x 128 output
-// tile restricted to one of `splits` contiguous K ranges (partial s goes to C + s * split_stride;
-// the caller sums the partials in a fixed order, so results do not depend on scheduling).
-// Two TMEM accumulators: the epilogue of item j overlaps the MMAs of item j + 1.
-__global__ void __launch_bounds__(kThreadsTc, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
-               const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
-               float *__restrict__ C, int rows_total, int F, int K, int n_row_tiles, int n_f_tiles, int splits,
-               long long split_stride)
-{
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full_bar[2], acc_empty_bar[2];
-    __shared__ uint32_t tmem_base_slot;
-
-    uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb = (K + kBlockK - 1) / kBlockK;
-    const int n_tiles = n_row_tiles * n_f_tiles;
-    const int n_items = n_tiles * splits;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX_lo) : "memory");
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&acc_full_bar[a], 1);
-            mbar_init(&acc_empty_bar[a], 4);     // one arrival per epilogue warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                     "n"(2 * kTileN)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_slot;
-
-    // item -> (W row tile, frame tile, K range).  Frame tiles vary fastest: the CTAs running
-    // at the same time share a few W panels (one DRAM read each, the rest L2 hits) and the
-    // frame operand stays L2-resident.  With W row tiles fastest, A^T z (W = 403 MB of bf16
-    // hi/lo, 8 frame tiles) re-read W from DRAM once per frame tile: 578 us vs 467 us.
-#define LSB_TC_DECODE_ITEM(item)                                               \
-    const int split = (item) / n_tiles, tile = (item) - split * n_tiles;      \
-    const int row0 = (tile / n_f_tiles) * kTileRows;                           \
-    const int f0 = (tile % n_f_tiles) * kTileN;                                \
-    const int kb0 = (int)(((long long)split * num_kb) / splits);               \
-    const int kb1 = (int)(((long long)(split + 1) * num_kb) / splits);
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                LSB_TC_DECODE_ITEM(item)
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t phase = (it / kStages) & 1;
-                    mbar_wait(&empty_bar[s], phase ^ 1);
-                    uint8_t *st = tiles + s * kStageBytes;
-                    mbar_expect_tx(&full_bar[s], kStageBytes);
-                    tma_load_2d(st, &mapW_hi, &full_bar[s], kb * kBlockK, row0);
-                    tma_load_2d(st + kTileBytes, &mapW_lo, &full_bar[s], kb * kBlockK, row0);
-                    tma_load_2d(st + 2 * kTileBytes, &mapX_hi, &full_bar[s], kb * kBlockK, f0);
-                    tma_load_2d(st + 3 * kTileBytes, &mapX_lo, &full_bar[s], kb * kBlockK, f0);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
-                                   ((uint32_t)(kTileRows >> 4) << 24);
-            uint32_t it = 0, j = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
-                LSB_TC_DECODE_ITEM(item)
-                (void)row0;
-                (void)f0;
-                const uint32_t a = j & 1;
-                mbar_wait(&acc_empty_bar[a], ((j >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tmem_d = tmem_base + a * kTileN;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t phase = (it / kStages) & 1;
-                    mbar_wait(&full_bar[s], phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t base = smem_u32(tiles + s * kStageBytes);
-                    const uint64_t dW_hi = umma_desc(base), dW_lo = umma_desc(base + kTileBytes);
-                    const uint64_t dX_hi = umma_desc(base + 2 * kTileBytes), dX_lo = umma_desc(base + 3 * kTileBytes);
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per K step inside the swizzle row
-                        umma_bf16(tmem_d, dW_hi + adv, dX_hi + adv, idesc, (kb != kb0) || (k != 0));
-                        umma_bf16(tmem_d, dW_lo + adv, dX_hi + adv, idesc, 1);
-                        umma_bf16(tmem_d, dW_hi + adv, dX_lo + adv, idesc, 1);
-                    }
-                    umma_commit(&empty_bar[s]);      // stage reusable once these MMAs have read it
-                }
-                umma_commit(&acc_full_bar[a]);       // accumulator complete
-            }
-        }
-    } else if (warp >= 4) {
-        const int q = warp & 3;                   // TMEM lane quarter this warp may read
-        uint32_t j = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
-            LSB_TC_DECODE_ITEM(item)
-            (void)kb0;
-            (void)kb1;
-            const uint32_t a = j & 1;
-            float *Cs = C + (size_t)split * (size_t)split_stride;
-            mbar_wait(&acc_full_bar[a], (j >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int r = row0 + q * 32 + lane;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kTileN; c0 += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + a * kTileN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (r < rows_total) {
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int f = f0 + c0 + jj;
-                        if (f < F) Cs[(size_t)f * rows_total + r] = __uint_as_float(v[jj]);
-                    }
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty_bar[a]);
-        }
-    }
-#undef LSB_TC_DECODE_ITEM
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTileN) : "memory");
-    }
-}
-
-// out = sum of `splits` partial products, added in index order (fixed result)
-__global__ void reduce_splits_kernel(const float4 *__restrict__ part, float4 *__restrict__ out, long long n4, int splits)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (; i < n4; i += step) {
-        float4 a = part[i];
-        for (int s = 1; s < splits; ++s) {
-            const float4 b = part[(long long)s * n4 + i];
-            a.x += b.x;
-            a.y += b.y;
-            a.z += b.z;
-            a.w += b.w;
-        }
-        out[i] = a;
-    }
-}
-
-// x (fp32 or fp64) -> hi = bf16(x), lo = bf16(x - hi)
-template <typename T>
-__global__ void split_kernel(const T *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
-                             long long n)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += step) {
-        const float v = (float)x[i];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hi[i] = h;
-        lo[i] = __float2bfloat16_rn((float)((double)x[i] - (double)__bfloat162float(h)));
-    }
-}
-
-// fp32 frame operand, 8 elements per thread: two 16-byte loads, one 16-byte store per output
-// (the scalar kernel's 2-byte stores held it at 4.1 TB/s).  x - hi is exact in fp32 (hi is x rounded to
-// 8 mantissa bits), so the residual needs no fp64.
-__global__ void split8_kernel(const float4 *__restrict__ x, uint4 *__restrict__ hi, uint4 *__restrict__ lo, long long n8)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (; i < n8; i += step) {
-        const float4 a = x[2 * i], b = x[2 * i + 1];
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * k] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * k + 1] - __bfloat162float(h1));
-            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
-        lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
-    }
-}
-
-// out[c, r] = in[r, c]  (tiled through shared memory), in is [rows, cols]
-__global__ void transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int rows, int cols)
-{
-    __shared__ double tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int r = r0 + j, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
-    }
-    __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int c = c0 + j, r = r0 + threadIdx.x;
-        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
-    }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    });
-    return fn;
-}
-
-// 2-D bf16 tensor [rows, K] (K contiguous), box = 64 x 128, 128-byte swizzle, zero fill out of bounds
-int make_map(CUtensorMap *map, const void *ptr, uint64_t rows, uint64_t K)
-{
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) {
-        lsb::set_error("cuTensorMapEncodeTiled entry point not available");
-        return LSB_ERR_CUDA;
-    }
-    const cuuint64_t dims[2] = {K, rows};
-    const cuuint64_t strides[1] = {K * sizeof(__nv_bfloat16)};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, 128};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        lsb::set_error("cuTensorMapEncodeTiled failed (%d) for [%llu x %llu]", (int)r, (unsigned long long)rows,
-                       (unsigned long long)K);
-        return LSB_ERR_CUDA;
-    }
-    return LSB_OK;
-}
-
-}  // namespace
 
 // One operand W [rows, K] kept as bf16 hi/lo + its TMA maps
 struct TcOperand {
