@@ -37,6 +37,10 @@
 #ifndef LSB_BP_CHEAP_SYNDROME
 #define LSB_BP_CHEAP_SYNDROME 1
 #endif
+// 1: the fp32 sumprod2 check node runs in the exp domain (check_node_edomain); 0: Lxor form (min + 2 log terms)
+#ifndef LSB_BP_EDOMAIN
+#define LSB_BP_EDOMAIN 1
+#endif
 // resident CTAs per SM the fp32 degree<=8 kernel's register budget is tuned for
 #ifndef LSB_BP_OCC8
 #define LSB_BP_OCC8 5
@@ -123,6 +127,83 @@ __device__ __forceinline__ T lxor(T a, T b)
     return out;
 }
 
+// fp32 sumprod2 check node in the EXP DOMAIN (LSB_BP_EDOMAIN).  With E = 2^-|L| (log2-domain LLRs) the
+// exact box-plus c_ldpc.c:234-251 evaluates -- sign(a)sign(b)min(|a|,|b|) + log(1+e^-|a+b|) - log(1+e^-|a-b|)
+// = 2 atanh(tanh(a/2) tanh(b/2)) -- becomes
+//     E(a [+] b) = (Ea + Eb) / (1 + Ea Eb),       sign(a [+] b) = sign(a) sign(b),
+// a ratio of two polynomials with positive coefficients: no cancellation anywhere.  The trellis of Lxfb
+// (same association order: f[k] = f[k-1] [+] L[k], b[k] = b[k+1] [+] L[k], out[k] = f[k-1] [+] b[k+1])
+// is run on fractions N/D that are never divided out:
+//     (Na/Da) [+] (Nb/Db) = (Na Db + Nb Da) / (Da Db + Na Nb),      (N/D) [+] E = (N + E D) / (D + E N),
+// and an extrinsic magnitude is lg2(D) - lg2(N).  Per check: dc EX2 + 2 dc LG2 = 3 dc MUFU and 8 (dc - 2) FMA-pipe
+// operations, against 4 (3 dc - 6) MUFU and ~13 (3 dc - 6) other instructions of the Lxor form above (dc = 7:
+// 21 + 40 against 60 + 195).
+// Range.  2^-|L| underflows at |L| = 126 (87 in natural units) while slowly converging frames reach LLRs of
+// several hundred, so the node works on |L| - s, s = max(min|L| - 32, 0), and adds s back to its outputs: once
+// every input exceeds 32 the E^2 terms are below 2^-64 and box-plus commutes with the shift to fp32 accuracy.
+// Inputs more than ~120 above the shifted minimum flush to E = 0, which is exact as long as every output still
+// sees one input in range; the one case that is not -- a single weak input among inputs that are all > 120
+// larger -- shows up as a numerator below 2^-120 and is reported to the caller (NaN, nothing stored), who runs
+// the Lxor form on that check.  D stays below 2^dc.
+// The stop rule needs the sign of the XOR of all inputs and whether any input is exactly zero (then the
+// reference's b[0] is 0 and "aggr <= 0" holds): the returned value carries that sign and min |L|.
+constexpr float kEdomainKeep = 32.0f;
+constexpr float kEdomainTiny = 7.5231638e-37f;      // 2^-120
+
+template <int DC>
+__device__ __forceinline__ float check_node_edomain(float (&L)[DC])
+{
+    unsigned par = __float_as_uint(L[0]);
+    float mn = fabsf(L[0]);
+#pragma unroll
+    for (int i = 1; i + 1 < DC; i += 2) {
+        par ^= __float_as_uint(L[i]) ^ __float_as_uint(L[i + 1]);
+        mn = fminf(fminf(mn, fabsf(L[i])), fabsf(L[i + 1]));          // FMNMX3
+    }
+    if ((DC & 1) == 0) {
+        par ^= __float_as_uint(L[DC - 1]);
+        mn = fminf(mn, fabsf(L[DC - 1]));
+    }
+    const float s = fmaxf(mn - kEdomainKeep, 0.0f);
+    float E[DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) E[i] = Num<float>::ex2(s - fabsf(L[i]));
+    float bN[DC], bD[DC];
+    bN[DC - 1] = E[DC - 1];
+    bD[DC - 1] = 1.0f;
+#pragma unroll
+    for (int i = DC - 2; i >= 1; --i) {
+        bN[i] = fmaf(E[i], bD[i + 1], bN[i + 1]);
+        bD[i] = fmaf(E[i], bN[i + 1], bD[i + 1]);
+    }
+    float oN[DC], oD[DC];
+    float fN = E[0], fD = 1.0f;
+    oN[0] = bN[DC > 1 ? 1 : 0];
+    oD[0] = bD[DC > 1 ? 1 : 0];
+#pragma unroll
+    for (int i = 1; i < DC - 1; ++i) {
+        oN[i] = fmaf(fN, bD[i + 1], bN[i + 1] * fD);
+        oD[i] = fmaf(fD, bD[i + 1], fN * bN[i + 1]);
+        const float n = fmaf(E[i], fD, fN);
+        fD = fmaf(E[i], fN, fD);
+        fN = n;
+    }
+    oN[DC - 1] = fN;
+    oD[DC - 1] = fD;
+    float lo = oN[0];
+#pragma unroll
+    for (int i = 1; i + 1 < DC; i += 2) lo = fminf(fminf(lo, oN[i]), oN[i + 1]);
+    if ((DC & 1) == 0) lo = fminf(lo, oN[DC - 1]);
+    if (!(lo >= kEdomainTiny)) return __int_as_float(0x7fffffff);     // out of range (or NaN input): caller takes the Lxor form
+#pragma unroll
+    for (int i = 0; i < DC; ++i) {
+        const float mag = (__log2f(oD[i]) - __log2f(oN[i])) + s;
+        // |mag| (rounding can leave -ulp when every other input is ~0) with the sign of the other inputs' product
+        L[i] = __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | ((par ^ __float_as_uint(L[i])) & 0x80000000u));
+    }
+    return __uint_as_float(__float_as_uint(mn) | (par & 0x80000000u));
+}
+
 // One check node with its dc messages in registers (c_ldpc.c:294-314).
 // Returns the LLR of the XOR of all inputs (b[0] in the reference).  Lxor is
 // symmetric in its arguments, so only the association order matters and that
@@ -145,6 +226,7 @@ __device__ __forceinline__ T check_node(T (&L)[DC], T scale)
     } else {
         constexpr bool CORR = (ALGO == LSB_BP_SUMPROD2);
         constexpr bool F32 = sizeof(T) == 4;
+        if constexpr (F32 && CORR && LSB_BP_EDOMAIN && DC >= 2) return check_node_edomain<DC>(L);
         T b[DC];
         b[DC - 1] = L[DC - 1];
 #pragma unroll
@@ -167,18 +249,6 @@ __device__ __forceinline__ T check_node(T (&L)[DC], T scale)
         }
         return b[0];
     }
-}
-
-template <typename T, int DC, int ALGO>
-__device__ __forceinline__ T check_node_strided(T *m, int stride, T scale)
-{
-    T L[DC];
-#pragma unroll
-    for (int i = 0; i < DC; ++i) L[i] = m[i * stride];
-    T syn = check_node<T, DC, ALGO>(L, scale);
-#pragma unroll
-    for (int i = 0; i < DC; ++i) m[i * stride] = L[i];
-    return syn;
 }
 
 // Any degree up to kMaxDc: same recursion with local-memory arrays (generic /
@@ -214,6 +284,23 @@ __device__ __noinline__ T check_node_dyn(T *m, int stride, int dc, T scale)
         syn = b[0];
     }
     for (int i = 0; i < dc; ++i) m[i * stride] = L[i];
+    return syn;
+}
+
+// Loads the dc messages of a check (stride apart), runs the trellis, stores the extrinsics.  fp32 sumprod2 in the
+// exp domain: a NaN return means "out of range, nothing stored" (see check_node_edomain).
+template <typename T, int DC, int ALGO>
+__device__ __forceinline__ T check_node_strided(T *m, int stride, T scale)
+{
+    T L[DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) L[i] = m[i * stride];
+    T syn = check_node<T, DC, ALGO>(L, scale);
+    if constexpr (sizeof(T) == 4 && ALGO == LSB_BP_SUMPROD2 && LSB_BP_EDOMAIN) {
+        if (syn != syn) return syn;
+    }
+#pragma unroll
+    for (int i = 0; i < DC; ++i) m[i * stride] = L[i];
     return syn;
 }
 
@@ -333,6 +420,11 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
     __shared__ QcTables tabs;
     __shared__ long long s_frame;
     __shared__ int s_err[kThreads / 32];
+    constexpr bool kEdomain = sizeof(T) == 4 && ALGO == LSB_BP_SUMPROD2 && LSB_BP_EDOMAIN;
+    constexpr int kExcCap = 128;                       // checks deferred to the Lxor form per iteration (overflow: inline)
+    __shared__ int s_exc_n;
+    __shared__ unsigned short s_exc[kExcCap];
+    if (threadIdx.x == 0) s_exc_n = 0;
     unsigned long long tot_bit = 0, tot_frame = 0, tot_n = 0, tot_it = 0;     // thread 0: this CTA's Monte-Carlo counters
 
     const int tid = threadIdx.x;
@@ -394,7 +486,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
             }
             __syncthreads();
             // ---- check nodes: lane = consecutive checks of a (degree-sorted) row
-            int unsatisfied = 0;
+            int unsatisfied = 0, deferred = 0;
             for (int p = tid; p < nc; p += kThreads) {
                 const int ri = (int)__umulhi((unsigned)p, magic);
                 const int k = p - ri * z;
@@ -402,9 +494,37 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
                 const int e0 = tabs.row_ptr[r];
                 const int dc = tabs.row_ptr[r + 1] - e0;
                 T syn = check_node_bucket<T, ALGO, MAXDC>(msg + e0 * z + k, z, dc, scale);
+                if (kEdomain && syn != syn) {
+                    // out of the exp-domain node's range (rare: see check_node_edomain): queue the check for the
+                    // Lxor form, run by consecutive threads after the pass instead of divergently inside it
+                    const int slot = atomicAdd(&s_exc_n, 1);
+                    if (slot < kExcCap) {
+                        s_exc[slot] = (unsigned short)p;
+                        deferred = 1;
+                        continue;
+                    }
+                    syn = check_node_dyn<T, ALGO>(msg + e0 * z + k, z, dc, scale);
+                }
                 unsatisfied |= (syn <= (T)0);
             }
-            if (!__syncthreads_or(unsatisfied)) break;
+            int any = __syncthreads_or(unsatisfied | deferred);
+            if (kEdomain) {
+                const int n_exc = min(s_exc_n, kExcCap);          // CTA-uniform: every push precedes the barrier
+                if (n_exc > 0) {
+                    for (int q = tid; q < n_exc; q += kThreads) {
+                        const int p = s_exc[q];
+                        const int ri = (int)__umulhi((unsigned)p, magic);
+                        const int k = p - ri * z;
+                        const int r = tabs.row_order[ri];
+                        const int e0 = tabs.row_ptr[r];
+                        const T syn = check_node_dyn<T, ALGO>(msg + e0 * z + k, z, tabs.row_ptr[r + 1] - e0, scale);
+                        unsatisfied |= (syn <= (T)0);
+                    }
+                    any = __syncthreads_or(unsatisfied);
+                    if (tid == 0) s_exc_n = 0;                      // next push: after the next VN-pass barrier
+                }
+            }
+            if (!any) break;
         }
 
         if (tid == 0 && iters) iters[f] = it;
