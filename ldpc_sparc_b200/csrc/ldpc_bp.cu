@@ -174,6 +174,7 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
         a.max_it = max_it;
         a.algo = algo;
         a.max_dc = g->max_dc;
+        a.z = g->z;
         a.scale = (T)scale;
         a.queue = queue;
         a.smem = qc_smem_bytes(g, sizeof(T));

@@ -44,7 +44,7 @@ struct QcLaunch {
     uint8_t *hard;
     int32_t *iters;
     long long n_frames;
-    int max_it, algo, max_dc;
+    int max_it, algo, max_dc, z;
     T scale;
     unsigned long long *queue;
     size_t smem;        // dynamic shared memory of one CTA

@@ -60,6 +60,14 @@ struct Num<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
         return y;
     }
+    // lg2.approx.ftz: __log2f carries a denormal-input rescue (FSETP + 2 predicated ops per call) that the exp-domain
+    // node does not need -- its arguments are >= 2^-120
+    static __device__ __forceinline__ float lg2(float x)
+    {
+        float y;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
     // fp32 sumprod2 messages are kept in the LOG2 DOMAIN: every LLR is scaled by
     // log2(e) when the frame is loaded (kIn) and by ln 2 when APP is stored (kOut).
     // The variable-node rule is linear and the stopping rule looks at signs only,
@@ -197,7 +205,7 @@ __device__ __forceinline__ float check_node_edomain(float (&L)[DC])
     if (!(lo >= kEdomainTiny)) return __int_as_float(0x7fffffff);     // out of range (or NaN input): caller takes the Lxor form
 #pragma unroll
     for (int i = 0; i < DC; ++i) {
-        const float mag = (__log2f(oD[i]) - __log2f(oN[i])) + s;
+        const float mag = (Num<float>::lg2(oD[i]) - Num<float>::lg2(oN[i])) + s;
         // |mag| (rounding can leave -ulp when every other input is ~0) with the sign of the other inputs' product
         L[i] = __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | ((par ^ __float_as_uint(L[i])) & 0x80000000u));
     }
@@ -326,33 +334,69 @@ __device__ __forceinline__ T check_node_bucket(T *m, int stride, int dc, T scale
 
 // One variable node of a QC column (c_ldpc.c:171-178): total = ch + sum of its
 // dv edge messages in port order (= increasing protograph row); every message is
-// replaced by total - message.  entry[t] = (edge*z - shift, shift): the message
-// of variable j on that edge sits at edge*z + (j - shift mod z).
-template <typename T, int DV>
-__device__ __forceinline__ T variable_node(T *msg, const int2 *entry, int j, int z, T total)
+// replaced by total - message.  The message of variable j on protograph entry
+// (edge, shift) sits at edge*z + (j - shift mod z).
+// entry[t] = (32-bit SHARED-WINDOW address of message edge*z - shift, shift); j_b = j * sizeof(T), z_b = z * sizeof(T):
+// the address of a message is three integer instructions (compare, select, 3-input add) -- no scaling, no base
+// pointer -- and the access is an explicit ld/st.shared on it.
+__device__ __forceinline__ float lds(unsigned a, float)
 {
-    int idx[DV];
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds(unsigned a, double)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// x + j_b, plus z_b when j < shift: compare, add, predicated add
+__device__ __forceinline__ unsigned wrap_addr(int x, int shift, int j, int j_b, int z_b)
+{
+    unsigned a;
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.lt.s32 p, %1, %2;\n\t"
+        "add.s32 %0, %3, %4;\n\t"
+        "@p add.s32 %0, %0, %5;\n\t"
+        "}"
+        : "=r"(a)
+        : "r"(j), "r"(shift), "r"(x), "r"(j_b), "r"(z_b));
+    return a;
+}
+
+template <typename T, int DV>
+__device__ __forceinline__ T variable_node(const int2 *entry, int j, int j_b, int z_b, T total)
+{
+    unsigned a[DV];
     T m[DV];
 #pragma unroll
     for (int i = 0; i < DV; ++i) {
         const int2 e = entry[i];
-        idx[i] = e.x + j + (j < e.y ? z : 0);
-        m[i] = msg[idx[i]];
+        a[i] = wrap_addr(e.x, e.y, j, j_b, z_b);
+        m[i] = lds(a[i], T());
     }
 #pragma unroll
     for (int i = 0; i < DV; ++i) total += m[i];
 #pragma unroll
-    for (int i = 0; i < DV; ++i) msg[idx[i]] = total - m[i];
+    for (int i = 0; i < DV; ++i) sts(a[i], total - m[i]);
     return total;
 }
 
 template <typename T>
-__device__ __forceinline__ T variable_node_any(T *msg, const int2 *entry, int dv, int j, int z, T total)
+__device__ __forceinline__ T variable_node_any(const int2 *entry, int dv, int j, int z, T total)
 {
+    int j_b = j * (int)sizeof(T);
+    asm volatile("" : "+r"(j_b));          // keep j_b in a register: folded back into j * 4 + x it costs an IMAD per edge
+    const int z_b = z * (int)sizeof(T);
     switch (dv) {
 #define LSB_CASE(D) \
     case D:         \
-        return variable_node<T, D>(msg, entry, j, z, total);
+        return variable_node<T, D>(entry, j, j_b, z_b, total);
         LSB_CASE(1) LSB_CASE(2) LSB_CASE(3) LSB_CASE(4) LSB_CASE(5) LSB_CASE(6) LSB_CASE(7) LSB_CASE(8)
         LSB_CASE(9) LSB_CASE(10) LSB_CASE(11) LSB_CASE(12)
 #undef LSB_CASE
@@ -362,12 +406,12 @@ __device__ __forceinline__ T variable_node_any(T *msg, const int2 *entry, int dv
     T sum = total;
     for (int t = 0; t < dv; ++t) {
         const int2 e = entry[t];
-        sum += msg[e.x + j + (j < e.y ? z : 0)];
+        sum += lds(wrap_addr(e.x, e.y, j, j_b, z_b), T());
     }
     for (int t = 0; t < dv; ++t) {
         const int2 e = entry[t];
-        const int idx = e.x + j + (j < e.y ? z : 0);
-        msg[idx] = sum - msg[idx];
+        const unsigned a = wrap_addr(e.x, e.y, j, j_b, z_b);
+        sts(a, sum - lds(a, T()));
     }
     return sum;
 }
@@ -414,8 +458,10 @@ template <typename T, int ALGO, int MAXDC>
 __global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T)>::value)
 bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *__restrict__ app,
              uint8_t *__restrict__ hard, int32_t *__restrict__ iters, long long n_frames,
-             int max_it, T scale, unsigned long long *__restrict__ queue, McParams mc)
+             int max_it, T scale, unsigned long long *__restrict__ queue, McParams mc, int z)
 {
+    // z arrives as a kernel parameter (not only in the tables) so that the compiler keeps it, and every multiple of it
+    // in the strided check-node addressing, in uniform registers
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ QcTables tabs;
     __shared__ long long s_frame;
@@ -431,8 +477,14 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
     for (int i = tid; i < (int)(sizeof(QcTables) / sizeof(int)); i += kThreads)
         reinterpret_cast<int *>(&tabs)[i] = reinterpret_cast<const int *>(g_tabs)[i];
     __syncthreads();
+    {   // column entries -> shared-window byte addresses of the messages (see variable_node)
+        const unsigned msg_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+        for (int i = tid; i < tabs.col_ptr[tabs.cols]; i += kThreads)
+            tabs.col_entry[i].x = (int)(msg_base + (unsigned)tabs.col_entry[i].x * (unsigned)sizeof(T));
+    }
+    __syncthreads();
 
-    const int z = tabs.z, nv = tabs.nv, nc = tabs.nc;
+    const int nv = tabs.nv, nc = tabs.nc;
     const int n_msg = tabs.n_edges * z;
     const unsigned magic = tabs.magic;
     T *msg = reinterpret_cast<T *>(smem_raw);   // [n_edges][z]
@@ -481,7 +533,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
                 const int c = (int)__umulhi((unsigned)v, magic);
                 const int j = v - c * z;
                 const int t0 = tabs.col_ptr[c];
-                const T total = variable_node_any<T>(msg, tabs.col_entry + t0, tabs.col_ptr[c + 1] - t0, j, z, ch[v]);
+                const T total = variable_node_any<T>(tabs.col_entry + t0, tabs.col_ptr[c + 1] - t0, j, z, ch[v]);
                 ap[v] = total;
             }
             __syncthreads();
@@ -640,7 +692,7 @@ int launch_qc_bucket(const QcLaunch<T> &a)
     long long grid = *a.cached_grid;
     if (grid > a.n_frames) grid = a.n_frames;
     kern<<<(unsigned)grid, kThreads, smem, a.stream>>>(a.tabs, a.llr, a.app, a.hard, a.iters, a.n_frames,
-                                                      a.max_it, a.scale, a.queue, a.mc);
+                                                      a.max_it, a.scale, a.queue, a.mc, a.z);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     return LSB_OK;
