@@ -37,6 +37,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 N_FRAMES = 65536
 MAX_IT = 50
 SNR_DB = 1.2
+# warp instructions bp_qc_kernel<float, sumprod2, 8> executes per frame-iteration on this workload: ncu
+# smsp__inst_executed.sum / frame-iterations of the profiled launch (profiles/r2_bp_edomain_v2_ncu_full.csv)
+WARP_INSTR_PER_FRAME_ITER = 10632.0      # 18 166 078 038 / 1 708 694
 BYTES_PER_FRAME_ITER = 71280          # (2*Nmsg + 2*Nv) * 4 B, SURVEY.md section 8(d)
 METRIC = "decoded info bits/s (LDPC 802.11n r1/2 n=1944 sum-product BP, <=50 its, batched AWGN frames)"
 
@@ -397,16 +400,27 @@ def main():
                       "api": "lsb_ldpc_decode_host_f32 (C-ABI, pinned host LLR in, uint8 decisions + iteration counts out)"}
 
     out["clocks"] = clocks.summary()
-    # the pipe the kernel is really bound by: 4 MUFU (2 ex2 + 2 lg2) per corrected Lxor, 3 dc - 6 of them per
-    # check of degree dc (cdeg 7 x 810, 8 x 162 for this code), against 16 MUFU lanes per SM per clock
-    mufu_per_frame_iter = 4 * int(sum(3 * int(dc) - 6 for dc in code.cdeg))
+    # Secondary rooflines (what the kernel is really bound by; messages never leave shared memory).
+    # MUFU: the exp-domain check node spends dc EX2 + 2 dc LG2 per check = 3 per edge and iteration (it was
+    # 4 (3 dc - 6) per check in round 1, when this pipe was the bound), against 16 MUFU lanes per SM per clock.
+    # Issue: warp instructions per frame-iteration counted by ncu on this kernel and workload
+    # (profiles/r2_bp_edomain_v2_ncu_full.csv: smsp__inst_executed.sum / frame-iterations of that launch), against
+    # 4 issue slots per SM per clock.
+    mufu_per_frame_iter = 3 * int(sum(int(dc) for dc in code.cdeg))
     sm_mhz = out["clocks"].get("sm_mhz") or out["clocks"].get("sm_max_mhz") or 1965.0
-    mufu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * float(sm_mhz) * 1e6
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    mufu_peak = 16.0 * n_sm * float(sm_mhz) * 1e6
     mufu_rate = mufu_per_frame_iter * frame_iters_rank / (kernel_ms_avg * 1e-3)
     out["roofline_mufu"] = {"bound": "mufu", "achieved": mufu_rate / 1e12, "peak": mufu_peak / 1e12, "unit": "T MUFU op/s",
                             "frac": mufu_rate / mufu_peak, "mufu_per_frame_iteration": mufu_per_frame_iter,
-                            "note": "secondary roofline: 16 MUFU lanes/SM/clk at the SM clock sampled under load; "
-                                    "ncu reports the XU pipe 83 % busy (profiles/r1_bp_qc_f32_v3_ncu_full.csv)"}
+                            "note": "16 MUFU lanes/SM/clk at the SM clock sampled under load"}
+    issue_peak = 4.0 * n_sm * float(sm_mhz) * 1e6
+    issue_rate = WARP_INSTR_PER_FRAME_ITER * frame_iters_rank / (kernel_ms_avg * 1e-3)
+    out["roofline_issue"] = {"bound": "issue", "achieved": issue_rate / 1e12, "peak": issue_peak / 1e12,
+                             "unit": "T warp-instructions/s", "frac": issue_rate / issue_peak,
+                             "warp_instructions_per_frame_iteration": WARP_INSTR_PER_FRAME_ITER,
+                             "note": "the real bound of the round-2 kernel: ncu smsp__issue_active 82 % "
+                                     "(profiles/r2_bp_edomain_v2_ncu_full.csv); instruction count from that capture"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(code, args, args.cpu_seconds)
     if not args.no_extras:

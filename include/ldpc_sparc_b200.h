@@ -310,6 +310,13 @@ int lsb_tc_ab_dev_f32(lsb_tc_design *g, const float *x /* [F, ML] */, float *out
                       void *stream);
 int lsb_tc_az_dev_f32(lsb_tc_design *g, const float *z /* [F, n] */, float *out /* [F, ML] */, int64_t F,
                       void *stream);
+/* Whole dense-design AMP decode on the tensor-core path (replaces the loop of sparc_sophie/sparc_new.py:885-912
+ * for a batch): per iteration  A beta (tcgen05 GEMM) -> residual + tau^2 -> A^T z with the section-wise softmax
+ * denoiser (sparc_new.py:1040-1066) as the GEMM epilogue.  y [F, n] device fp32; beta_out [F, ML] receives the soft
+ * estimate after t_max iterations; s_out (may be NULL) the last s = beta + A^T z; tau_trace (may be NULL) [t_max, F]
+ * the tau^2 of every iteration.  M must be a power of two in [2, 128]; pointers 16-byte aligned. */
+int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M, double P, double sqrt_nPl, int t_max,
+                       float *beta_out, float *s_out, double *tau_trace, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Complex SPARCs: sub-sampled DFT design (sparc.py sub_fft :593-646, sparc_transforms

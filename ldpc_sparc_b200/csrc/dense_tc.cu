@@ -46,11 +46,32 @@ struct lsb_tc_design {
         size_t x_cap = 0;
         float *part = nullptr;
         size_t part_cap = 0;
+        // fused AMP chain (lsb_tc_amp_dev_f32): z and its bf16 pair, beta's bf16 pair, scalars
+        float *z = nullptr, *bsq_part = nullptr;
+        __nv_bfloat16 *z_hi = nullptr, *z_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+        double *tau = nullptr;
+        size_t amp_frames = 0;
     };
     std::map<cudaStream_t, Staging> staging;
 };
 
 namespace {
+
+// K splits of a product with n_tiles output tiles and num_kb K blocks: few tiles (A beta: n/128 x F/128) leave most
+// of the last wave idle; pick the split count that minimises rounds-per-split, charging 3% per extra partial
+int pick_splits(int n_tiles, int num_kb, int sms)
+{
+    int splits = 1;
+    double best = 1e30;
+    for (int sp = 1; sp <= 8 && sp * 8 <= num_kb; ++sp) {
+        const double cost = (double)((n_tiles * sp + sms - 1) / sms) / sp + 0.03 * (sp - 1);
+        if (cost < best - 1e-9) {
+            best = cost;
+            splits = sp;
+        }
+    }
+    return splits;
+}
 
 int build_operand(TcOperand *op, const double *d_src, int64_t rows, int64_t K)
 {
@@ -106,19 +127,7 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     const int n_row_tiles = (int)((W.rows + kTileRows - 1) / kTileRows), n_f_tiles = (int)((F + kTileN - 1) / kTileN);
     const int n_tiles = n_row_tiles * n_f_tiles, sms = lsb::sm_count();
     const int num_kb = (int)((W.K + kBlockK - 1) / kBlockK);
-    // K splits: few tiles (A beta: n/128 x F/128) leave most of the last wave idle; pick the
-    // split count that minimises rounds-per-split, charging 3% per extra partial written
-    int splits = 1;
-    {
-        double best = 1e30;
-        for (int sp = 1; sp <= 8 && sp * 8 <= num_kb; ++sp) {
-            const double cost = (double)((n_tiles * sp + sms - 1) / sms) / sp + 0.03 * (sp - 1);
-            if (cost < best - 1e-9) {
-                best = cost;
-                splits = sp;
-            }
-        }
-    }
+    int splits = pick_splits(n_tiles, num_kb, sms);
     const size_t out_count = (size_t)F * (size_t)W.rows;
     if (((uintptr_t)out & 15) != 0) splits = 1;     // the partial sum runs on float4
     float *dst = out;
@@ -149,9 +158,113 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     return LSB_OK;
 }
 
+template <int M>
+void launch_denoise_gemm(int grid, cudaStream_t st, const CUtensorMap &w_hi, const CUtensorMap &w_lo, const CUtensorMap &x_hi,
+                         const CUtensorMap &x_lo, float *beta, int has_beta, __nv_bfloat16 *b_hi, __nv_bfloat16 *b_lo,
+                         float *s_out, const double *tau, float *bsq_part, float sq, int rows, int F, int K, int n_row_tiles,
+                         int n_f_tiles)
+{
+    lsb::ensure_dynamic_smem(tc_gemm_denoise_kernel<M>, kSmemBytes);
+    tc_gemm_denoise_kernel<M><<<grid, kThreadsTc, kSmemBytes, st>>>(w_hi, w_lo, x_hi, x_lo, beta, has_beta, b_hi, b_lo, s_out,
+                                                                    tau, bsq_part, sq, rows, F, K, n_row_tiles, n_f_tiles);
+}
+
 }  // namespace
 
 extern "C" {
+
+// Whole dense-design AMP decode (sparc_new.py:885-912) for F frames sharing the design, three launches per
+// iteration: A beta (K-split partials) -> tc_residual_kernel -> A^T z with the denoiser as its epilogue.
+// beta_out [F, ML] is the iterate itself (zeroed here, soft estimate on return); s_out (optional) receives the
+// last iteration's s = beta + A^T z; tau_trace (optional) [t_max, F] the tau^2 of every iteration.
+int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M, double P, double sqrt_nPl, int t_max,
+                       float *beta_out, float *s_out, double *tau_trace, void *stream)
+{
+    if (F == 0) return LSB_OK;
+    LSB_REQUIRE(g && y && beta_out, "null pointer");
+    LSB_REQUIRE(F > 0 && F < (1 << 24) && t_max >= 1, "bad frame count or t_max");
+    LSB_REQUIRE((int64_t)L * M == g->ML, "L * M = %lld does not match the design (ML = %lld)", (long long)L * M,
+                (long long)g->ML);
+    LSB_REQUIRE(M >= 2 && M <= 128 && (M & (M - 1)) == 0, "the fused denoiser handles M = 2 .. 128 (power of two), got %d", M);
+    LSB_REQUIRE(g->ML % 32 == 0, "the fused denoiser needs L * M to be a multiple of 32 (whole 32-column accumulator chunks)");
+    LSB_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)beta_out & 15) == 0 && (!s_out || ((uintptr_t)s_out & 15) == 0),
+                "y, beta_out and s_out must be 16-byte aligned");
+    int dev = -1;
+    LSB_CUDA(cudaGetDevice(&dev));
+    LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::unique_lock<std::mutex> lock(g->mu);
+    LSB_REQUIRE(g->staging.size() < 32 || g->staging.count(st), "more than 32 streams use this design");
+    lsb_tc_design::Staging &sg = g->staging[st];
+    lock.unlock();
+
+    const int n = (int)g->n, ML = (int)g->ML, sms = lsb::sm_count();
+    const int n_f_tiles = (int)((F + kTileN - 1) / kTileN);
+    const int ab_row_tiles = (n + kTileRows - 1) / kTileRows, az_row_tiles = (ML + kTileRows - 1) / kTileRows;
+    const int splits = pick_splits(ab_row_tiles * n_f_tiles, (ML + kBlockK - 1) / kBlockK, sms);
+    if (sg.amp_frames < (size_t)F) {
+        LSB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(sg.z); cudaFree(sg.bsq_part); cudaFree(sg.z_hi); cudaFree(sg.z_lo); cudaFree(sg.b_hi); cudaFree(sg.b_lo);
+        cudaFree(sg.tau);
+        sg.z = sg.bsq_part = nullptr;
+        sg.z_hi = sg.z_lo = sg.b_hi = sg.b_lo = nullptr;
+        sg.tau = nullptr;
+        sg.amp_frames = 0;
+        LSB_CUDA(cudaMalloc((void **)&sg.z, (size_t)F * n * sizeof(float)));
+        LSB_CUDA(cudaMalloc((void **)&sg.z_hi, (size_t)F * n * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.z_lo, (size_t)F * n * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.b_hi, (size_t)F * ML * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.b_lo, (size_t)F * ML * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.bsq_part, (size_t)F * az_row_tiles * sizeof(float)));
+        LSB_CUDA(cudaMalloc((void **)&sg.tau, (size_t)F * sizeof(double)));
+        sg.amp_frames = (size_t)F;
+    }
+    const size_t out_count = (size_t)F * (size_t)n;
+    if (sg.part_cap < out_count * (size_t)splits) {
+        LSB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(sg.part);
+        sg.part = nullptr;
+        sg.part_cap = 0;
+        LSB_CUDA(cudaMalloc((void **)&sg.part, out_count * (size_t)splits * sizeof(float)));
+        sg.part_cap = out_count * (size_t)splits;
+    }
+    CUtensorMap mb_hi, mb_lo, mz_hi, mz_lo;
+    int rc = make_map(&mb_hi, sg.b_hi, (uint64_t)F, (uint64_t)ML);
+    if (!rc) rc = make_map(&mb_lo, sg.b_lo, (uint64_t)F, (uint64_t)ML);
+    if (!rc) rc = make_map(&mz_hi, sg.z_hi, (uint64_t)F, (uint64_t)n);
+    if (!rc) rc = make_map(&mz_lo, sg.z_lo, (uint64_t)F, (uint64_t)n);
+    if (rc) return rc;
+    LSB_CUDA(lsb::ensure_dynamic_smem(tc_gemm_kernel, kSmemBytes));
+
+    const int ab_items = ab_row_tiles * n_f_tiles * splits, az_items = az_row_tiles * n_f_tiles;
+    for (int t = 0; t < t_max; ++t) {
+        if (t > 0) {
+            tc_gemm_kernel<<<ab_items < sms ? ab_items : sms, kThreadsTc, kSmemBytes, st>>>(
+                g->A.map_hi, g->A.map_lo, mb_hi, mb_lo, sg.part, n, (int)F, ML, ab_row_tiles, n_f_tiles, splits,
+                (long long)out_count);
+            lsb::count_launch();
+        }
+        tc_residual_kernel<<<(unsigned)F, kThreadsTc, 0, st>>>(y, sg.part, splits, (long long)out_count, sg.z, sg.z_hi, sg.z_lo,
+                                                             sg.bsq_part, az_row_tiles, sg.tau,
+                                                             tau_trace ? tau_trace + (size_t)t * F : nullptr, (int)F, n, P,
+                                                             t == 0);
+        lsb::count_launch();
+        float *so = (t == t_max - 1) ? s_out : nullptr;
+        const int grid = az_items < sms ? az_items : sms;
+#define LSB_DN(MM)                                                                                                       \
+    case MM:                                                                                                             \
+        launch_denoise_gemm<MM>(grid, st, g->At.map_hi, g->At.map_lo, mz_hi, mz_lo, beta_out, t > 0, sg.b_hi, sg.b_lo, so, \
+                                sg.tau, sg.bsq_part, (float)sqrt_nPl, ML, (int)F, n, az_row_tiles, n_f_tiles);           \
+        break;
+        switch (M) {
+            LSB_DN(2) LSB_DN(4) LSB_DN(8) LSB_DN(16) LSB_DN(32) LSB_DN(64) LSB_DN(128)
+        }
+#undef LSB_DN
+        lsb::count_launch();
+        LSB_CUDA(cudaGetLastError());
+    }
+    return LSB_OK;
+}
 
 int lsb_tc_design_create(const double *A, int64_t n, int64_t ML, lsb_tc_design **out)
 {
@@ -210,6 +323,13 @@ void lsb_tc_design_destroy(lsb_tc_design *g)
         cudaFree(kv.second.x_hi);
         cudaFree(kv.second.x_lo);
         cudaFree(kv.second.part);
+        cudaFree(kv.second.z);
+        cudaFree(kv.second.bsq_part);
+        cudaFree(kv.second.z_hi);
+        cudaFree(kv.second.z_lo);
+        cudaFree(kv.second.b_hi);
+        cudaFree(kv.second.b_lo);
+        cudaFree(kv.second.tau);
     }
     delete g;
 }

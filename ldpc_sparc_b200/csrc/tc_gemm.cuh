@@ -392,6 +392,302 @@ tc_items_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_consta
     }
 }
 
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (lane = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b)
+{
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A^T z product with the AMP denoiser as its epilogue (dense design, sparc_new.py:907-908 + 1040-1066):
+//     s = beta + A^T z,   beta <- sqrt_nPl * softmax_section(sqrt_nPl * s / tau^2)
+// Same pipeline as tc_gemm_kernel with the operand roles swapped: the frame tile is the MMA's M operand, so a
+// TMEM lane is a FRAME and the 128 accumulator columns are 128 consecutive entries of its beta -- whole sections
+// (M <= 128 divides 128), each owned by one thread.  The epilogue thread reads its accumulator row, adds the old
+// beta, runs the section softmax in registers and writes the new beta as fp32 and as the bf16 hi / lo pair that
+// the next A beta product consumes, so the separate denoiser, the fp32 -> bf16 split and the [F, ML] round trip
+// of A^T z are gone.  |beta|^2 goes out as one fp32 partial per (row tile, frame); the residual kernel adds the
+// partials of a frame in index order.  No K split (the epilogue needs the whole sum).
+template <int M>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+tc_gemm_denoise_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                       const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                       float *beta, int has_beta, __nv_bfloat16 *__restrict__ beta_hi, __nv_bfloat16 *__restrict__ beta_lo,
+                       float *__restrict__ s_out, const double *__restrict__ tau_sqr, float *__restrict__ bsq_part,
+                       float sqrt_nPl, int rows_total, int F, int K, int n_row_tiles, int n_f_tiles)
+{
+    constexpr int SEC = M < 32 ? 32 : M;          // accumulator columns handled at a time (whole sections)
+    static_assert(M >= 2 && M <= 128 && (M & (M - 1)) == 0, "section size must be a power of two in [2, 128]");
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full_bar[2], acc_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (K + kBlockK - 1) / kBlockK;
+    const int n_items = n_row_tiles * n_f_tiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX_lo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full_bar[a], 1);
+            mbar_init(&acc_empty_bar[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "n"(2 * kTileN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    // frame tiles fastest (see tc_gemm_kernel)
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int row0 = (item / n_f_tiles) * kTileRows, f0 = (item % n_f_tiles) * kTileN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&empty_bar[s], phase ^ 1);
+                    uint8_t *st = tiles + s * kStageBytes;
+                    mbar_expect_tx(&full_bar[s], kStageBytes);
+                    tma_load_2d(st, &mapW_hi, &full_bar[s], kb * kBlockK, row0);
+                    tma_load_2d(st + kTileBytes, &mapW_lo, &full_bar[s], kb * kBlockK, row0);
+                    tma_load_2d(st + 2 * kTileBytes, &mapX_hi, &full_bar[s], kb * kBlockK, f0);
+                    tma_load_2d(st + 3 * kTileBytes, &mapX_lo, &full_bar[s], kb * kBlockK, f0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileRows >> 3) << 17) |
+                                   ((uint32_t)(kTileN >> 4) << 24);
+            uint32_t it = 0, j = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+                const uint32_t a = j & 1;
+                mbar_wait(&acc_empty_bar[a], ((j >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + a * kTileRows;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t phase = (it / kStages) & 1;
+                    mbar_wait(&full_bar[s], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(tiles + s * kStageBytes);
+                    const uint64_t dW_hi = umma_desc(base), dW_lo = umma_desc(base + kTileBytes);
+                    const uint64_t dX_hi = umma_desc(base + 2 * kTileBytes), dX_lo = umma_desc(base + 3 * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+                        umma_bf16(tmem_d, dX_hi + adv, dW_hi + adv, idesc, (kb != 0) || (k != 0));     // lanes = frames
+                        umma_bf16(tmem_d, dX_hi + adv, dW_lo + adv, idesc, 1);
+                        umma_bf16(tmem_d, dX_lo + adv, dW_hi + adv, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full_bar[a]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        uint32_t j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            const int row_tile = item / n_f_tiles;
+            const int row0 = row_tile * kTileRows, f0 = (item % n_f_tiles) * kTileN;
+            const uint32_t a = j & 1;
+            const int f = f0 + q * 32 + lane;
+            const bool live = f < F;
+            const float scale = live ? (float)((double)sqrt_nPl / tau_sqr[f]) : 0.0f;
+            float sq = 0.0f;
+            mbar_wait(&acc_full_bar[a], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < kTileRows; c0 += SEC) {
+                float sv[SEC];
+#pragma unroll
+                for (int h = 0; h < SEC / 32; ++h)
+                    tmem_ld32(tmem_base + a * kTileRows + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32 * h), sv + 32 * h);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (live && row0 + c0 < rows_total) {
+                    const size_t base = (size_t)f * (size_t)rows_total + (size_t)(row0 + c0);
+                    if (has_beta) {
+#pragma unroll
+                        for (int k = 0; k < SEC / 4; ++k) {
+                            const float4 b = *reinterpret_cast<const float4 *>(beta + base + 4 * k);
+                            sv[4 * k] += b.x;
+                            sv[4 * k + 1] += b.y;
+                            sv[4 * k + 2] += b.z;
+                            sv[4 * k + 3] += b.w;
+                        }
+                    }
+                    if (s_out) {
+#pragma unroll
+                        for (int k = 0; k < SEC / 4; ++k)
+                            *reinterpret_cast<float4 *>(s_out + base + 4 * k) =
+                                make_float4(sv[4 * k], sv[4 * k + 1], sv[4 * k + 2], sv[4 * k + 3]);
+                    }
+#pragma unroll
+                    for (int s0 = 0; s0 < SEC; s0 += M) {
+                        float mx = sv[s0];
+#pragma unroll
+                        for (int i = 1; i < M; ++i) mx = fmaxf(mx, sv[s0 + i]);
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < M; ++i) {
+                            sv[s0 + i] = expf((sv[s0 + i] - mx) * scale);
+                            sum += sv[s0 + i];
+                        }
+                        const float inv = sqrt_nPl / sum;
+#pragma unroll
+                        for (int i = 0; i < M; ++i) {
+                            sv[s0 + i] *= inv;
+                            sq = fmaf(sv[s0 + i], sv[s0 + i], sq);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < SEC / 4; ++k)
+                        *reinterpret_cast<float4 *>(beta + base + 4 * k) =
+                            make_float4(sv[4 * k], sv[4 * k + 1], sv[4 * k + 2], sv[4 * k + 3]);
+#pragma unroll
+                    for (int k = 0; k < SEC / 8; ++k) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float v0 = sv[8 * k + 2 * u], v1 = sv[8 * k + 2 * u + 1];
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                            h[u] = pack_bf16(h0, h1);
+                            l[u] = pack_bf16(__float2bfloat16_rn(v0 - __bfloat162float(h0)),
+                                             __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+                        }
+                        *reinterpret_cast<uint4 *>(beta_hi + base + 8 * k) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(beta_lo + base + 8 * k) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+            }
+            if (live) bsq_part[(size_t)row_tile * (size_t)F + (size_t)f] = sq;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty_bar[a]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kTileN) : "memory");
+    }
+}
+
+// deterministic block sum (fixed tree), result valid in thread 0
+__device__ __forceinline__ double tc_block_sum(double v, double *red /* [kThreadsTc / 32] shared */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kThreadsTc / 32; ++w) tot += red[w];
+    __syncthreads();
+    return tot;
+}
+
+// Residual step of the dense-design AMP on the tensor-core path (sparc_new.py:898,904-905), one CTA per frame:
+//     z <- y - sum_s part_s + z (P - |beta|^2 / n) / tau^2        (first: z <- y),     tau^2 <- |z|^2 / n
+// reading the K-split partials of A beta directly (no reduce pass) and the per-row-tile partials of |beta|^2, and
+// writing z as fp32 plus the bf16 hi / lo pair the A^T z product consumes (no split pass).  n % 8 == 0.
+__global__ void __launch_bounds__(kThreadsTc)
+tc_residual_kernel(const float *__restrict__ y, const float *__restrict__ part, int splits, long long split_stride,
+                   float *__restrict__ z, __nv_bfloat16 *__restrict__ z_hi, __nv_bfloat16 *__restrict__ z_lo,
+                   const float *__restrict__ bsq_part, int n_bsq, double *__restrict__ tau_sqr, double *__restrict__ tau_trace,
+                   int F, int n, double P, int first)
+{
+    __shared__ double red[kThreadsTc / 32];
+    __shared__ float s_coef;
+    const size_t f = blockIdx.x;
+    if (!first) {
+        double b = 0.0;
+        for (int i = threadIdx.x; i < n_bsq; i += kThreadsTc) b += (double)bsq_part[(size_t)i * F + f];
+        const double bsq = tc_block_sum(b, red);
+        if (threadIdx.x == 0) s_coef = (float)((P - bsq / n) / tau_sqr[f]);
+        __syncthreads();
+    }
+    const float coef = first ? 0.0f : s_coef;
+    double acc = 0.0;
+    for (int i8 = threadIdx.x; i8 < n / 8; i8 += kThreadsTc) {
+        const size_t p = f * (size_t)n + (size_t)i8 * 8;
+        float v[8];
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(y + p), b = *reinterpret_cast<const float4 *>(y + p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        if (!first) {
+            float ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int s = 0; s < splits; ++s) {
+                const float *ps = part + (size_t)s * (size_t)split_stride + p;
+                const float4 a = *reinterpret_cast<const float4 *>(ps), b = *reinterpret_cast<const float4 *>(ps + 4);
+                ab[0] += a.x; ab[1] += a.y; ab[2] += a.z; ab[3] += a.w; ab[4] += b.x; ab[5] += b.y; ab[6] += b.z; ab[7] += b.w;
+            }
+            const float4 a = *reinterpret_cast<const float4 *>(z + p), b = *reinterpret_cast<const float4 *>(z + p + 4);
+            const float zo[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (v[k] - ab[k]) + zo[k] * coef;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * u]), h1 = __float2bfloat16_rn(v[2 * u + 1]);
+            h[u] = pack_bf16(h0, h1);
+            l[u] = pack_bf16(__float2bfloat16_rn(v[2 * u] - __bfloat162float(h0)),
+                             __float2bfloat16_rn(v[2 * u + 1] - __bfloat162float(h1)));
+        }
+        *reinterpret_cast<float4 *>(z + p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(z + p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<uint4 *>(z_hi + p) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(z_lo + p) = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += (double)v[k] * (double)v[k];
+    }
+    const double tot = tc_block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        tau_sqr[f] = tot / n;
+        if (tau_trace) tau_trace[f] = tot / n;
+    }
+}
+
 // out = sum of `splits` partial products, added in index order (fixed result)
 __global__ void reduce_splits_kernel(const float4 *__restrict__ part, float4 *__restrict__ out, long long n4, int splits)
 {

@@ -331,9 +331,26 @@ def _amp_iteration(eng, y, st, P, L, M, sq, first, s_out=None):
     eng.denoise(st["beta"], atz, st["beta"], s_out, st["tau"], st["beta_sq"], L, M, sq)
 
 
+FUSED_TC_AMP = True       # tensor-core mode: the whole AMP loop in one C call (lsb_tc_amp_dev_f32)
+
+
 def _amp_device(eng, yd, P, L, M, sq, t_max, return_trace=False):
     """t_max AMP iterations on device frames ``yd [F, n]``; returns device tensors
     ``(beta, s[, tau^2 per iteration])``."""
+    if eng.tc and FUSED_TC_AMP and 2 <= M <= 128 and (L * M) % 32 == 0 and t_max >= 1 and yd.shape[0] > 0:
+        # three launches per iteration, no Python in the loop: A beta -> residual (+ bf16 split of z) ->
+        # A^T z with the denoiser (+ bf16 split of beta) as the GEMM epilogue
+        t = eng.torch
+        F = yd.shape[0]
+        beta, s = eng.empty(F, L * M), eng.empty(F, L * M)
+        taus = t.empty((t_max, F), dtype=t.float64, device=eng.dev) if return_trace else None
+        _lib.check(_lib.lib().lsb_tc_amp_dev_f32(eng.h, yd.data_ptr(), F, L, M, float(P), float(sq), int(t_max),
+                                                 beta.data_ptr(), s.data_ptr(),
+                                                 taus.data_ptr() if return_trace else None, eng.stream()), "tc_amp")
+        if return_trace:
+            return beta, s, taus.t().contiguous()
+        return beta, s
+
     def run(yc):
         st = _amp_state(eng, yc, L, M)
         s = eng.empty(yc.shape[0], L * M)
