@@ -236,6 +236,25 @@ int lsb_sparc_amp_host_f32(lsb_sparc_design *g, const float *y, int64_t n_frames
                            const lsb_sparc_amp_params *p, int32_t *idx, int32_t *t_final,
                            double *psi);
 
+/* ---- (3b) the same design stored explicitly, products on the tensor cores (csrc/sparc_band_tc.cu)
+ * For designs whose blocks keep few of the w transform outputs (spatially coupled: BASELINE config 4 keeps 332 of
+ * 65536 per block) the blocks of A are generated once on the device from the closed form above and kept as bf16
+ * hi / lo pairs in both orientations; A beta and A^T z for a frame batch are block-banded tcgen05 GEMMs (three
+ * bf16 products per operand pair, fp32 accumulation) and the rest of sparc_amp (sparc.py:931-999) runs in two
+ * memory-bound kernels per iteration.  Same arguments and outputs as lsb_sparc_design_create /
+ * lsb_sparc_ab_dev_f32 / lsb_sparc_az_dev_f32 / lsb_sparc_amp_dev_f32 (modulation <= 1 only; M <= 1024; L*M a
+ * multiple of 8).  Device memory: lsb_band_design_bytes(). */
+typedef struct lsb_band_design lsb_band_design;
+int lsb_band_design_create(const double *W, int Lr, int Lc, int L, int M, int n,
+                           const uint32_t *order0, const uint32_t *order1, lsb_band_design **out);
+void lsb_band_design_destroy(lsb_band_design *g);
+int64_t lsb_band_design_bytes(const lsb_band_design *g);
+int lsb_band_ab_dev_f32(lsb_band_design *g, const float *x, float *out, int64_t n_frames, void *stream);
+int lsb_band_az_dev_f32(lsb_band_design *g, const float *y, float *out, int64_t n_frames, void *stream);
+int lsb_band_amp_dev_f32(lsb_band_design *g, const float *y, int64_t n_frames,
+                         const lsb_sparc_amp_params *p, const int32_t *idx0,
+                         const lsb_sparc_amp_out *out, void *stream);
+
 /* ----------------------------- (4) SPARC, dense Gaussian design (sparc_sophie)
  * Replaces, for batches of frames that share one design matrix A [n x ML]
  * (sparc_new.py:1284-1294), the NumPy steps of sparc_amp / sparc_amp_single_it

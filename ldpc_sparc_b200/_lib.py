@@ -68,6 +68,12 @@ SIGNATURES = {
     # SPARC (sub-sampled DCT design)
     "lsb_sparc_design_create": (ct.c_int, [c_f64p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_u32p, c_u32p, ct.POINTER(ct.c_void_p)]),
     "lsb_sparc_design_destroy": (None, [ct.c_void_p]),
+    "lsb_band_design_create": (ct.c_int, [c_f64p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_u32p, c_u32p, ct.POINTER(ct.c_void_p)]),
+    "lsb_band_design_destroy": (None, [ct.c_void_p]),
+    "lsb_band_design_bytes": (ct.c_int64, [ct.c_void_p]),
+    "lsb_band_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    "lsb_band_az_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
+    "lsb_band_amp_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
     "lsb_sparc_design_info": (ct.c_int, [ct.c_void_p, c_i64p]),
     "lsb_sparc_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_sparc_ab_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),

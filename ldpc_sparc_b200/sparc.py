@@ -395,7 +395,28 @@ class Design:
             self._handle = h
         return self._handle
 
+    def band_handle(self):
+        """Explicit (block-banded, bf16 hi / lo) copy of the design for the tensor-core path
+        (``precision='tc'``, csrc/sparc_band_tc.cu); built on first use."""
+        if self.csparc:
+            raise NotImplementedError("precision='tc' handles the real (DCT) design")
+        if getattr(self, "_band", None) is None:
+            _lib.require_device()
+            h = ct.c_void_p()
+            _lib.check(_lib.lib().lsb_band_design_create(
+                self.Wm.ctypes.data_as(_lib.c_f64p), self.Lr, self.Lc, self.L, self.M, self.n,
+                self.order0.ctypes.data_as(_lib.c_u32p), self.order1.ctypes.data_as(_lib.c_u32p), ct.byref(h)),
+                "lsb_band_design_create")
+            self._band = h
+        return self._band
+
     def __del__(self):
+        try:
+            if getattr(self, "_band", None) is not None:
+                _lib.lib().lsb_band_design_destroy(self._band)
+                self._band = None
+        except Exception:
+            pass
         try:
             if getattr(self, "_handle", None) is not None:
                 destroy = _lib.lib().lsb_csparc_design_destroy if self.csparc else _lib.lib().lsb_sparc_design_destroy
@@ -426,9 +447,10 @@ class Design:
         out = torch.empty((x.shape[0], n_out), dtype=dt, device=x.device)
         L_ = _lib.lib()
         fn = {(False, "fp32"): L_.lsb_sparc_ab_dev_f32, (False, "fp64"): L_.lsb_sparc_ab_dev_f64,
-              (True, "fp32"): L_.lsb_sparc_az_dev_f32, (True, "fp64"): L_.lsb_sparc_az_dev_f64}[(transpose, precision)]
+              (True, "fp32"): L_.lsb_sparc_az_dev_f32, (True, "fp64"): L_.lsb_sparc_az_dev_f64,
+              (False, "tc"): L_.lsb_band_ab_dev_f32, (True, "tc"): L_.lsb_band_az_dev_f32}[(transpose, precision)]
         with torch.cuda.device(x.device):
-            _lib.check(fn(self.handle(), x.data_ptr(), out.data_ptr(), x.shape[0],
+            _lib.check(fn(self.band_handle() if precision == "tc" else self.handle(), x.data_ptr(), out.data_ptr(), x.shape[0],
                           torch.cuda.current_stream().cuda_stream), "lsb_sparc_ab/az")
         if single:
             out = out[0]
@@ -580,9 +602,16 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method), int(K), 0)
     ptr = lambda t: t.data_ptr() if t is not None else None
     out = _lib.AmpOut(ptr(idx), ptr(t_final), ptr(psi), ptr(nmse), ptr(beta_soft), ptr(s_last), ptr(tau_tr), ptr(psi_tr))
-    fn = getattr(_lib.lib(), "lsb_%s_amp_dev_%s" % ("csparc" if cplx else "sparc", "f64" if precision == "fp64" else "f32"))
+    if precision == "tc":
+        # explicit block-banded design, A beta / A^T z as tcgen05 GEMMs over the frame batch (csrc/sparc_band_tc.cu)
+        if cplx or K != 1:
+            raise NotImplementedError("precision='tc' handles real, unmodulated SPARCs")
+        fn, handle = _lib.lib().lsb_band_amp_dev_f32, design.band_handle()
+    else:
+        fn = getattr(_lib.lib(), "lsb_%s_amp_dev_%s" % ("csparc" if cplx else "sparc", "f64" if precision == "fp64" else "f32"))
+        handle = design.handle()
     with torch.cuda.device(dev):
-        _lib.check(fn(design.handle(), yt.data_ptr(), F, ct.byref(params), ptr(idx0), ct.byref(out),
+        _lib.check(fn(handle, yt.data_ptr(), F, ct.byref(params), ptr(idx0), ct.byref(out),
                       torch.cuda.current_stream().cuda_stream), "lsb_sparc_amp_dev")
 
     extra = {}
