@@ -275,18 +275,32 @@ band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
     const bool has_beta = t > 0;
     double psi_part = 0.0, nm_part = 0.0;
     if (PL > 0) {
+        // a lane owns PL CONSECUTIVE entries of the section (16-byte loads / stores for PL >= 4, bf16 pairs packed)
         constexpr int P_ = PL > 0 ? PL : 1;
         for (int sec = warp; sec < secs; sec += kBandThreads / 32) {
-            const size_t base = base_c + (size_t)sec * d.M;
+            const size_t a0 = base_c + (size_t)sec * d.M + (size_t)lane * P_;
             float sv[P_];
+            if (P_ % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < P_; k += 4) {
+                    const float4 az4 = *reinterpret_cast<const float4 *>(s.atz + a0 + k);
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_beta) b4 = *reinterpret_cast<const float4 *>(s.beta + a0 + k);
+                    sv[k] = b4.x + tau_c * az4.x;
+                    sv[k + 1] = b4.y + tau_c * az4.y;
+                    sv[k + 2] = b4.z + tau_c * az4.z;
+                    sv[k + 3] = b4.w + tau_c * az4.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < P_; ++k) sv[k] = (has_beta ? s.beta[a0 + k] : 0.0f) + tau_c * s.atz[a0 + k];
+            }
             float mx = -INFINITY;
             int arg = 0x7fffffff;
 #pragma unroll
             for (int k = 0; k < P_; ++k) {
-                const size_t a = base + lane + 32 * k;
-                sv[k] = (has_beta ? s.beta[a] : 0.0f) + tau_c * s.atz[a];
-                if (s.s_last) s.s_last[a] = sv[k];
-                if (sv[k] > mx) { mx = sv[k]; arg = lane + 32 * k; }
+                if (s.s_last) s.s_last[a0 + k] = sv[k];
+                if (sv[k] > mx) { mx = sv[k]; arg = lane * P_ + k; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -306,15 +320,36 @@ band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
             const int truth = s.idx0 ? s.idx0[f * d.L + sec0 + sec] : -1;
 #pragma unroll
             for (int k = 0; k < P_; ++k) {
-                const size_t a = base + lane + 32 * k;
-                const float b = sv[k] * inv;
-                s.beta[a] = b;
-                const __nv_bfloat16 h = __float2bfloat16_rn(b);
-                s.b_hi[a] = h;
-                s.b_lo[a] = __float2bfloat16_rn(b - __bfloat162float(h));
-                psi_part += (double)b * (double)((sum - sv[k]) * inv);
-                const double dlt = (double)b - ((lane + 32 * k) == truth ? 1.0 : 0.0);
+                const float e = sv[k];
+                sv[k] = e * inv;
+                psi_part += (double)sv[k] * (double)((sum - e) * inv);
+                const double dlt = (double)sv[k] - ((lane * P_ + k) == truth ? 1.0 : 0.0);
                 nm_part += dlt * dlt;
+            }
+            if (P_ % 8 == 0) {
+#pragma unroll
+                for (int k = 0; k < P_; k += 8) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float v0 = sv[k + 2 * u], v1 = sv[k + 2 * u + 1];
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                        h[u] = pack_bf16(h0, h1);
+                        l[u] = pack_bf16(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+                    }
+                    *reinterpret_cast<float4 *>(s.beta + a0 + k) = make_float4(sv[k], sv[k + 1], sv[k + 2], sv[k + 3]);
+                    *reinterpret_cast<float4 *>(s.beta + a0 + k + 4) = make_float4(sv[k + 4], sv[k + 5], sv[k + 6], sv[k + 7]);
+                    *reinterpret_cast<uint4 *>(s.b_hi + a0 + k) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(s.b_lo + a0 + k) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < P_; ++k) {
+                    s.beta[a0 + k] = sv[k];
+                    const __nv_bfloat16 h = __float2bfloat16_rn(sv[k]);
+                    s.b_hi[a0 + k] = h;
+                    s.b_lo[a0 + k] = __float2bfloat16_rn(sv[k] - __bfloat162float(h));
+                }
             }
             if (lane == 0) s.idx[f * d.L + sec0 + sec] = arg;
         }
@@ -481,8 +516,10 @@ int prepare_work(lsb_band_design *g, lsb_band_design::Work &wk, long long F)
 
     const int n_f_tiles = (int)((F + kTileN - 1) / kTileN), sms = lsb::sm_count();
     std::vector<TcItem> ab, az;
-    for (int r = 0; r < d.Lr; ++r)
-        for (int c = g->clo[r]; c <= g->chi[r]; ++c) {
+    // column block outermost: the row blocks that use column block c run together and share its beta tiles in L2
+    // (row block outermost re-read every beta panel from DRAM once per row block of the band: 6x for config 4)
+    for (int c = 0; c < d.Lc; ++c)
+        for (int r = g->rlo[c]; r <= g->rhi[c]; ++r) {
             if (g->W[r * d.Lc + c] == 0.0) continue;
             const int cc = c - g->clo[r];
             for (int tt = 0; tt * kTileRows < d.Mr; ++tt)
