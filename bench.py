@@ -433,7 +433,10 @@ def main():
             ("sparc_amp_config1", lambda: workloads.amp_workload(ctx, "c1", 16384, k, 2)),
             # same decode with the early-stop atol at the fp32 noise floor instead of the reference's 2e-15
             ("sparc_amp_config1_atol_1e-7", lambda: workloads.amp_workload(ctx, "c1", 16384, k, 2, atol=1e-7, e2e=False)),
-            ("sparc_amp_config4_sc_wave", lambda: workloads.amp_workload(ctx, "c4", 592, 2 if args.steps < 20 else 5, 1)),
+            # config 4 (SC wave, w = 65536): the explicit-design tensor-core path is the throughput path; the FFT
+            # path (exact fp32 arithmetic, 1e-4 parity per iteration) beside it on a smaller batch
+            ("sparc_amp_config4_sc_wave", lambda: workloads.amp_workload(ctx, "c4", 512, k, 2, precision="tc")),
+            ("sparc_amp_config4_sc_wave_fft_fp32", lambda: workloads.amp_workload(ctx, "c4", 148, 2, 1, e2e=False)),
             ("dense_amp_config3_tcgen05", lambda: workloads.dense_workload(ctx, 1024, k, 2)),
             ("ldpc_sparc_config5", lambda: workloads.c5_workload(ctx, 256, k, 2)),
         )

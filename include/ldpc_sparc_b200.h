@@ -254,6 +254,9 @@ int lsb_band_az_dev_f32(lsb_band_design *g, const float *y, float *out, int64_t 
 int lsb_band_amp_dev_f32(lsb_band_design *g, const float *y, int64_t n_frames,
                          const lsb_sparc_amp_params *p, const int32_t *idx0,
                          const lsb_sparc_amp_out *out, void *stream);
+/* host-pointer form, as lsb_sparc_amp_host_f32 */
+int lsb_band_amp_host_f32(lsb_band_design *g, const float *y, int64_t n_frames,
+                          const lsb_sparc_amp_params *p, int32_t *idx, int32_t *t_final, double *psi);
 
 /* ----------------------------- (4) SPARC, dense Gaussian design (sparc_sophie)
  * Replaces, for batches of frames that share one design matrix A [n x ML]

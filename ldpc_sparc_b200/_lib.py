@@ -82,6 +82,7 @@ SIGNATURES = {
     "lsb_sparc_amp_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
     "lsb_sparc_amp_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
     "lsb_sparc_amp_host_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.c_void_p, ct.c_void_p]),
+    "lsb_band_amp_host_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.c_void_p, ct.c_void_p]),
     # SPARC (dense Gaussian design) + section <-> bit glue
     "lsb_dense_design_create": (ct.c_int, [c_f64p, ct.c_int64, ct.c_int64, ct.c_int, ct.c_int, ct.POINTER(ct.c_void_p)]),
     "lsb_dense_design_destroy": (None, [ct.c_void_p]),

@@ -441,6 +441,11 @@ struct lsb_band_design {
         CUtensorMap mb_hi, mb_lo, mz_hi, mz_lo;
     };
     std::map<cudaStream_t, Work> work;
+    // host-pointer entry: its own stream and staging buffer
+    std::mutex host_mu;
+    cudaStream_t host_stream = nullptr;
+    void *host_stage = nullptr;
+    size_t host_stage_bytes = 0;
 };
 
 namespace {
@@ -713,6 +718,8 @@ void lsb_band_design_destroy(lsb_band_design *g)
     for (void *p : g->allocs) cudaFree(p);
     for (auto &kv : g->work)
         for (void *p : kv.second.allocs) cudaFree(p);
+    cudaFree(g->host_stage);
+    if (g->host_stream) cudaStreamDestroy(g->host_stream);
     delete g;
 }
 
@@ -819,6 +826,52 @@ int lsb_band_amp_dev_f32(lsb_band_design *g, const float *y, int64_t F, const ls
     if (po->beta_soft)
         LSB_CUDA(cudaMemcpyAsync(po->beta_soft, s.beta, (size_t)F * d.L * d.M * sizeof(float), cudaMemcpyDeviceToDevice, st));
     LSB_CUDA(cudaGetLastError());
+    return LSB_OK;
+}
+
+/* Host-pointer form (what a loop over the reference's sparc_decode, sparc.py:55-74, takes and returns): y [F, n] in
+ * host memory (pinned memory makes the copies asynchronous), idx [F, L] / t_final [F] / psi [F, Lc] (optional) back in
+ * host memory when the call returns.  One call at a time per handle. */
+int lsb_band_amp_host_f32(lsb_band_design *g, const float *y, int64_t F, const lsb_sparc_amp_params *pp, int32_t *idx,
+                          int32_t *t_final, double *psi)
+{
+    if (F == 0) return LSB_OK;
+    LSB_REQUIRE(g && y && pp && idx && t_final, "null pointer");
+    LSB_REQUIRE(F > 0 && F <= 65535, "frame count outside [1, 65535]");
+    int dev = -1;
+    LSB_CUDA(cudaGetDevice(&dev));
+    LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);
+    std::lock_guard<std::mutex> lock(g->host_mu);
+    if (!g->host_stream) LSB_CUDA(cudaStreamCreateWithFlags(&g->host_stream, cudaStreamNonBlocking));
+    const BandDev &d = g->dev;
+    const size_t by = (size_t)F * d.n * sizeof(float), bi = (size_t)F * d.L * sizeof(int32_t), bt = (size_t)F * sizeof(int32_t),
+                 bp = (size_t)F * d.Lc * sizeof(double);
+    const size_t need = by + bi + bt + bp + 64;
+    if (g->host_stage_bytes < need) {
+        LSB_CUDA(cudaStreamSynchronize(g->host_stream));
+        cudaFree(g->host_stage);
+        g->host_stage = nullptr;
+        g->host_stage_bytes = 0;
+        LSB_CUDA(cudaMalloc(&g->host_stage, need));
+        g->host_stage_bytes = need;
+    }
+    char *base = (char *)g->host_stage;
+    float *d_y = (float *)base;
+    double *d_psi = (double *)(base + ((by + 15) & ~(size_t)15));
+    int32_t *d_idx = (int32_t *)((char *)d_psi + bp);
+    int32_t *d_t = (int32_t *)((char *)d_idx + bi);
+    cudaStream_t st = g->host_stream;
+    LSB_CUDA(cudaMemcpyAsync(d_y, y, by, cudaMemcpyHostToDevice, st));
+    lsb_sparc_amp_out o{};
+    o.idx = d_idx;
+    o.t_final = d_t;
+    o.psi = d_psi;
+    int rc = lsb_band_amp_dev_f32(g, d_y, F, pp, nullptr, &o, st);
+    if (rc) return rc;
+    LSB_CUDA(cudaMemcpyAsync(idx, d_idx, bi, cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaMemcpyAsync(t_final, d_t, bt, cudaMemcpyDeviceToHost, st));
+    if (psi) LSB_CUDA(cudaMemcpyAsync(psi, d_psi, bp, cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
     return LSB_OK;
 }
 

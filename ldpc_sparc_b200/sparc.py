@@ -644,12 +644,13 @@ def sparc_amp(y, code_params, decode_params, awgn_var, rand_seed, beta0, Ab=None
     return res + (extra,) if extra else res
 
 
-def sparc_decode_host(y, code_params, decode_params, awgn_var, Ab, out=None):
+def sparc_decode_host(y, code_params, decode_params, awgn_var, Ab, out=None, precision="fp32"):
     """Batched fp32 AMP decode through the host-pointer C-ABI entry ``lsb_sparc_amp_host_f32``: the call a
     Monte-Carlo loop over the reference's ``sparc_decode`` (sparc.py:55-74, sparc_sim.py:21-24) makes, for
     ``F`` frames at once.  ``y``: float32 ``[F, n]`` in host memory (a numpy array, or a pinned CPU torch
     tensor for asynchronous copies).  Returns ``(idx [F, L] int32, t_final [F] int32, psi [F, Lc] float64)``
-    as numpy arrays (or fills the pinned torch tensors passed in ``out``); ``expect_err = psi.mean(1) >= 1e-3``."""
+    as numpy arrays (or fills the pinned torch tensors passed in ``out``); ``expect_err = psi.mean(1) >= 1e-3``.
+    ``precision='tc'``: the explicit-design tensor-core path (``lsb_band_amp_host_f32``)."""
     import torch
     check_decode_params(decode_params)
     _require_real_unmodulated(code_params)
@@ -673,7 +674,10 @@ def sparc_decode_host(y, code_params, decode_params, awgn_var, Ab, out=None):
     t_max, rtol, phi_est_method = map(decode_params.get, ['t_max', 'rtol', 'phi_est_method'])
     atol = float(decode_params.get('atol', 2 * np.finfo(float).resolution))
     params = _lib.AmpParams(float(awgn_var), float(rtol), atol, int(t_max), int(phi_est_method), int(_modulation(code_params)), 0)
-    _lib.check(_lib.lib().lsb_sparc_amp_host_f32(design.handle(), y_ptr, F, ct.byref(params), *ptrs), "lsb_sparc_amp_host_f32")
+    if precision == "tc":
+        _lib.check(_lib.lib().lsb_band_amp_host_f32(design.band_handle(), y_ptr, F, ct.byref(params), *ptrs), "lsb_band_amp_host_f32")
+    else:
+        _lib.check(_lib.lib().lsb_sparc_amp_host_f32(design.handle(), y_ptr, F, ct.byref(params), *ptrs), "lsb_sparc_amp_host_f32")
     return idx, t_final, psi
 
 

@@ -147,3 +147,24 @@ def test_band_config4_sc_wave_matches_reference_golden(gold):
         assert T64[f] - 1 <= Ttc[f] <= dp["t_max"] - 1
         Tc = int(min(T64[f], Ttc[f]))
         assert rel_err(extc["tau"][f, :Tc], ex64["tau"][f, :Tc]) < kTauTol
+
+
+def test_band_host_entry_equals_device_path():
+    """lsb_band_amp_host_f32 (host y in; decisions, t_final, psi out) against the device-pointer entry."""
+    import torch
+    cp = dict(P=15.0, R=1.4, L=256, M=32, spatially_coupled=True, omega=2, Lambda=8)
+    dp = dict(t_max=25)
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, 1.0, [1, 2])
+    sparc.check_decode_params(dp)
+    L, M, n = cp["L"], cp["M"], cp["n"]
+    rng = np.random.RandomState(9)
+    F = 37
+    idx0 = rng.randint(0, M, (F, L))
+    b0 = np.zeros((F, L * M))
+    b0[np.arange(F)[:, None], np.arange(L)[None, :] * M + idx0] = 1
+    y = (Ab(b0) + rng.randn(F, n)).astype(np.float32)
+    idx_h, T_h, psi_h = sparc.sparc_decode_host(y, cp, dp, 1.0, Ab, precision="tc")
+    idx_d, T_d, _, psi_d = sparc.sparc_amp(torch.from_numpy(y).cuda(), cp, dp, 1.0, [1, 2], None, Ab, Az, precision="tc")
+    assert np.array_equal(idx_h, idx_d.cpu().numpy()) and np.array_equal(T_h, T_d.cpu().numpy())
+    assert np.array_equal(psi_h, psi_d.cpu().numpy())
+    assert (idx_h != idx0).mean() < 5e-2

@@ -181,7 +181,7 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
     bits, idx, T, _, _ = res["out"]
     frame_iters_rank = float(T.sum().item())
     sec_err, frame_iters, n_frames = ctx.sum_over_ranks([float((idx != idx0).sum().item()), frame_iters_rank, F])
-    hbm, _, src = peaks()
+    hbm, tens, src = peaks()
     achieved = bytes_per_frame_iter * frame_iters_rank / (ms * 1e-3) / 1e9      # this rank's kernel
     out = {
         "workload": "sparc_public AMP decode, config %s L=%d M=%d R=1.5 (n=%d), t_max=%d, %d frames per GPU sharing one design"
@@ -198,7 +198,23 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
                               % bytes_per_frame_iter},
         "clocks": clocks,
     }
-    if e2e and precision == "fp32":
+    if precision == "tc":
+        # explicit block-banded design on the tensor cores (csrc/sparc_band_tc.cu): the bound is the tcgen05 pipe.
+        # Algorithmic flops: 2 per stored design entry per product; a frame that runs T iterations does T products
+        # A^T z and T - 1 products A beta.  The split-bf16 kernel issues 3x that (plus tile padding).
+        d = Ab.design
+        nnz = float(np.count_nonzero(d.Wm)) * d.Mr * d.Mc
+        flops = 2.0 * nnz * (2.0 * frame_iters_rank - F)
+        ach = flops / (ms * 1e-3) / 1e12
+        out["dtype"] = "bf16x3 (split) products, f32 elsewhere"
+        out["roofline_hbm_model"] = out["roofline"]
+        out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tens, "unit": "TFLOP/s", "frac": ach / tens,
+                           "peak_source": src, "traffic": None,
+                           "model": "%.2f GFLOP per frame-iteration (2 flops per stored design entry and product, %d non-zero "
+                                    "blocks of %d x %d; A beta skipped in a frame's first iteration); algorithmic flops -- the "
+                                    "split-bf16 kernel issues 3x" % (4.0 * nnz / 1e9, int(np.count_nonzero(d.Wm)), d.Mr, d.Mc)}
+        out["design_bytes"] = int(_lib_bytes(d))
+    if e2e and precision in ("fp32", "tc"):
         h_y = torch.empty(y.shape, dtype=torch.float32).pin_memory()
         h_y.copy_(y)
         h_idx = torch.empty(idx.shape, dtype=torch.int32).pin_memory()
@@ -206,7 +222,7 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
         h_psi = torch.empty((F, Ab.design.Lc), dtype=torch.float64).pin_memory()
 
         def e2e_step():
-            sparc.sparc_decode_host(h_y, cp, dp, 1.0, Ab, out=(h_idx, h_T, h_psi))
+            sparc.sparc_decode_host(h_y, cp, dp, 1.0, Ab, out=(h_idx, h_T, h_psi), precision=precision)
 
         n_e2e = max(1, min(steps, 3))
         e_ms, _ = timed(ctx, e2e_step, n_e2e, 1, host_sync=True)
@@ -215,10 +231,16 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
                       "h2d_bytes_per_step": h_y.numel() * 4,
                       "d2h_bytes_per_step": h_idx.numel() * 4 + h_T.numel() * 4 + h_psi.numel() * 8,
                       "ms_per_step": e_ms / n_e2e,
-                      "api": "lsb_sparc_amp_host_f32 (C-ABI, pinned host y in; decisions, t_final, psi out)"}
+                      "api": "%s (C-ABI, pinned host y in; decisions, t_final, psi out)"
+                             % ("lsb_band_amp_host_f32" if precision == "tc" else "lsb_sparc_amp_host_f32")}
     else:
         out["e2e"] = None
     return out
+
+
+def _lib_bytes(design):
+    from ldpc_sparc_b200 import _lib
+    return _lib.lib().lsb_band_design_bytes(design.band_handle())
 
 
 def traffic_entry(key):
