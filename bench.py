@@ -438,7 +438,7 @@ def main():
             ("sparc_amp_config4_sc_wave", lambda: workloads.amp_workload(ctx, "c4", 512, k, 2, precision="tc")),
             ("sparc_amp_config4_sc_wave_fft_fp32", lambda: workloads.amp_workload(ctx, "c4", 148, 2, 1, e2e=False)),
             ("dense_amp_config3_tcgen05", lambda: workloads.dense_workload(ctx, 1024, k, 2)),
-            ("ldpc_sparc_config5", lambda: workloads.c5_workload(ctx, 256, k, 2)),
+            ("ldpc_sparc_config5", lambda: workloads.c5_workload(ctx, 512, k, 2)),
         )
         for key, fn in plan:
             try:

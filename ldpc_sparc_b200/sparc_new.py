@@ -334,10 +334,14 @@ def _amp_iteration(eng, y, st, P, L, M, sq, first, s_out=None):
 FUSED_TC_AMP = True       # tensor-core mode: the whole AMP loop in one C call (lsb_tc_amp_dev_f32)
 
 
+def _fused_tc_ok(eng, L, M, t_max, F):
+    return eng.tc and FUSED_TC_AMP and 2 <= M <= 128 and (L * M) % 32 == 0 and t_max >= 1 and F > 0
+
+
 def _amp_device(eng, yd, P, L, M, sq, t_max, return_trace=False):
     """t_max AMP iterations on device frames ``yd [F, n]``; returns device tensors
     ``(beta, s[, tau^2 per iteration])``."""
-    if eng.tc and FUSED_TC_AMP and 2 <= M <= 128 and (L * M) % 32 == 0 and t_max >= 1 and yd.shape[0] > 0:
+    if _fused_tc_ok(eng, L, M, t_max, yd.shape[0]):
         # three launches per iteration, no Python in the loop: A beta -> residual (+ bf16 split of z) ->
         # A^T z with the denoiser (+ bf16 split of beta) as the GEMM epilogue
         t = eng.torch
@@ -518,20 +522,27 @@ def sparc_ldpc_decode(y, sparc_params, ldpc_params, decode_params, ldpc_bool, le
     c = code(ldpc_params["standard"], ldpc_params["rate"], ldpc_params["z"]) if ldpc_bool else None
     logM = int(round(np.log2(M)))
 
+    def finish(beta, s, Fc):
+        if ldpc_bool:
+            _, llr = eng.section_to_bit(beta, L, M, sq, want_probs=False)
+            return eng.hard_bits(eng.bp(llr, c, 200), c)
+        idx = s.reshape(Fc, L, M).argmax(dim=2)                   # MAP on s (sparc_new.py:79-80)
+        shifts = eng.torch.arange(logM - 1, -1, -1, device=eng.dev)
+        return ((idx.unsqueeze(-1) >> shifts) & 1).reshape(Fc, -1).to(eng.torch.uint8)
+
     def run(yc):
         st = _amp_state(eng, yc, L, M)
         s = eng.empty(yc.shape[0], L * M)
         for t in range(decode_params['t_max']):
             _amp_iteration(eng, yc, st, P, L, M, sq, t == 0, s)
             yield
-        if ldpc_bool:
-            _, llr = eng.section_to_bit(st["beta"], L, M, sq, want_probs=False)
-            return eng.hard_bits(eng.bp(llr, c, 200), c)
-        idx = s.reshape(yc.shape[0], L, M).argmax(dim=2)          # MAP on s (sparc_new.py:79-80)
-        shifts = eng.torch.arange(logM - 1, -1, -1, device=eng.dev)
-        return ((idx.unsqueeze(-1) >> shifts) & 1).reshape(yc.shape[0], -1).to(eng.torch.uint8)
+        return finish(st["beta"], s, yc.shape[0])
 
-    bits = _drive(eng, yd, run)
+    if _fused_tc_ok(eng, L, M, decode_params['t_max'], yd.shape[0]):
+        beta, s = _amp_device(eng, yd, P, L, M, sq, decode_params['t_max'])     # the AMP loop as one C call
+        bits = finish(beta, s, yd.shape[0])
+    else:
+        bits = _drive(eng, yd, run)
     if ldpc_bool:
         return _finish_bits(bits, single)
     bits = bits.bool().cpu().numpy()
