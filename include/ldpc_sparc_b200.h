@@ -238,9 +238,9 @@ int lsb_sparc_amp_host_f32(lsb_sparc_design *g, const float *y, int64_t n_frames
 
 /* ---- (3b) the same design stored explicitly, products on the tensor cores (csrc/sparc_band_tc.cu)
  * For designs whose blocks keep few of the w transform outputs (spatially coupled: BASELINE config 4 keeps 332 of
- * 65536 per block) the blocks of A are generated once on the device from the closed form above and kept as bf16
+ * 65536 per block) the blocks of A are generated once on the device from the closed form above and kept as fp16
  * hi / lo pairs in both orientations; A beta and A^T z for a frame batch are block-banded tcgen05 GEMMs (three
- * bf16 products per operand pair, fp32 accumulation) and the rest of sparc_amp (sparc.py:931-999) runs in two
+ * fp16 products per operand pair, fp32 accumulation) and the rest of sparc_amp (sparc.py:931-999) runs in two
  * memory-bound kernels per iteration.  Same arguments and outputs as lsb_sparc_design_create /
  * lsb_sparc_ab_dev_f32 / lsb_sparc_az_dev_f32 / lsb_sparc_amp_dev_f32 (modulation <= 1 only; M <= 1024; L*M a
  * multiple of 8).  Device memory: lsb_band_design_bytes(). */
@@ -320,10 +320,10 @@ int lsb_integrated_onsager_dev_f64(const double *beta, const double *vk, const d
                                    int64_t F, int L, int M, double sqrt_nPl, void *stream);
 
 /* Tensor-core variant of the two dense products (tcgen05 + TMEM + TMA, csrc/dense_tc.cu):
- * operands split into two bf16 terms, three MMAs per tile into one fp32 accumulator, so
+ * operands split into two fp16 terms, three MMAs per tile into one fp32 accumulator, so
  * results carry ~16 mantissa bits (about 2e-5 relative), enough for the 1e-4 bound on
  * tau^2 / beta.  fp32 in / fp32 out; n and ML must be multiples of 8.  The handle holds
- * bf16 hi/lo copies of A and of A^T (8 bytes per entry in total). */
+ * fp16 hi/lo copies of A and of A^T (8 bytes per entry in total). */
 typedef struct lsb_tc_design lsb_tc_design;
 int lsb_tc_design_create(const double *A /* host, row-major [n, ML] */, int64_t n, int64_t ML,
                          lsb_tc_design **out);

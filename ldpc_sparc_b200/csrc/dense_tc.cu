@@ -3,10 +3,13 @@
 //   C[f, r] = sum_k W[r, k] * X[f, k]        W = A (r = row of A, k < ML)    -> A beta   (sparc_new.py:903)
 //                                            W = A^T (r = column of A, k < n) -> A^T z   (sparc_new.py:907)
 // for a batch of F frames that share the design matrix.  The reference computes these
-// in float64; north_star asks for 1e-4 relative on tau^2 / beta, which plain bf16
-// (8-bit mantissa) cannot give.  Each operand is therefore split into two bf16 terms
-// (x = hi + lo, 16 mantissa bits) and three MMAs accumulate into the same fp32 TMEM
-// tile:  W_hi X_hi + W_lo X_hi + W_hi X_lo  (the lo*lo term is below 2^-16 relative).
+// in float64; north_star asks for 1e-4 relative on tau^2 / beta, which one 16-bit operand
+// (8 or 11 mantissa bits) cannot give.  Each operand is therefore split into two fp16 terms
+// (x = hi + lo, 22 mantissa bits; the design is stored times a power of two so that its lo
+// terms stay normal numbers) and three MMAs accumulate into the same fp32 TMEM tile:
+// W_hi X_hi + W_lo X_hi + W_hi X_lo  (the lo*lo term is below 2^-22 relative).  The tensor
+// core rounds its accumulator toward zero, so K is accumulated in TMEM 8 K blocks at a time
+// and the chunks are summed in registers with round-to-nearest (tc_gemm.cuh, kChunkKb).
 //
 // Kernel anatomy (persistent, one CTA per SM; a work item is one 128 x 128 output tile over
 // one K range, K streamed in 64-element blocks; K is split when the tile count alone would
@@ -15,20 +18,23 @@
 //                      SWIZZLE_128B) per stage, 3-stage ring, mbarrier expect_tx
 //   warp 1, one lane : MMA issuer    - 4 k-steps x 3 tcgen05.mma.cta_group::1.kind::f16
 //                      (M = 128, N = 128, K = 16) per stage, tcgen05.commit frees the stage
-//   warp 2           : TMEM allocator (2 accumulators x 128 fp32 columns)
+//   warp 2           : TMEM allocator (ring of 4 accumulators x 128 fp32 columns)
 //   warps 4..7       : epilogue      - tcgen05.ld 32x32b.x32, transposed store C[f, r]
-//                      (lanes = consecutive r: coalesced); drains accumulator j & 1 while
-//                      the MMAs of the CTA's next item fill the other one
+//                      (lanes = consecutive r: coalesced); takes over the accumulator of K chunk j
+//                      (summing the chunks of an item in registers) while the MMAs of the next
+//                      chunks fill the other three
 #include "tc_gemm.cuh"
 
+#include <algorithm>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <new>
 
 
-// One operand W [rows, K] kept as bf16 hi/lo + its TMA maps
+// One operand W [rows, K] kept as fp16 hi/lo + its TMA maps
 struct TcOperand {
-    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    tc_t *hi = nullptr, *lo = nullptr;
     CUtensorMap map_hi, map_lo;
     int64_t rows = 0, K = 0;
 };
@@ -36,19 +42,23 @@ struct TcOperand {
 struct lsb_tc_design {
     int device = 0;
     int64_t n = 0, ML = 0;
+    // The stored operands are A * 2^shift (exact), shift chosen so that the largest entry lands in [8, 16): the lo
+    // terms of an fp16 pair then stay in the normal range (an i.i.d. N(0, 1/n) design has entries ~ 0.01, whose lo
+    // terms would be fp16 subnormals with 10 bits fewer).  Epilogues multiply the accumulators by out_scale = 2^-shift.
+    float out_scale = 1.0f;
     TcOperand A, At;              // A: [n, ML] (K = ML) for A beta;  At: [ML, n] (K = n) for A^T z
     std::mutex mu;
     // Staging (split frame operand, K-split partials) is kept per stream: calls on one stream are
     // ordered by the stream itself, calls on different streams (two half-batches whose element-wise
     // kernels overlap each other's GEMMs) never share a buffer.
     struct Staging {
-        __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr;
+        tc_t *x_hi = nullptr, *x_lo = nullptr;
         size_t x_cap = 0;
         float *part = nullptr;
         size_t part_cap = 0;
-        // fused AMP chain (lsb_tc_amp_dev_f32): z and its bf16 pair, beta's bf16 pair, scalars
+        // fused AMP chain (lsb_tc_amp_dev_f32): z and its fp16 pair, beta's fp16 pair, scalars
         float *z = nullptr, *bsq_part = nullptr;
-        __nv_bfloat16 *z_hi = nullptr, *z_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+        tc_t *z_hi = nullptr, *z_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
         double *tau = nullptr;
         size_t amp_frames = 0;
     };
@@ -73,14 +83,14 @@ int pick_splits(int n_tiles, int num_kb, int sms)
     return splits;
 }
 
-int build_operand(TcOperand *op, const double *d_src, int64_t rows, int64_t K)
+int build_operand(TcOperand *op, const double *d_src, int64_t rows, int64_t K, double pre)
 {
     const size_t count = (size_t)rows * K;
     // TMA needs the row pitch to be a multiple of 16 bytes
-    LSB_REQUIRE((K * sizeof(__nv_bfloat16)) % 16 == 0, "inner dimension %lld must be a multiple of 8", (long long)K);
-    LSB_CUDA(cudaMalloc((void **)&op->hi, count * sizeof(__nv_bfloat16)));
-    LSB_CUDA(cudaMalloc((void **)&op->lo, count * sizeof(__nv_bfloat16)));
-    split_kernel<double><<<lsb::sm_count() * 8, 256>>>(d_src, op->hi, op->lo, (long long)count);
+    LSB_REQUIRE((K * sizeof(tc_t)) % 16 == 0, "inner dimension %lld must be a multiple of 8", (long long)K);
+    LSB_CUDA(cudaMalloc((void **)&op->hi, count * sizeof(tc_t)));
+    LSB_CUDA(cudaMalloc((void **)&op->lo, count * sizeof(tc_t)));
+    split_kernel<double><<<lsb::sm_count() * 8, 256>>>(d_src, op->hi, op->lo, (long long)count, pre);
     lsb::count_launch();
     LSB_CUDA(cudaGetLastError());
     op->rows = rows;
@@ -109,15 +119,15 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
         cudaFree(sg.x_lo);
         sg.x_hi = sg.x_lo = nullptr;
         sg.x_cap = 0;
-        LSB_CUDA(cudaMalloc((void **)&sg.x_hi, need * sizeof(__nv_bfloat16)));
-        LSB_CUDA(cudaMalloc((void **)&sg.x_lo, need * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.x_hi, need * sizeof(tc_t)));
+        LSB_CUDA(cudaMalloc((void **)&sg.x_lo, need * sizeof(tc_t)));
         sg.x_cap = need;
     }
     const long long count = (long long)F * W.K;
     if (count % 8 == 0 && ((uintptr_t)x & 15) == 0)
         split8_kernel<<<lsb::sm_count() * 8, 256, 0, st>>>((const float4 *)x, (uint4 *)sg.x_hi, (uint4 *)sg.x_lo, count / 8);
     else
-        split_kernel<float><<<lsb::sm_count() * 4, 256, 0, st>>>(x, sg.x_hi, sg.x_lo, count);
+        split_kernel<float><<<lsb::sm_count() * 4, 256, 0, st>>>(x, sg.x_hi, sg.x_lo, count, 1.0);
     lsb::count_launch();
     CUtensorMap mx_hi, mx_lo;
     int rc = make_map(&mx_hi, sg.x_hi, (uint64_t)F, (uint64_t)W.K);
@@ -146,7 +156,7 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
     const int n_items = n_tiles * splits;
     tc_gemm_kernel<<<n_items < sms ? n_items : sms, kThreadsTc, kSmemBytes, st>>>(
         W.map_hi, W.map_lo, mx_hi, mx_lo, dst, (int)W.rows, (int)F, (int)W.K, n_row_tiles, n_f_tiles, splits,
-        (long long)out_count);
+        (long long)out_count, g->out_scale);
     if (splits > 1) {
         lsb::count_launch();
         LSB_CUDA(cudaGetLastError());
@@ -160,13 +170,14 @@ int tc_product(lsb_tc_design *g, const TcOperand &W, const float *x, float *out,
 
 template <int M>
 void launch_denoise_gemm(int grid, cudaStream_t st, const CUtensorMap &w_hi, const CUtensorMap &w_lo, const CUtensorMap &x_hi,
-                         const CUtensorMap &x_lo, float *beta, int has_beta, __nv_bfloat16 *b_hi, __nv_bfloat16 *b_lo,
+                         const CUtensorMap &x_lo, float *beta, int has_beta, tc_t *b_hi, tc_t *b_lo,
                          float *s_out, const double *tau, float *bsq_part, float sq, int rows, int F, int K, int n_row_tiles,
-                         int n_f_tiles)
+                         int n_f_tiles, float out_scale)
 {
     lsb::ensure_dynamic_smem(tc_gemm_denoise_kernel<M>, kSmemBytes);
     tc_gemm_denoise_kernel<M><<<grid, kThreadsTc, kSmemBytes, st>>>(w_hi, w_lo, x_hi, x_lo, beta, has_beta, b_hi, b_lo, s_out,
-                                                                    tau, bsq_part, sq, rows, F, K, n_row_tiles, n_f_tiles);
+                                                                    tau, bsq_part, sq, rows, F, K, n_row_tiles, n_f_tiles,
+                                                                    out_scale);
 }
 
 }  // namespace
@@ -211,10 +222,10 @@ int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M
         sg.tau = nullptr;
         sg.amp_frames = 0;
         LSB_CUDA(cudaMalloc((void **)&sg.z, (size_t)F * n * sizeof(float)));
-        LSB_CUDA(cudaMalloc((void **)&sg.z_hi, (size_t)F * n * sizeof(__nv_bfloat16)));
-        LSB_CUDA(cudaMalloc((void **)&sg.z_lo, (size_t)F * n * sizeof(__nv_bfloat16)));
-        LSB_CUDA(cudaMalloc((void **)&sg.b_hi, (size_t)F * ML * sizeof(__nv_bfloat16)));
-        LSB_CUDA(cudaMalloc((void **)&sg.b_lo, (size_t)F * ML * sizeof(__nv_bfloat16)));
+        LSB_CUDA(cudaMalloc((void **)&sg.z_hi, (size_t)F * n * sizeof(tc_t)));
+        LSB_CUDA(cudaMalloc((void **)&sg.z_lo, (size_t)F * n * sizeof(tc_t)));
+        LSB_CUDA(cudaMalloc((void **)&sg.b_hi, (size_t)F * ML * sizeof(tc_t)));
+        LSB_CUDA(cudaMalloc((void **)&sg.b_lo, (size_t)F * ML * sizeof(tc_t)));
         LSB_CUDA(cudaMalloc((void **)&sg.bsq_part, (size_t)F * az_row_tiles * sizeof(float)));
         LSB_CUDA(cudaMalloc((void **)&sg.tau, (size_t)F * sizeof(double)));
         sg.amp_frames = (size_t)F;
@@ -241,7 +252,7 @@ int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M
         if (t > 0) {
             tc_gemm_kernel<<<ab_items < sms ? ab_items : sms, kThreadsTc, kSmemBytes, st>>>(
                 g->A.map_hi, g->A.map_lo, mb_hi, mb_lo, sg.part, n, (int)F, ML, ab_row_tiles, n_f_tiles, splits,
-                (long long)out_count);
+                (long long)out_count, g->out_scale);
             lsb::count_launch();
         }
         tc_residual_kernel<<<(unsigned)F, kThreadsTc, 0, st>>>(y, sg.part, splits, (long long)out_count, sg.z, sg.z_hi, sg.z_lo,
@@ -254,7 +265,8 @@ int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M
 #define LSB_DN(MM)                                                                                                       \
     case MM:                                                                                                             \
         launch_denoise_gemm<MM>(grid, st, g->At.map_hi, g->At.map_lo, mz_hi, mz_lo, beta_out, t > 0, sg.b_hi, sg.b_lo, so, \
-                                sg.tau, sg.bsq_part, (float)sqrt_nPl, ML, (int)F, n, az_row_tiles, n_f_tiles);           \
+                                sg.tau, sg.bsq_part, (float)sqrt_nPl, ML, (int)F, n, az_row_tiles, n_f_tiles,            \
+                                g->out_scale);                                                                           \
         break;
         switch (M) {
             LSB_DN(2) LSB_DN(4) LSB_DN(8) LSB_DN(16) LSB_DN(32) LSB_DN(64) LSB_DN(128)
@@ -295,10 +307,24 @@ int lsb_tc_design_create(const double *A, int64_t n, int64_t ML, lsb_tc_design *
         lsb::set_error("uploading the design matrix: %s", cudaGetErrorString(e));
         rc = LSB_ERR_CUDA;
     }
-    if (!rc) rc = build_operand(&g->A, d_A, n, ML);
-    if (!rc) rc = build_operand(&g->At, d_At, ML, n);
+    double pre = 1.0;
+#if LSB_TC_HALF
+    {
+        double mx = 0.0;
+        for (size_t i = 0; i < count; ++i) mx = std::max(mx, std::fabs(A[i]));
+        if (mx > 0.0 && std::isfinite(mx)) {
+            int e = 0;
+            std::frexp(mx, &e);                       // mx = m 2^e, m in [0.5, 1)
+            const int shift = std::min(24, std::max(-24, 4 - e));     // mx 2^shift in [8, 16)
+            pre = std::ldexp(1.0, shift);
+        }
+    }
+#endif
+    g->out_scale = (float)(1.0 / pre);
+    if (!rc) rc = build_operand(&g->A, d_A, n, ML, pre);
+    if (!rc) rc = build_operand(&g->At, d_At, ML, n, pre);
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) {
-        lsb::set_error("building the bf16 operands: %s", cudaGetErrorString(cudaGetLastError()));
+        lsb::set_error("building the fp16 operands: %s", cudaGetErrorString(cudaGetLastError()));
         rc = LSB_ERR_CUDA;
     }
     cudaFree(d_A);

@@ -7,16 +7,16 @@
 // coupled design keeps very few: BASELINE config 4 (sparc_demo_sc_decode_wave) has Mr = 332 rows per block out of
 // w = 65536, 192 non-zero blocks, so one iteration is 384 transforms of 65536 points (~1 GFLOP of butterflies
 // through a 256 KB buffer that does not fit shared memory) to produce what a 332 x 32768 matrix block produces
-// directly.  Stored explicitly the whole design is 192 x 332 x 32768 entries = 4.2 GB per bf16 array, which a B200
+// directly.  Stored explicitly the whole design is 192 x 332 x 32768 entries = 4.2 GB per fp16 array, which a B200
 // holds many times over, and A beta / A^T z over a frame batch become block-banded GEMMs on the tcgen05 pipeline
-// of tc_gemm.cuh (split-bf16 operands, fp32 accumulation in TMEM): 8.4 GFLOP per frame-iteration, 25 issued.
+// of tc_gemm.cuh (split-fp16 operands, fp32 accumulation in TMEM): 8.4 GFLOP per frame-iteration, 25 issued.
 //
 // Layout.  Arow [Lr * Mr_pad, kmax] holds, for row block r, the blocks (r, clo_r .. chi_r) side by side (K pitch
 // Mc_pad per block, zero padded), rows padded to whole 128-row tiles; Acol [L M, kz] holds, for column block c, the
 // blocks (rlo_c .. rhi_c, c) transposed, side by side along K (= the rows of z they multiply, which are contiguous).
 // A work item (TcItem) is one 128 x 128 output tile of one block (A beta: partial p = c - clo_r, summed in index
 // order by the residual kernel) or of one column block (A^T z: complete).  Everything else of the iteration is two
-// memory-bound kernels (band_residual_kernel, band_denoise_kernel) that also produce the bf16 operand pairs.
+// memory-bound kernels (band_residual_kernel, band_denoise_kernel) that also produce the fp16 operand pairs.
 #include "tc_gemm.cuh"
 
 #include <algorithm>
@@ -32,7 +32,7 @@ constexpr int kMaxLr = 64, kMaxLc = 64;
 
 struct BandDev {
     int L, M, n, Lr, Lc, Mr, Mc;
-    int Mr_p, n_pitch;                        // bf16 pair of z: row block r starts at r * Mr_p (Mr rounded up to 8: TMA
+    int Mr_p, n_pitch;                        // fp16 pair of z: row block r starts at r * Mr_p (Mr rounded up to 8: TMA
                                               // needs 16-byte aligned box starts), row pitch n_pitch = Lr * Mr_p
     const double *W;                          // [Lr, Lc]
     const int *clo, *chi;                     // [Lr] first / last non-zero column block of row block r
@@ -46,7 +46,7 @@ struct BandParams {
 // per-call state and outputs (device pointers)
 struct BandState {
     float *beta, *atz, *z, *part;
-    __nv_bfloat16 *b_hi, *b_lo, *z_hi, *z_lo;
+    tc_t *b_hi, *b_lo, *z_hi, *z_lo;
     double *psi, *psi_prev, *phi, *tau;
     int *done, *n_done;
     long long part_stride;                    // elements between two partials of A beta
@@ -79,16 +79,16 @@ __device__ __forceinline__ double design_entry(double scale, unsigned o0, unsign
     return scale * cospi((double)k / (double)(2u * w));
 }
 
-__device__ __forceinline__ void store_split(__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t e, double v)
+__device__ __forceinline__ void store_split(tc_t *hi, tc_t *lo, size_t e, double v)
 {
     const float x = (float)v;
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const tc_t h = to_tc(x);
     hi[e] = h;
-    lo[e] = __float2bfloat16_rn((float)(v - (double)__bfloat162float(h)));
+    lo[e] = to_tc((float)(v - (double)from_tc(h)));
 }
 
 __global__ void gen_rows_kernel(BandDev d, const uint32_t *__restrict__ order0, const uint32_t *__restrict__ order1, unsigned w,
-                                int Mr_pad, int Mc_pad, long long kmax, __nv_bfloat16 *hi, __nv_bfloat16 *lo)
+                                int Mr_pad, int Mc_pad, long long kmax, tc_t *hi, tc_t *lo)
 {
     const long long total = (long long)d.Lr * Mr_pad * kmax;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -109,7 +109,7 @@ __global__ void gen_rows_kernel(BandDev d, const uint32_t *__restrict__ order0, 
 }
 
 __global__ void gen_cols_kernel(BandDev d, const int *__restrict__ rlo, const int *__restrict__ rhi, const uint32_t *__restrict__ order0,
-                                const uint32_t *__restrict__ order1, unsigned w, long long kz, __nv_bfloat16 *hi, __nv_bfloat16 *lo)
+                                const uint32_t *__restrict__ order1, unsigned w, long long kz, tc_t *hi, tc_t *lo)
 {
     const long long total = (long long)d.L * d.M * kz;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -130,8 +130,8 @@ __global__ void gen_cols_kernel(BandDev d, const int *__restrict__ rlo, const in
 }
 
 // ---------------------------------------------------------------- plain operand split (operators Ab / Az)
-// x [F, len] fp32 -> bf16 pair with row pitch `pitch`; entry i goes to (i / blk) * blk_p + i % blk
-__global__ void band_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+// x [F, len] fp32 -> fp16 pair with row pitch `pitch`; entry i goes to (i / blk) * blk_p + i % blk
+__global__ void band_split_kernel(const float *__restrict__ x, tc_t *__restrict__ hi, tc_t *__restrict__ lo,
                                   long long F, int len, int pitch, int blk, int blk_p)
 {
     const long long total = F * (long long)len;
@@ -139,10 +139,10 @@ __global__ void band_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__
         const long long f = e / len;
         const int i = (int)(e - f * len);
         const float v = x[e];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const tc_t h = to_tc(v);
         const int o = (i / blk) * blk_p + i % blk;
         hi[f * pitch + o] = h;
-        lo[f * pitch + o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        lo[f * pitch + o] = to_tc(v - from_tc(h));
     }
 }
 
@@ -166,7 +166,7 @@ __global__ void band_sum_partials_kernel(BandDev d, const float *__restrict__ pa
 //   [t >= 2: early-stop test of iteration t - 1 (:984-986); a stopped frame is frozen from here on]
 //   gamma_r = sum_c W_rc psi_c / Lc;  t > 0: z_r <- y_r - (A beta)_r + (gamma_r / phi_prev_r) z_r   (t = 0: z = y)
 //   phi_r = awgn_var + gamma_r | mean(z_r^2);   tau_c = (L / Mr) / sum_r W_rc / phi_r
-//   operand of A^T: z_r / phi_r as a bf16 pair
+//   operand of A^T: z_r / phi_r as a fp16 pair
 __global__ void __launch_bounds__(kBandThreads)
 band_residual_kernel(BandDev d, BandParams p, BandState s, const float *__restrict__ y_all, long long F, int t)
 {
@@ -246,13 +246,13 @@ band_residual_kernel(BandDev d, BandParams p, BandState s, const float *__restri
         tau_g[tid] = tc;
         if (s.tau_trace) s.tau_trace[(f * p.t_max + t) * d.Lc + tid] = tc;
     }
-    __nv_bfloat16 *zh = s.z_hi + f * d.n_pitch, *zl = s.z_lo + f * d.n_pitch;
+    tc_t *zh = s.z_hi + f * d.n_pitch, *zl = s.z_lo + f * d.n_pitch;
     for (int i = tid; i < d.n; i += kBandThreads) {
         const int r = i / d.Mr, o = r * d.Mr_p + (i - r * d.Mr);
         const float v = z[i] * (float)(1.0 / phi[r]);
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const tc_t h = to_tc(v);
         zh[o] = h;
-        zl[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        zl[o] = to_tc(v - from_tc(h));
     }
 }
 
@@ -260,7 +260,7 @@ band_residual_kernel(BandDev d, BandParams p, BandState s, const float *__restri
 // One CTA per (column block, frame), one warp per section (M >= 32: PL = M / 32 entries per lane; M < 32: 32 / M
 // sections per warp pass):  s = beta + tau_c (A^T z)_c  (:972),  beta = softmax(s / tau_c)  (:402-432, per-section max
 // shift), psi_c = sum beta (1 - beta) / (L / Lc)  (:976-978), nmse (:979-981), the MAP decision argmax s (:997, kept
-// from the last iteration a frame runs), beta as fp32 and as the bf16 pair of the next A beta.
+// from the last iteration a frame runs), beta as fp32 and as the fp16 pair of the next A beta.
 template <int PL>
 __global__ void __launch_bounds__(kBandThreads)
 band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
@@ -275,7 +275,7 @@ band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
     const bool has_beta = t > 0;
     double psi_part = 0.0, nm_part = 0.0;
     if (PL > 0) {
-        // a lane owns PL CONSECUTIVE entries of the section (16-byte loads / stores for PL >= 4, bf16 pairs packed)
+        // a lane owns PL CONSECUTIVE entries of the section (16-byte loads / stores for PL >= 4, fp16 pairs packed)
         constexpr int P_ = PL > 0 ? PL : 1;
         for (int sec = warp; sec < secs; sec += kBandThreads / 32) {
             const size_t a0 = base_c + (size_t)sec * d.M + (size_t)lane * P_;
@@ -333,9 +333,9 @@ band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float v0 = sv[k + 2 * u], v1 = sv[k + 2 * u + 1];
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                        h[u] = pack_bf16(h0, h1);
-                        l[u] = pack_bf16(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+                        const tc_t h0 = to_tc(v0), h1 = to_tc(v1);
+                        h[u] = pack_pair(h0, h1);
+                        l[u] = pack_pair(to_tc(v0 - from_tc(h0)), to_tc(v1 - from_tc(h1)));
                     }
                     *reinterpret_cast<float4 *>(s.beta + a0 + k) = make_float4(sv[k], sv[k + 1], sv[k + 2], sv[k + 3]);
                     *reinterpret_cast<float4 *>(s.beta + a0 + k + 4) = make_float4(sv[k + 4], sv[k + 5], sv[k + 6], sv[k + 7]);
@@ -346,9 +346,9 @@ band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
 #pragma unroll
                 for (int k = 0; k < P_; ++k) {
                     s.beta[a0 + k] = sv[k];
-                    const __nv_bfloat16 h = __float2bfloat16_rn(sv[k]);
+                    const tc_t h = to_tc(sv[k]);
                     s.b_hi[a0 + k] = h;
-                    s.b_lo[a0 + k] = __float2bfloat16_rn(sv[k] - __bfloat162float(h));
+                    s.b_lo[a0 + k] = to_tc(sv[k] - from_tc(h));
                 }
             }
             if (lane == 0) s.idx[f * d.L + sec0 + sec] = arg;
@@ -377,9 +377,9 @@ band_denoise_kernel(BandDev d, BandParams p, BandState s, int t)
             if (live) {
                 const float inv = 1.0f / sum, b = e * inv;
                 s.beta[a] = b;
-                const __nv_bfloat16 h = __float2bfloat16_rn(b);
+                const tc_t h = to_tc(b);
                 s.b_hi[a] = h;
-                s.b_lo[a] = __float2bfloat16_rn(b - __bfloat162float(h));
+                s.b_lo[a] = to_tc(b - from_tc(h));
                 psi_part += (double)b * (double)((sum - e) * inv);
                 const int truth = s.idx0 ? s.idx0[f * d.L + sec0 + sec] : -1;
                 const double dlt = (double)b - (j == truth ? 1.0 : 0.0);
@@ -427,7 +427,7 @@ struct lsb_band_design {
     std::vector<double> W;
     std::vector<int> clo, chi, rlo, rhi;
     std::vector<void *> allocs;
-    __nv_bfloat16 *row_hi = nullptr, *row_lo = nullptr, *col_hi = nullptr, *col_lo = nullptr;
+    tc_t *row_hi = nullptr, *row_lo = nullptr, *col_hi = nullptr, *col_lo = nullptr;
     CUtensorMap map_row_hi, map_row_lo, map_col_hi, map_col_lo;
     std::mutex mu;
     // per (stream) work state, sized for the largest batch seen
@@ -516,8 +516,8 @@ int prepare_work(lsb_band_design *g, lsb_band_design::Work &wk, long long F)
     if (rc) return rc;
     s.part_stride = (long long)F * d.n;
     // the padding columns of the z pair are read by TMA (multiplied by zero rows of W): keep them finite
-    LSB_CUDA(cudaMemset(s.z_hi, 0, (size_t)F * d.n_pitch * sizeof(__nv_bfloat16)));
-    LSB_CUDA(cudaMemset(s.z_lo, 0, (size_t)F * d.n_pitch * sizeof(__nv_bfloat16)));
+    LSB_CUDA(cudaMemset(s.z_hi, 0, (size_t)F * d.n_pitch * sizeof(tc_t)));
+    LSB_CUDA(cudaMemset(s.z_lo, 0, (size_t)F * d.n_pitch * sizeof(tc_t)));
 
     const int n_f_tiles = (int)((F + kTileN - 1) / kTileN), sms = lsb::sm_count();
     std::vector<TcItem> ab, az;
@@ -723,11 +723,11 @@ void lsb_band_design_destroy(lsb_band_design *g)
     delete g;
 }
 
-/* bytes of device memory held by the explicit design (both orientations, bf16 pairs) */
+/* bytes of device memory held by the explicit design (both orientations, fp16 pairs) */
 int64_t lsb_band_design_bytes(const lsb_band_design *g)
 {
     if (!g) return 0;
-    return (int64_t)(2 * sizeof(__nv_bfloat16)) *
+    return (int64_t)(2 * sizeof(tc_t)) *
            ((int64_t)g->dev.Lr * g->Mr_pad * g->kmax + (int64_t)g->dev.L * g->dev.M * g->kz);
 }
 

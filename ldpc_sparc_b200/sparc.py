@@ -396,7 +396,7 @@ class Design:
         return self._handle
 
     def band_handle(self):
-        """Explicit (block-banded, bf16 hi / lo) copy of the design for the tensor-core path
+        """Explicit (block-banded, fp16 hi / lo) copy of the design for the tensor-core path
         (``precision='tc'``, csrc/sparc_band_tc.cu); built on first use."""
         if self.csparc:
             raise NotImplementedError("precision='tc' handles the real (DCT) design")

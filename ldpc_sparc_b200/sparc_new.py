@@ -11,7 +11,7 @@ All decoding arithmetic runs on the GPU (csrc/sparc_dense.cu + the BP kernels).
 design ``A``); ``A`` is a NumPy array -- uploaded once and cached -- exactly what
 ``sparc_ldpc_encode`` returns.  ``precision`` is 'fp64' (parity mode, default, the
 reference's float64), 'fp32' (SIMT fp32) or 'tc' (throughput mode: the two products
-A beta and A^T z run on the tensor cores -- tcgen05, split-bf16 operands with fp32
+A beta and A^T z run on the tensor cores -- tcgen05, split-fp16 operands with fp32
 accumulation, about 2e-5 relative -- and everything else in fp32).
 """
 import ctypes as ct
@@ -119,7 +119,7 @@ class _Engine:
         _lib.require_device()
         self.torch = torch
         self.precision = precision
-        self.tc = precision == "tc"          # tensor-core products (tcgen05, split bf16), fp32 everywhere else
+        self.tc = precision == "tc"          # tensor-core products (tcgen05, split fp16), fp32 everywhere else
         self.bp_precision = "fp64" if precision == "fp64" else "fp32"
         self.dt = torch.float64 if precision == "fp64" else torch.float32
         self.suf = "f64" if precision == "fp64" else "f32"
@@ -342,8 +342,8 @@ def _amp_device(eng, yd, P, L, M, sq, t_max, return_trace=False):
     """t_max AMP iterations on device frames ``yd [F, n]``; returns device tensors
     ``(beta, s[, tau^2 per iteration])``."""
     if _fused_tc_ok(eng, L, M, t_max, yd.shape[0]):
-        # three launches per iteration, no Python in the loop: A beta -> residual (+ bf16 split of z) ->
-        # A^T z with the denoiser (+ bf16 split of beta) as the GEMM epilogue
+        # three launches per iteration, no Python in the loop: A beta -> residual (+ fp16 split of z) ->
+        # A^T z with the denoiser (+ fp16 split of beta) as the GEMM epilogue
         t = eng.torch
         F = yd.shape[0]
         beta, s = eng.empty(F, L * M), eng.empty(F, L * M)

@@ -94,7 +94,7 @@ def performance_sweep(sparc_params, sparc_ldpc_params, ldpc_params, lengths, dec
 
     The reference draws a new design matrix for every run (sparc_new.py:48,1290 seeded per run by
     performance_plots_general.py:101-118), i.e. its BER curves average over the design ensemble.  ``n_designs`` > 1
-    keeps a pool of that many device-resident designs (seeds ``design_seed + d``; 4 bf16 copies of A each, 3.3 GB at
+    keeps a pool of that many device-resident designs (seeds ``design_seed + d``; 4 fp16 copies of A each, 3.3 GB at
     BASELINE config 5) and runs chunk ``c`` on design ``c mod n_designs``; 1 (default) is the fixed-design experiment.
 
     Returns a dict with ``snr_store``, ``ber_store_averages [len(sims), n_snr]``,

@@ -1,10 +1,12 @@
 """GPU parity tests of the tensor-core form of the sparc_public decoder (csrc/sparc_band_tc.cu): the sub-sampled DCT
-design stored explicitly as a block-banded bf16 hi / lo matrix, A beta and A^T z as tcgen05 GEMMs over the frame
-batch (`precision='tc'`).  Checked against the dense matrix of the numpy oracle, the reference's golden runs and the
-fp64 FFT kernel.  Bar of this mode: section decisions and frame / section error counts exact, t_final within the
-fp32 stop rule's slack, the converged tau within 5e-4; the per-iteration tau of the transient iterations within 5e-3
-(kTauTol): an operand kept as two bf16 terms carries 16-17 mantissa bits, i.e. ~1e-5 per product, and the AMP
-transient (the decoding wave of a coupled design) amplifies that by 10-100x.  The fp32 FFT path keeps 1e-4 throughout."""
+design stored explicitly as a block-banded matrix of fp16 hi / lo pairs, A beta and A^T z as tcgen05 GEMMs over the
+frame batch (`precision='tc'`).  Checked against the dense matrix of the numpy oracle, the reference's golden runs and
+the fp64 FFT kernel.  Bar of this mode: section decisions and frame / section error counts exact, t_final within the
+fp32 stop rule's slack, per-iteration tau within 2e-4 relative (kTauTol; measured <= 8e-5 on every golden incl. full-size
+config 4) and the converged tau within 1e-4.  Two things made that possible: operands as fp16
+pairs (22 mantissa bits instead of the 16 of fp16 pairs) and K accumulated in TMEM only 8 K blocks at a time, the chunks
+summed in registers with round-to-nearest -- the tensor core rounds its fp32 accumulator toward zero at every MMA and
+that bias, linear in K, was the dominant error (7e-4 in tau at config 4 before)."""
 import json
 import os
 
@@ -16,7 +18,7 @@ from conftest import GOLDEN
 from ldpc_sparc_b200 import sparc
 
 pytestmark = pytest.mark.gpu
-kTauTol = 5e-3
+kTauTol = 2e-4
 
 
 @pytest.fixture(scope="module")
@@ -76,15 +78,15 @@ def test_band_amp_matches_reference_golden(gold, name):
         assert T - 1 <= t_final <= dp["t_max"] - 1, (t_final, T)
         Tc = min(T, t_final)
         assert rel_err(ex["tau"][:Tc], g[pre + "tau_it"][:Tc]) < kTauTol
-        assert rel_err(ex["tau"][Tc - 1], g[pre + "tau_it"][Tc - 1]) < 5e-4          # converged
+        assert rel_err(ex["tau"][Tc - 1], g[pre + "tau_it"][Tc - 1]) < 1e-4          # converged
         ref_psi = g[pre + "psi_it"][:Tc]
-        # tau (what the decoder uses) is held to 1e-4; psi_c = sum beta (1 - beta) of a nearly converged block is
-        # exp(-gap / tau) with gap / tau ~ 10 .. 100, which amplifies the 2^-17 operand rounding of the split products
-        assert np.all(np.abs(ex["psi"][:Tc] - ref_psi) <= 2e-2 * ref_psi + 1e-5)
-        assert np.allclose(nmse[:Tc + 1], g[pre + "nmse"][:Tc + 1], rtol=2e-2, atol=1e-5)
+        # psi_c = sum beta (1 - beta) of a nearly converged block is exp(-gap / tau) with gap / tau ~ 10 .. 100, which
+        # amplifies the rounding of s by 1 / tau (same floor as the fp32 FFT kernel's test, scaled)
+        assert np.all(np.abs(ex["psi"][:Tc] - ref_psi) <= 2e-3 * ref_psi + 1e-6)
+        assert np.allclose(nmse[:Tc + 1], g[pre + "nmse"][:Tc + 1], rtol=5e-3, atol=1e-6)
         if t_final == T:
             ref_beta = g[pre + "beta_soft"].astype(np.float64)
-            assert np.max(np.abs(ex["beta_soft"] - ref_beta)) < 2e-3
+            assert np.max(np.abs(ex["beta_soft"] - ref_beta)) < 2e-4
 
 
 def test_band_amp_batch_equals_fft_kernels():
@@ -109,16 +111,19 @@ def test_band_amp_batch_equals_fft_kernels():
     idxtc, Ttc, nmtc, psitc, extc = out["tc"]
     assert np.array_equal(idx64, idxtc)
     assert (idx64 != idx0).mean() < 2e-2
+    errs = []
     for f in range(F):
         assert T64[f] - 1 <= Ttc[f] <= dp["t_max"] - 1
         Tc = int(min(T64[f], Ttc[f]))
-        assert rel_err(extc["tau"][f, :Tc], ex64["tau"][f, :Tc]) < kTauTol
+        errs.append(rel_err(extc["tau"][f, :Tc], ex64["tau"][f, :Tc]))
+    # 150 frames x 30 iterations x 8 column blocks: the slowest-converging frames amplify most in their transient
+    assert np.percentile(errs, 90) < kTauTol and max(errs) < 2e-3, (np.percentile(errs, 90), max(errs))
 
 
 def test_band_config4_sc_wave_matches_reference_golden(gold):
     """BASELINE config 4 at full size (L = 2048, M = 512, Lr = 37, Lc = 32, n = 12284, 192 blocks of 332 x 32768 out of
-    w = 65536): the reference's golden frame plus three fresh ones through the explicit design (19.6 GB of bf16
-    operands): decisions identical to the reference / the fp64 FFT kernel, tau within 1e-4."""
+    w = 65536): the reference's golden frame plus three fresh ones through the explicit design (19.6 GB of fp16
+    operands): decisions identical to the reference / the fp64 FFT kernel, tau within kTauTol."""
     g, meta = gold
     m = meta["c4_sc_wave"]
     pre = "c4_sc_wave_s0_"

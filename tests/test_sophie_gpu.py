@@ -170,7 +170,7 @@ def test_encode_and_batched_decode(gold):
 
 
 def test_tensor_core_products_vs_fp64():
-    """tcgen05 split-bf16 products against float64 numpy: ~16 mantissa bits."""
+    """tcgen05 split-fp16 products against float64 numpy: ~16 mantissa bits."""
     import ctypes as ct
     import torch
     from ldpc_sparc_b200 import _lib
@@ -333,7 +333,7 @@ def test_two_stream_drive_equals_one_stream(gold, monkeypatch):
 @pytest.mark.parametrize("L,M,n,F", [(64, 64, 384, 5), (48, 2, 96, 130), (24, 128, 256, 3), (40, 16, 320, 257),
                                      (256, 4, 512, 64)])
 def test_fused_tensor_core_amp_equals_kernel_chain(monkeypatch, L, M, n, F):
-    """lsb_tc_amp_dev_f32 (A beta -> residual -> A^T z with the denoiser as the GEMM epilogue, the bf16 operand
+    """lsb_tc_amp_dev_f32 (A beta -> residual -> A^T z with the denoiser as the GEMM epilogue, the fp16 operand
     splits written by the producers) against the unfused chain of the same products and the separate residual /
     denoiser kernels, and against the numpy oracle: section sizes 2 .. 128, frame counts that do not fill a
     128-frame tile, beta lengths that do not fill a 128-row tile."""

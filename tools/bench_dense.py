@@ -2,7 +2,7 @@
 """Throughput of the dense-Gaussian-design AMP decoder (BASELINE config 3: sparc_sophie design, L=512 M=64, R=1 ->
 n=3072, A = 3072 x 32768, P=19.44, t_max=25), F frames sharing one design.  Prints one JSON object
 (tools/workloads.dense_workload): decoded info bits/s and the tensor roofline of SURVEY 8(d): 402.7 MFLOP per
-frame-iteration against the measured sustained bf16 peak.  precision: tc (tcgen05 split-bf16) | fp32 (SIMT)."""
+frame-iteration against the measured sustained bf16 peak.  precision: tc (tcgen05 split-fp16) | fp32 (SIMT)."""
 import argparse
 import json
 import os

@@ -4,7 +4,7 @@
 A length-4096 transform factors as 64 x 64: two stages of 64 DFT-64s with a twiddle and a transposition between
 them.  One stage over a batch is the GEMM  out[128, 64 T] = D64 [128 x 128] x X [128, 64 T]  (D64 = the DFT-64
 matrix in real form, X = real and imaginary parts stacked), T = transforms in the batch.  This script runs exactly
-that GEMM through the library's tcgen05 kernel (csrc/tc_gemm.cuh, split-bf16 operands: three MMAs per product, the
+that GEMM through the library's tcgen05 kernel (csrc/tc_gemm.cuh, split-fp16 operands: three MMAs per product, the
 precision the 1e-4 parity bound needs) and reports DFT-64 STAGES of 4096-point transforms per second, next to the
 rate the shared-memory FFT kernel sustains inside the AMP decoder:
 
@@ -67,11 +67,11 @@ def main():
     stages = args.transforms / (ms * 1e-3)
     fft_transforms = 57.3e3 * 23.84 * 64
     print(json.dumps({
-        "what": "one DFT-64 stage of T 4096-point transforms as a tcgen05 GEMM [128 x 128] x [128, 64 T], split-bf16 (3 MMAs)",
+        "what": "one DFT-64 stage of T 4096-point transforms as a tcgen05 GEMM [128 x 128] x [128, 64 T], split-fp16 (3 MMAs)",
         "transforms_per_launch": args.transforms, "ms_per_launch": ms, "max_rel_err_vs_numpy_fft": err,
         "dft64_stages_per_s": stages,
         "upper_bound_transforms_per_s": stages / 2,
-        "note": "includes the fp32 -> bf16 hi/lo split of the operand (split8_kernel) and the fp32 store of the result; "
+        "note": "includes the fp32 -> fp16 hi/lo split of the operand (split8_kernel) and the fp32 store of the result; "
                 "a 4096-point transform needs two stages + twiddles + a transposition, so stages/2 is an upper bound",
         "bytes_per_stage_transform": 64 * (128 * 4 + 2 * 128 * 2 * 2 + 128 * 4),
         "fft_kernel_transforms_per_s_inside_amp": fft_transforms,

@@ -201,18 +201,18 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
     if precision == "tc":
         # explicit block-banded design on the tensor cores (csrc/sparc_band_tc.cu): the bound is the tcgen05 pipe.
         # Algorithmic flops: 2 per stored design entry per product; a frame that runs T iterations does T products
-        # A^T z and T - 1 products A beta.  The split-bf16 kernel issues 3x that (plus tile padding).
+        # A^T z and T - 1 products A beta.  The split-fp16 kernel issues 3x that (plus tile padding).
         d = Ab.design
         nnz = float(np.count_nonzero(d.Wm)) * d.Mr * d.Mc
         flops = 2.0 * nnz * (2.0 * frame_iters_rank - F)
         ach = flops / (ms * 1e-3) / 1e12
-        out["dtype"] = "bf16x3 (split) products, f32 elsewhere"
+        out["dtype"] = "f16x3 (split) products, f32 elsewhere"
         out["roofline_hbm_model"] = out["roofline"]
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tens, "unit": "TFLOP/s", "frac": ach / tens,
                            "peak_source": src, "traffic": None,
                            "model": "%.2f GFLOP per frame-iteration (2 flops per stored design entry and product, %d non-zero "
                                     "blocks of %d x %d; A beta skipped in a frame's first iteration); algorithmic flops -- the "
-                                    "split-bf16 kernel issues 3x" % (4.0 * nnz / 1e9, int(np.count_nonzero(d.Wm)), d.Mr, d.Mc)}
+                                    "split-fp16 kernel issues 3x" % (4.0 * nnz / 1e9, int(np.count_nonzero(d.Wm)), d.Mr, d.Mc)}
         out["design_bytes"] = int(_lib_bytes(d))
     if e2e and precision in ("fp32", "tc"):
         h_y = torch.empty(y.shape, dtype=torch.float32).pin_memory()
@@ -285,12 +285,12 @@ def dense_workload(ctx, frames=1024, steps=5, warmup=2, precision="tc", L=512, M
         "workload": "dense-design AMP, L=%d M=%d n=%d (A %dx%d), t_max=%d, %d frames per GPU" % (L, M, n, n, L * M, t_max, F),
         "metric": "decoded info bits/s", "value": ctx.world * F * L * logM / (ms * 1e-3), "unit": "info bits/s",
         "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "scaling": "weak",
-        "dtype": "bf16x3 (split) products, f32 elsewhere" if precision == "tc" else precision, "precision": precision,
+        "dtype": "f16x3 (split) products, f32 elsewhere" if precision == "tc" else precision, "precision": precision,
         "frames_per_s": ctx.world * F / (ms * 1e-3), "section_error_rate": ser_sum / (ctx.world * F * L),
         "roofline": {"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "peak_source": src,
                      "traffic": None,
                      "model": "402.7 MFLOP per frame-iteration at L=512 M=64 (SURVEY 8(d)); algorithmic flops, one product per "
-                              "operand pair -- the split-bf16 kernel issues 3x as many MMA flops"},
+                              "operand pair -- the split-fp16 kernel issues 3x as many MMA flops"},
         "e2e": None, "clocks": clocks,
     }
 
@@ -335,13 +335,13 @@ def c5_workload(ctx, frames=256, steps=5, warmup=2, precision="tc", small=False,
                     % (mults, L_sl, t_max, frames, list(snrs), list(sims)),
         "metric": "decoded user bits/s", "value": float(out["bits"].sum()) / (ms * 1e-3), "unit": "info bits/s",
         "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "scaling": "weak",
-        "dtype": "bf16x3 (split) products, f32 elsewhere", "precision": precision,
+        "dtype": "f16x3 (split) products, f32 elsewhere", "precision": precision,
         "frames_per_s": n_frames / (ms * 1e-3),
         "ber": {name: [float(v) for v in out["ber_store_averages"][i]] for i, name in enumerate(sims)},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "peak_source": src,
                      "traffic": None,
                      "model": "2 (2 n LM) = %.2f GFLOP per frame-iteration at L=n=%d (SURVEY 8(d)), (2 t_max - 1)/2 such per "
-                              "frame; algorithmic flops (the split-bf16 kernel issues 3x). BP: (2 Nmsg + 2 Nv) 4 B = %d B per "
+                              "frame; algorithmic flops (the split-fp16 kernel issues 3x). BP: (2 Nmsg + 2 Nv) 4 B = %d B per "
                               "block-iteration, %d blocks per frame, hidden under the GEMMs' time"
                               % (4.0 * n * LM / 1e9, n, (2 * int(c.Nmsg) + 2 * int(c.N)) * 4, mults),
                      "includes": "frame generation (encode, A beta0, noise) and error counting inside the step"},
