@@ -338,7 +338,11 @@ int lsb_tc_az_dev_f32(lsb_tc_design *g, const float *z /* [F, n] */, float *out 
  * estimate after t_max iterations; s_out (may be NULL) the last s = beta + A^T z; tau_trace (may be NULL) [t_max, F]
  * the tau^2 of every iteration.  M must be a power of two in [2, 128]; pointers 16-byte aligned. */
 int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M, double P, double sqrt_nPl, int t_max,
-                       float *beta_out, float *s_out, double *tau_trace, void *stream);
+                       float *beta_out, float *s_out, double *tau_trace, int32_t *idx_out /* [F, L] MAP decisions, may be NULL */,
+                       void *stream);
+/* host-pointer form: y [F, n] host -> idx [F, L] host (argmax of the last s per section, sparc_new.py:79-80) */
+int lsb_tc_amp_host_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M, double P, double sqrt_nPl, int t_max,
+                        int32_t *idx);
 
 /* ---------------------------------------------------------------------------
  * Complex SPARCs: sub-sampled DFT design (sparc.py sub_fft :593-646, sparc_transforms

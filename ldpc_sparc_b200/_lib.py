@@ -91,7 +91,9 @@ SIGNATURES = {
     "lsb_tc_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_tc_az_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_tc_amp_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_double,
-                                      ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
+                                      ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p]),
+    "lsb_tc_amp_host_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_int, ct.c_int, ct.c_double, ct.c_double,
+                                       ct.c_int, ct.c_void_p]),
     # complex SPARCs (sub-sampled DFT design)
     "lsb_csparc_design_create": (ct.c_int, [c_f64p, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_u32p, c_u32p, ct.POINTER(ct.c_void_p)]),
     "lsb_csparc_design_destroy": (None, [ct.c_void_p]),

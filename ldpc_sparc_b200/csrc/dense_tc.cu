@@ -63,6 +63,11 @@ struct lsb_tc_design {
         size_t amp_frames = 0;
     };
     std::map<cudaStream_t, Staging> staging;
+    // host-pointer entry (lsb_tc_amp_host_f32): its own stream and staging, one call at a time
+    std::mutex host_mu;
+    cudaStream_t host_stream = nullptr;
+    void *host_stage = nullptr;
+    size_t host_stage_bytes = 0;
 };
 
 namespace {
@@ -172,12 +177,12 @@ template <int M>
 void launch_denoise_gemm(int grid, cudaStream_t st, const CUtensorMap &w_hi, const CUtensorMap &w_lo, const CUtensorMap &x_hi,
                          const CUtensorMap &x_lo, float *beta, int has_beta, tc_t *b_hi, tc_t *b_lo,
                          float *s_out, const double *tau, float *bsq_part, float sq, int rows, int F, int K, int n_row_tiles,
-                         int n_f_tiles, float out_scale)
+                         int n_f_tiles, float out_scale, int32_t *idx_out)
 {
     lsb::ensure_dynamic_smem(tc_gemm_denoise_kernel<M>, kSmemBytes);
     tc_gemm_denoise_kernel<M><<<grid, kThreadsTc, kSmemBytes, st>>>(w_hi, w_lo, x_hi, x_lo, beta, has_beta, b_hi, b_lo, s_out,
                                                                     tau, bsq_part, sq, rows, F, K, n_row_tiles, n_f_tiles,
-                                                                    out_scale);
+                                                                    out_scale, idx_out);
 }
 
 }  // namespace
@@ -189,7 +194,7 @@ extern "C" {
 // beta_out [F, ML] is the iterate itself (zeroed here, soft estimate on return); s_out (optional) receives the
 // last iteration's s = beta + A^T z; tau_trace (optional) [t_max, F] the tau^2 of every iteration.
 int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M, double P, double sqrt_nPl, int t_max,
-                       float *beta_out, float *s_out, double *tau_trace, void *stream)
+                       float *beta_out, float *s_out, double *tau_trace, int32_t *idx_out, void *stream)
 {
     if (F == 0) return LSB_OK;
     LSB_REQUIRE(g && y && beta_out, "null pointer");
@@ -261,12 +266,13 @@ int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M
                                                              t == 0);
         lsb::count_launch();
         float *so = (t == t_max - 1) ? s_out : nullptr;
+        int32_t *io = (t == t_max - 1) ? idx_out : nullptr;
         const int grid = az_items < sms ? az_items : sms;
 #define LSB_DN(MM)                                                                                                       \
     case MM:                                                                                                             \
         launch_denoise_gemm<MM>(grid, st, g->At.map_hi, g->At.map_lo, mz_hi, mz_lo, beta_out, t > 0, sg.b_hi, sg.b_lo, so, \
                                 sg.tau, sg.bsq_part, (float)sqrt_nPl, ML, (int)F, n, az_row_tiles, n_f_tiles,            \
-                                g->out_scale);                                                                           \
+                                g->out_scale, io);                                                                       \
         break;
         switch (M) {
             LSB_DN(2) LSB_DN(4) LSB_DN(8) LSB_DN(16) LSB_DN(32) LSB_DN(64) LSB_DN(128)
@@ -275,6 +281,41 @@ int lsb_tc_amp_dev_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M
         lsb::count_launch();
         LSB_CUDA(cudaGetLastError());
     }
+    return LSB_OK;
+}
+
+/* Host-pointer form: y [F, n] in host memory (pinned memory makes the copies asynchronous) -> MAP section decisions
+ * idx [F, L] (argmax of the last iteration's s, sparc_new.py:79-80 / 1099-1116) back in host memory on return. */
+int lsb_tc_amp_host_f32(lsb_tc_design *g, const float *y, int64_t F, int L, int M, double P, double sqrt_nPl, int t_max,
+                        int32_t *idx)
+{
+    if (F == 0) return LSB_OK;
+    LSB_REQUIRE(g && y && idx && F > 0, "null pointer or negative frame count");
+    int dev = -1;
+    LSB_CUDA(cudaGetDevice(&dev));
+    LSB_REQUIRE(dev == g->device, "design was created on device %d, current device is %d", g->device, dev);
+    std::lock_guard<std::mutex> lock(g->host_mu);
+    if (!g->host_stream) LSB_CUDA(cudaStreamCreateWithFlags(&g->host_stream, cudaStreamNonBlocking));
+    const size_t by = (size_t)F * g->n * sizeof(float), bb = (size_t)F * g->ML * sizeof(float), bi = (size_t)F * L * sizeof(int32_t);
+    const size_t need = ((by + 255) & ~(size_t)255) + ((bb + 255) & ~(size_t)255) + bi;
+    if (g->host_stage_bytes < need) {
+        LSB_CUDA(cudaStreamSynchronize(g->host_stream));
+        cudaFree(g->host_stage);
+        g->host_stage = nullptr;
+        g->host_stage_bytes = 0;
+        LSB_CUDA(cudaMalloc(&g->host_stage, need));
+        g->host_stage_bytes = need;
+    }
+    char *base = (char *)g->host_stage;
+    float *d_y = (float *)base;
+    float *d_beta = (float *)(base + ((by + 255) & ~(size_t)255));
+    int32_t *d_idx = (int32_t *)((char *)d_beta + ((bb + 255) & ~(size_t)255));
+    cudaStream_t st = g->host_stream;
+    LSB_CUDA(cudaMemcpyAsync(d_y, y, by, cudaMemcpyHostToDevice, st));
+    int rc = lsb_tc_amp_dev_f32(g, d_y, F, L, M, P, sqrt_nPl, t_max, d_beta, nullptr, nullptr, d_idx, st);
+    if (rc) return rc;
+    LSB_CUDA(cudaMemcpyAsync(idx, d_idx, bi, cudaMemcpyDeviceToHost, st));
+    LSB_CUDA(cudaStreamSynchronize(st));
     return LSB_OK;
 }
 
@@ -357,6 +398,8 @@ void lsb_tc_design_destroy(lsb_tc_design *g)
         cudaFree(kv.second.b_lo);
         cudaFree(kv.second.tau);
     }
+    cudaFree(g->host_stage);
+    if (g->host_stream) cudaStreamDestroy(g->host_stream);
     delete g;
 }
 

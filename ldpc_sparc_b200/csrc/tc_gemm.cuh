@@ -469,7 +469,8 @@ tc_gemm_denoise_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid
                        const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
                        float *beta, int has_beta, tc_t *__restrict__ beta_hi, tc_t *__restrict__ beta_lo,
                        float *__restrict__ s_out, const double *__restrict__ tau_sqr, float *__restrict__ bsq_part,
-                       float sqrt_nPl, int rows_total, int F, int K, int n_row_tiles, int n_f_tiles, float out_scale)
+                       float sqrt_nPl, int rows_total, int F, int K, int n_row_tiles, int n_f_tiles, float out_scale,
+                       int32_t *__restrict__ idx_out)
 {
     constexpr int SEC = M < 32 ? 32 : M;          // accumulator columns handled at a time (whole sections)
     static_assert(M >= 2 && M <= 128 && (M & (M - 1)) == 0, "section size must be a power of two in [2, 128]");
@@ -623,6 +624,12 @@ tc_gemm_denoise_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid
                         float mx = sv[s0];
 #pragma unroll
                         for (int i = 1; i < M; ++i) mx = fmaxf(mx, sv[s0 + i]);
+                        if (idx_out) {                       // MAP decision on s (sparc_new.py:1099-1116): first maximum
+                            int arg = 0;
+#pragma unroll
+                            for (int i = M - 1; i >= 0; --i) arg = sv[s0 + i] == mx ? i : arg;
+                            idx_out[(size_t)f * (size_t)(rows_total / M) + (size_t)((row0 + c0 + s0) / M)] = arg;
+                        }
                         float sum = 0.0f;
 #pragma unroll
                         for (int i = 0; i < M; ++i) {

@@ -350,7 +350,7 @@ def _amp_device(eng, yd, P, L, M, sq, t_max, return_trace=False):
         taus = t.empty((t_max, F), dtype=t.float64, device=eng.dev) if return_trace else None
         _lib.check(_lib.lib().lsb_tc_amp_dev_f32(eng.h, yd.data_ptr(), F, L, M, float(P), float(sq), int(t_max),
                                                  beta.data_ptr(), s.data_ptr(),
-                                                 taus.data_ptr() if return_trace else None, eng.stream()), "tc_amp")
+                                                 taus.data_ptr() if return_trace else None, None, eng.stream()), "tc_amp")
         if return_trace:
             return beta, s, taus.t().contiguous()
         return beta, s
@@ -385,6 +385,30 @@ def sparc_amp(y, sparc_params, decode_params, A, precision=None, return_trace=Fa
     if return_trace:
         return res + (_out(out[2], single),)
     return res
+
+
+def sparc_amp_decide_host(y, sparc_params, decode_params, A, out=None):
+    """AMP decode + MAP decision through the host-pointer C-ABI entry ``lsb_tc_amp_host_f32`` (tensor-core mode):
+    ``y`` float32 ``[F, n]`` in host memory (numpy, or a pinned CPU torch tensor) -> section decisions ``[F, L]`` int32
+    (argmax of the last iteration's s, what sparc_ldpc_decode does without an LDPC code, sparc_new.py:79-80)."""
+    import torch
+    P, L, M = sparc_params['P'], sparc_params['L'], sparc_params['M']
+    eng = _engine(A, "tc")
+    n = eng.n
+    if isinstance(y, torch.Tensor):
+        assert y.device.type == "cpu" and y.dtype == torch.float32 and y.is_contiguous()
+        F, y_ptr = y.reshape(-1, n).shape[0], y.data_ptr()
+    else:
+        y = np.ascontiguousarray(y, dtype=np.float32).reshape(-1, n)
+        F, y_ptr = y.shape[0], y.ctypes.data
+    if out is None:
+        idx = np.empty((F, L), np.int32)
+        ptr = idx.ctypes.data
+    else:
+        idx, ptr = out, out.data_ptr()
+    _lib.check(_lib.lib().lsb_tc_amp_host_f32(eng.h, y_ptr, F, L, M, float(P), float(np.sqrt(n * (P / L))),
+                                              int(decode_params['t_max']), ptr), "lsb_tc_amp_host_f32")
+    return idx
 
 
 def sparc_amp_single_it(sparc_params, y, A, AT, beta, z, tau_sqr, precision=None):

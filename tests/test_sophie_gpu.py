@@ -365,3 +365,20 @@ def test_fused_tensor_core_amp_equals_kernel_chain(monkeypatch, L, M, n, F):
         assert np.max(np.abs(tau[f] - ref_tau) / ref_tau) < 1e-4
         assert np.max(np.abs(beta[f] - ref_beta)) < 5e-4 * sq          # 1e-4 at full size: test_config3_full_size_...
         assert np.array_equal(s[f].reshape(L, M).argmax(1), ref_s.reshape(L, M).argmax(1))
+
+
+def test_dense_amp_host_entry_equals_device_path():
+    """lsb_tc_amp_host_f32 (host y in, MAP section decisions out) against argmax of the device path's s."""
+    L, M, n, F, P = 64, 32, 320, 70, 12.0
+    rng = np.random.default_rng(11)
+    A = rng.normal(0, 1 / np.sqrt(n), (n, L * M))
+    sq = np.sqrt(n * P / L)
+    sp, dp = dict(P=P, R=1.0, L=L, M=M), dict(t_max=15)
+    idx0 = rng.integers(0, M, (F, L))
+    beta0 = np.zeros((F, L * M))
+    beta0[np.arange(F)[:, None], np.arange(L)[None, :] * M + idx0] = sq
+    ys = (beta0 @ A.T + np.sqrt(P / 8.0) * rng.standard_normal((F, n))).astype(np.float32)
+    idx_h = sparc_new.sparc_amp_decide_host(ys, sp, dp, A)
+    beta, s = sparc_new.sparc_amp(ys.astype(np.float64), sp, dp, A, precision="tc")
+    assert np.array_equal(idx_h, s.reshape(F, L, M).argmax(2))
+    assert (idx_h != idx0).mean() < 0.05

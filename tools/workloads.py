@@ -281,6 +281,23 @@ def dense_workload(ctx, frames=1024, steps=5, warmup=2, precision="tc", L=512, M
     flops = (2 * t_max - 1) * 2.0 * n * L * M * F            # A^T z every iteration, A beta from the second on (per rank)
     _, tf, src = peaks()
     ach = flops / (ms * 1e-3) / 1e12
+    e2e = None
+    if precision == "tc":
+        # the same decode through the host-pointer C-ABI entry: pinned y in, MAP section decisions out
+        h_y = torch.empty(y.shape, dtype=torch.float32).pin_memory()
+        h_y.copy_(y)
+        h_idx = torch.empty((F, L), dtype=torch.int32).pin_memory()
+        sp, dp = dict(P=P, L=L, M=M), dict(t_max=t_max)
+
+        def e2e_step():
+            sparc_new.sparc_amp_decide_host(h_y, sp, dp, A, out=h_idx)
+
+        n_e2e = max(1, min(steps, 3))
+        e_ms, _ = timed(ctx, e2e_step, n_e2e, 1, host_sync=True)
+        assert torch.equal(h_idx.to(ctx.dev).long(), res["s"].view(F, L, M).argmax(2)), "host-entry decisions differ"
+        e2e = {"value": ctx.world * F * L * logM / (e_ms / n_e2e * 1e-3), "unit": "info bits/s",
+               "h2d_bytes_per_step": h_y.numel() * 4, "d2h_bytes_per_step": h_idx.numel() * 4, "ms_per_step": e_ms / n_e2e,
+               "api": "lsb_tc_amp_host_f32 (C-ABI, pinned host y in; MAP section decisions out)"}
     return {
         "workload": "dense-design AMP, L=%d M=%d n=%d (A %dx%d), t_max=%d, %d frames per GPU" % (L, M, n, n, L * M, t_max, F),
         "metric": "decoded info bits/s", "value": ctx.world * F * L * logM / (ms * 1e-3), "unit": "info bits/s",
@@ -291,7 +308,7 @@ def dense_workload(ctx, frames=1024, steps=5, warmup=2, precision="tc", L=512, M
                      "traffic": None,
                      "model": "402.7 MFLOP per frame-iteration at L=512 M=64 (SURVEY 8(d)); algorithmic flops, one product per "
                               "operand pair -- the split-fp16 kernel issues 3x as many MMA flops"},
-        "e2e": None, "clocks": clocks,
+        "e2e": e2e, "clocks": clocks,
     }
 
 
