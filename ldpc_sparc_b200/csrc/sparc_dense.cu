@@ -401,6 +401,89 @@ onsager_closed_kernel(const T *__restrict__ beta, const T *__restrict__ vk, cons
     if (threadIdx.x == 0) out[f] = tot;
 }
 
+// ------------------------------------------------------------------ M = 2 (one LDPC bit per section), fp32
+// BASELINE config 5 runs L = 14400 sections of M = 2.  The general kernels above give a section to a group of lanes
+// and reduce across them with shuffles, which for M = 2 leaves a warp with 16 sections per pass and a chain of
+// dependent loads per pass (ncu launch list, 256 frames: Onsager 178 us, denoiser 92 us, bit -> section 80 us against
+// 10-20 us of memory traffic).  Here a thread owns whole sections (one 8-byte access per array), four in flight.
+// Same expressions as the general kernels; only the order of the per-frame fp64 partial sums differs.
+__global__ void __launch_bounds__(kThreads)
+denoise_m2_kernel(const float *beta_in, const float *__restrict__ atz, float *beta, float *__restrict__ s_out,
+                  const double *tau_sqr, double *beta_sq, int L, double sqrt_nPl)
+{
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    const float scale = (float)(sqrt_nPl / tau_sqr[f]), amp = (float)sqrt_nPl;
+    const float2 *az2 = reinterpret_cast<const float2 *>(atz) + f * (size_t)L;
+    const float2 *bi2 = beta_in ? reinterpret_cast<const float2 *>(beta_in) + f * (size_t)L : nullptr;
+    float2 *bo2 = reinterpret_cast<float2 *>(beta) + f * (size_t)L;
+    float2 *so2 = s_out ? reinterpret_cast<float2 *>(s_out) + f * (size_t)L : nullptr;
+    double part = 0.0;
+#pragma unroll 4
+    for (int l = threadIdx.x; l < L; l += kThreads) {
+        float2 v = az2[l];
+        if (bi2) { const float2 b = bi2[l]; v.x += b.x; v.y += b.y; }
+        if (so2) so2[l] = v;
+        const float mx = fmaxf(v.x, v.y);
+        const float e0 = expf((v.x - mx) * scale), e1 = expf((v.y - mx) * scale);
+        const float sum = e0 + e1;
+        const float b0 = amp * (e0 / sum), b1 = amp * (e1 / sum);
+        bo2[l] = make_float2(b0, b1);
+        part += (double)b0 * (double)b0 + (double)b1 * (double)b1;
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) beta_sq[f] = tot;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bit_to_section_m2_kernel(const float *__restrict__ app, float *__restrict__ probs, float *__restrict__ beta, double *beta_sq,
+                         int L, double sqrt_nPl)
+{
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    const float amp = (float)sqrt_nPl;
+    float2 *bo2 = reinterpret_cast<float2 *>(beta) + f * (size_t)L;
+    double part = 0.0;
+#pragma unroll 4
+    for (int l = threadIdx.x; l < L; l += kThreads) {
+        const float p = 1.0f / (1.0f + expf(-app[f * (size_t)L + l]));
+        if (probs) probs[f * (size_t)L + l] = p;
+        const float b0 = p * amp, b1 = (1.0f - p) * amp;
+        bo2[l] = make_float2(b0, b1);
+        part += (double)b0 * (double)b0 + (double)b1 * (double)b1;
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0 && beta_sq) beta_sq[f] = tot;
+}
+
+__global__ void __launch_bounds__(kThreads)
+onsager_m2_kernel(const float *__restrict__ beta, const float *__restrict__ vk, const float *__restrict__ vk0,
+                  const float *__restrict__ alpha_w, const double *tau_sqr, double *out, int L, double sqrt_nPl)
+{
+    __shared__ double red[kThreads / 32];
+    const size_t f = blockIdx.x;
+    const float c = (float)(sqrt_nPl / tau_sqr[f]), inv_amp = (float)(1.0 / sqrt_nPl);
+    const float2 *a2 = reinterpret_cast<const float2 *>(alpha_w) + f * (size_t)L;
+    const float2 *b2 = reinterpret_cast<const float2 *>(beta) + f * (size_t)L;
+    const float *v_f = vk + f * (size_t)L, *v0_f = vk0 + f * (size_t)L;
+    double part = 0.0;
+#pragma unroll 4
+    for (int l = threadIdx.x; l < L; l += kThreads) {
+        const float2 aw = a2[l], b = b2[l];
+        const float a0 = aw.x * inv_amp, a1 = aw.y * inv_amp;
+        const float Ak = a0;                                   // S_0 = {0}: entries whose (only) bit is 0
+        const float v0 = v0_f[l], v = v_f[l];
+        const float lo = fmaxf(v0, 1e-10f), hi = fmaxf((float)(1.0 - (double)v0), 1e-10f);
+        const float sub = 1.0f / (lo * hi);
+        const float acc0 = (1.0f - v) * sub * (1.0f - Ak);
+        const float acc1 = (-v) * sub * (0.0f - Ak);
+        part += (double)(b.x * (c * a0 * acc0));
+        part += (double)(b.y * (c * a1 * acc1));
+    }
+    const double tot = block_sum(part, red);
+    if (threadIdx.x == 0) out[f] = tot;
+}
+
 template <typename T>
 void launch_onsager(const T *beta, const T *vk, const T *vk0, const T *alpha_w, const double *tau_sqr, double *out,
                     int64_t F, int L, int M, int logM, double sqrt_nPl, cudaStream_t st)
@@ -408,7 +491,10 @@ void launch_onsager(const T *beta, const T *vk, const T *vk0, const T *alpha_w, 
     // fp64 is the parity mode and keeps the reference's operation order; fp32 takes the closed form
 #define LSB_ONSAGER_CLOSED(PER) \
     onsager_closed_kernel<T, PER><<<(unsigned)F, kThreads, 0, st>>>(beta, vk, vk0, alpha_w, tau_sqr, out, L, M, logM, sqrt_nPl)
-    if (sizeof(T) == 4 && M <= 32) LSB_ONSAGER_CLOSED(1);
+    if (sizeof(T) == 4 && M == 2)
+        onsager_m2_kernel<<<(unsigned)F, kThreads, 0, st>>>((const float *)beta, (const float *)vk, (const float *)vk0,
+                                                         (const float *)alpha_w, tau_sqr, out, L, sqrt_nPl);
+    else if (sizeof(T) == 4 && M <= 32) LSB_ONSAGER_CLOSED(1);
     else if (sizeof(T) == 4 && M == 64) LSB_ONSAGER_CLOSED(2);
     else if (sizeof(T) == 4 && M == 128) LSB_ONSAGER_CLOSED(4);
     else if (sizeof(T) == 4 && M == 256) LSB_ONSAGER_CLOSED(8);
@@ -558,6 +644,14 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
         LSB_REQUIRE(beta_out && atz && tau_sqr && beta_sq, "null pointer");                                      \
         LSB_REQUIRE(M >= 2 && M <= 256 && (M & (M - 1)) == 0, "M must be a power of two in [2, 256]");            \
         if (F <= 0) return LSB_OK;                                                                               \
+        if (sizeof(T) == 4 && M == 2 && ((uintptr_t)atz & 7) == 0 && ((uintptr_t)beta_out & 7) == 0 &&           \
+            (!beta_in || ((uintptr_t)beta_in & 7) == 0) && (!s_out || ((uintptr_t)s_out & 7) == 0)) {             \
+            denoise_m2_kernel<<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(                                \
+                (const float *)beta_in, (const float *)atz, (float *)beta_out, (float *)s_out, tau_sqr, beta_sq, L, sqrt_nPl); \
+            lsb::count_launch();                                                                                 \
+            LSB_CUDA(cudaGetLastError());                                                                        \
+            return LSB_OK;                                                                                       \
+        }                                                                                                        \
         switch (M >= 32 ? M / 32 : 0) {                                                                          \
             case 0: denoise_kernel<T, 0><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
             case 1: denoise_kernel<T, 1><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(beta_in, atz, beta_out, s_out, tau_sqr, beta_sq, L, M, sqrt_nPl); break; \
@@ -593,6 +687,13 @@ int lsb_dense_az_dev_f64(const lsb_dense_design *g, const double *z, double *out
         int logM = 0;                                                                                            \
         while ((1 << logM) < M) ++logM;                                                                          \
         if (F <= 0) return LSB_OK;                                                                               \
+        if (sizeof(T) == 4 && M == 2 && ((uintptr_t)beta & 7) == 0) {                                            \
+            bit_to_section_m2_kernel<<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(                         \
+                (const float *)app, (float *)probs, (float *)beta, beta_sq, L, sqrt_nPl);                         \
+            lsb::count_launch();                                                                                 \
+            LSB_CUDA(cudaGetLastError());                                                                        \
+            return LSB_OK;                                                                                       \
+        }                                                                                                        \
         bit_to_section_kernel<T><<<(unsigned)F, kThreads, 0, (cudaStream_t)stream>>>(app, probs, beta, beta_sq,  \
                                                                                     L, M, logM, sqrt_nPl);      \
         lsb::count_launch();                                                                                     \
