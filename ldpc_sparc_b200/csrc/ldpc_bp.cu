@@ -88,6 +88,7 @@ struct lsb_ldpc_graph {
     // frame-queue counters (ring, one per launch in flight)
     unsigned long long *d_queue = nullptr;
     std::atomic<unsigned> next_queue{0};
+    cudaEvent_t queue_ev[kCounters] = {};      // recorded behind the launch that used the slot: its next user waits on it
     // generic-kernel message workspace: one buffer per handle, so generic
     // launches are chained through ws_event (they may sit on different streams)
     std::mutex ws_mu;
@@ -157,7 +158,12 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
     int rc = check_device(g);
     if (rc) return rc;
 
-    unsigned long long *queue = g->d_queue + (g->next_queue.fetch_add(1) % kCounters);
+    // Frame-queue counter: a ring of kCounters slots.  The slot's previous user (64 launches ago, possibly on another
+    // stream and still running) must be done before the counter is zeroed again.
+    const unsigned slot = g->next_queue.fetch_add(1) % kCounters;
+    unsigned long long *queue = g->d_queue + slot;
+    if (g->queue_ev[slot]) LSB_CUDA(cudaStreamWaitEvent(st, g->queue_ev[slot], 0));
+    else LSB_CUDA(cudaEventCreateWithFlags(&g->queue_ev[slot], cudaEventDisableTiming));
     LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
 
     const bool qc_ok = g->is_qc && g->max_dc <= kMaxDcQc &&
@@ -181,7 +187,9 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
         a.cached_grid = &g->qc_grid[sizeof(T) == 8][algo];
         a.stream = st;
         if (mc) a.mc = *mc;
-        return launch_qc<T>(a);
+        rc = launch_qc<T>(a);
+        if (!rc) LSB_CUDA(cudaEventRecord(g->queue_ev[slot], st));
+        return rc;
     }
     LSB_REQUIRE(!mc, "the fused Monte-Carlo front end needs a QC graph within the QC kernel's limits");
     // generic path: one message workspace per handle, so launches are chained
@@ -224,6 +232,7 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
     rc = launch_generic<T>(a);
     if (rc) return rc;
     LSB_CUDA(cudaEventRecord(g->ws_event, st));
+    LSB_CUDA(cudaEventRecord(g->queue_ev[slot], st));
     return LSB_OK;
 }
 
@@ -544,6 +553,8 @@ void lsb_ldpc_graph_destroy(lsb_ldpc_graph *g)
     cudaFree(g->d_queue);
     cudaFree(g->d_ws);
     if (g->ws_event) cudaEventDestroy(g->ws_event);
+    for (cudaEvent_t e : g->queue_ev)
+        if (e) cudaEventDestroy(e);
     delete g;
 }
 
