@@ -183,3 +183,17 @@ def test_campaign_cli(tmp_path, capsys):
     campaign.main(["ldpc_sparc", "--mults", "1", "--frames", "32", "--snr", "2", "6", "2", "--npz", npz])
     saved = np.load(npz)
     assert saved["ber_store_averages"].shape == (4, 2) and np.all(saved["ber_store_averages"][1:, 1] == 0)
+
+
+def test_sparc_sim_batch_on_the_tensor_core_path():
+    """precision='tc' in the Monte-Carlo driver (explicit design, tcgen05 products): a spatially coupled code, same
+    messages and noise as the fp32 FFT run -- identical section / frame error counters, deterministic."""
+    from ldpc_sparc_b200 import sparc_sim
+    cp = dict(P=15.0, R=1.4, L=256, M=32, spatially_coupled=True, omega=2, Lambda=8)
+    dp = dict(t_max=25)
+    a = sparc_sim.sparc_sim_batch(dict(cp), dp, 1.6, 384, rand_seed=(1, 2), seed=4, chunk=192, precision="tc")
+    b = sparc_sim.sparc_sim_batch(dict(cp), dp, 1.6, 384, rand_seed=(1, 2), seed=4, chunk=192, precision="tc")
+    f = sparc_sim.sparc_sim_batch(dict(cp), dp, 1.6, 384, rand_seed=(1, 2), seed=4, chunk=192, precision="fp32")
+    assert a == b
+    assert a['frames'] == 384 and a['section_errors'] > 0
+    assert a['section_errors'] == f['section_errors'] and a['frame_errors'] == f['frame_errors']
