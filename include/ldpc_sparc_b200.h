@@ -243,7 +243,9 @@ int lsb_sparc_amp_host_f32(lsb_sparc_design *g, const float *y, int64_t n_frames
  * fp16 products per operand pair, fp32 accumulation) and the rest of sparc_amp (sparc.py:931-999) runs in two
  * memory-bound kernels per iteration.  Same arguments and outputs as lsb_sparc_design_create /
  * lsb_sparc_ab_dev_f32 / lsb_sparc_az_dev_f32 / lsb_sparc_amp_dev_f32 (modulation <= 1 only; M <= 1024; L*M a
- * multiple of 8).  Device memory: lsb_band_design_bytes(). */
+ * multiple of 8).  Device memory: lsb_band_design_bytes().  lsb_band_amp_dev_f32 enqueues on `stream` but also
+ * synchronises it every fourth iteration (it reads back how many frames have stopped), so it cannot be captured
+ * into a CUDA graph. */
 typedef struct lsb_band_design lsb_band_design;
 int lsb_band_design_create(const double *W, int Lr, int Lc, int L, int M, int n,
                            const uint32_t *order0, const uint32_t *order1, lsb_band_design **out);
