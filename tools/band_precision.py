@@ -1,5 +1,8 @@
+"""Per-iteration tau of the tensor-core AMP path (precision='tc') and of the fp32 FFT path against the reference's golden runs
+(tests/golden/sparc_reference.npz): the numbers behind the precision paragraph of DESIGN.md section 5 (fp16 pairs, chunked
+accumulation).  python tools/band_precision.py"""
 import sys, os, json
-R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "oracle")); sys.path.insert(0, os.path.join(R, "tests"))
 import numpy as np
 from ldpc_sparc_b200 import sparc

@@ -1,5 +1,8 @@
+"""Host -> device copy bandwidth per rank, alone and with every rank copying at once (512 MB pinned buffers), plus the CPU
+affinity / NUMA placement bench.bind_to_gpu_numa ends up with.  Explains the end-to-end leg at 8 GPUs.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/h2d_diag.py   [BIND=0 to skip binding]"""
 import os, sys, time
-R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tools"))
 import torch, torch.distributed as dist
 rank, lr, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
