@@ -405,3 +405,31 @@ def test_fused_monte_carlo_front_end():
     for k in montecarlo.COUNTER_FIELDS:
         assert np.array_equal(r1[k], r2[k]), k
     assert r1["frames"][0] == 3000 and 0 < r1["frame_errors"][0] < 1500
+
+
+@pytest.mark.parametrize("weak_frac", [0.002, 0.05])
+def test_exp_domain_node_range_handling(weak_frac):
+    """The fp32 sumprod2 check node works on 2^-|L| shifted by the check's smallest |L|; a check whose inputs are all
+    > 120 (log2 units) above one weak input is out of its range and is deferred to the Lxor form through a
+    shared-memory list (ldpc_bp_kernels.cuh: check_node_edomain, kExcCap).  LLRs of magnitude 300-600 with a few weak
+    or wrong positions exercise the shift, the deferred list (weak_frac 0.002) and its overflow branch (0.05: hundreds
+    of out-of-range checks per iteration): iteration counts and decisions equal to the fp64 kernel, APP within 1e-4."""
+    import torch
+    c = ldpc.code("802.11n", "1/2", 81)
+    rng = np.random.RandomState(11)
+    F = 96
+    x = c.encode(rng.randint(0, 2, (F, c.K)))
+    llr = (1.0 - 2.0 * x) * rng.uniform(300.0, 600.0, x.shape)
+    weak = rng.rand(*x.shape) < weak_frac
+    llr[weak] = rng.uniform(-1.5, 1.5, int(weak.sum()))          # weak, some of them wrong
+    llr[:8, :40] = 0.0                                            # erasures (exact zeros) in a few frames
+    t = torch.from_numpy(llr).cuda()
+    app64, it64 = c.decode(t, 50, precision="fp64")
+    app32, it32 = c.decode(t.float(), 50, precision="fp32")
+    assert torch.equal(it32, it64)
+    conv = it64 < 50
+    assert int(conv.sum()) >= F // 2
+    assert torch.equal((app32 < 0)[conv], (app64 < 0)[conv])
+    assert torch.equal((app64 < 0)[conv], torch.from_numpy(x != 0).cuda()[conv])
+    rel = ((app32[conv].double() - app64[conv]).abs() / app64[conv].abs().clamp(min=1.0)).max()
+    assert float(rel) < 1e-4, float(rel)
