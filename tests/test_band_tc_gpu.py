@@ -173,3 +173,26 @@ def test_band_host_entry_equals_device_path():
     assert np.array_equal(idx_h, idx_d.cpu().numpy()) and np.array_equal(T_h, T_d.cpu().numpy())
     assert np.array_equal(psi_h, psi_d.cpu().numpy())
     assert (idx_h != idx0).mean() < 5e-2
+
+
+def test_band_config4_batch_decisions_equal_fft_path():
+    """Config 4, 48 fresh frames at the bench's operating point: the tensor-core path and the fp32 FFT path make the
+    same section decisions on every frame (and so count the same section / frame errors), t_final within one."""
+    import torch
+    cp = dict(P=15.0, R=1.5, L=2048, M=512, spatially_coupled=True, omega=6, Lambda=32)
+    dp = dict(t_max=40)
+    bits_in, beta0, x, Ab, Az = sparc.sparc_encode(cp, 1.0, [1, 2])
+    sparc.check_decode_params(dp)
+    L, M, n = cp["L"], cp["M"], cp["n"]
+    F = 48
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    idx0 = torch.randint(0, M, (F, L), device="cuda", generator=gen, dtype=torch.int32)
+    b0 = torch.zeros((F, L * M), device="cuda")
+    b0.view(F, L, M).scatter_(2, idx0.long().unsqueeze(-1), 1.0)
+    y = Ab(b0, precision="fp32") + torch.randn((F, n), device="cuda", generator=gen)
+    del b0
+    idx_tc, T_tc, _, _ = sparc.sparc_amp(y, cp, dp, 1.0, [1, 2], None, Ab, Az, precision="tc")
+    idx_32, T_32, _, _ = sparc.sparc_amp(y, cp, dp, 1.0, [1, 2], None, Ab, Az, precision="fp32")
+    assert torch.equal(idx_tc, idx_32)
+    assert float((idx_tc != idx0).float().mean()) < 1e-3
+    assert int((T_tc - T_32).abs().max()) <= 1
