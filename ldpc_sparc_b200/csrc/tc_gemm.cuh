@@ -129,6 +129,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
 // ~2e-4 relative after the 6144 MMAs of a K = 32768 item, which the AMP transient amplified to 7e-4 in tau);
 // chunks of 32 K blocks (384 MMAs) summed in registers with round-to-nearest keep it near 1e-5.
 constexpr int kChunkKb = 8;
+// the dense-design kernels: their products feed a better-conditioned recursion (no decoding wave) and their denoiser
+// epilogue needs the slack; 32 K blocks (384 MMAs, ~1e-5) measured +4 % at config 5 against 8
+constexpr int kChunkKbDense = 32;
 // TMEM accumulators in the ring (4 x 128 fp32 columns = all 512 columns; one CTA per SM): the MMA warp may run three
 // chunks ahead of the epilogue, which needs that slack at item boundaries (stores / the denoiser of a finished tile)
 constexpr int kAccs = 4;
@@ -220,8 +223,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constan
                 LSB_TC_DECODE_ITEM(item)
                 (void)row0;
                 (void)f0;
-                for (int kc = kb0; kc < kb1; kc += kChunkKb, ++j) {
-                    const int kc1 = kc + kChunkKb < kb1 ? kc + kChunkKb : kb1;
+                for (int kc = kb0; kc < kb1; kc += kChunkKbDense, ++j) {
+                    const int kc1 = kc + kChunkKbDense < kb1 ? kc + kChunkKbDense : kb1;
                     const uint32_t a = j % kAccs;
                     mbar_wait(&acc_empty_bar[a], ((j / kAccs) & 1) ^ 1);     // epilogue has drained this accumulator
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -254,7 +257,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constan
             LSB_TC_DECODE_ITEM(item)
             float *Cs = C + (size_t)split * (size_t)split_stride;
             float acc[kTileN];                    // this thread's row of the tile, summed over the K chunks (RN)
-            for (int kc = kb0; kc < kb1; kc += kChunkKb, ++j) {
+            for (int kc = kb0; kc < kb1; kc += kChunkKbDense, ++j) {
                 const uint32_t a = j % kAccs;
                 mbar_wait(&acc_full_bar[a], (j / kAccs) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -536,8 +539,8 @@ tc_gemm_denoise_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid
                                    ((uint32_t)(kTileN >> 4) << 24);
             uint32_t it = 0, j = 0;                          // j counts K chunks (one TMEM accumulator each)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                for (int kc = 0; kc < num_kb; kc += kChunkKb, ++j) {
-                    const int kc1 = kc + kChunkKb < num_kb ? kc + kChunkKb : num_kb;
+                for (int kc = 0; kc < num_kb; kc += kChunkKbDense, ++j) {
+                    const int kc1 = kc + kChunkKbDense < num_kb ? kc + kChunkKbDense : num_kb;
                     const uint32_t a = j % kAccs;
                     mbar_wait(&acc_empty_bar[a], ((j / kAccs) & 1) ^ 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -574,7 +577,7 @@ tc_gemm_denoise_kernel(const __grid_constant__ CUtensorMap mapW_hi, const __grid
             const float scale = live ? (float)((double)sqrt_nPl / tau_sqr[f]) : 0.0f;
             float sq = 0.0f;
             float acc[kTileRows];                    // this frame's 128 entries of A^T z, summed over the K chunks (RN)
-            for (int kc = 0; kc < num_kb; kc += kChunkKb, ++j) {
+            for (int kc = 0; kc < num_kb; kc += kChunkKbDense, ++j) {
                 const uint32_t a = j % kAccs;
                 mbar_wait(&acc_full_bar[a], (j / kAccs) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
