@@ -734,6 +734,16 @@ std::vector<uint16_t> chunked(const std::vector<uint16_t> &v)
     return out;
 }
 
+// Mirror pair s (0..3) of thread t in the fused first pass of the transposed transform (post = false) or the fused
+// last pass of the forward transform (post = true) at H = 2^h, Q = H/4 (sparc_pair.cuh: PairTables)
+inline int pair_fused_k(int h, int t, int s, bool post)
+{
+    const int Q = 1 << (h - 2);
+    if (t == 0) return s == 0 ? Q / 2 : s == 1 ? 3 * Q / 2 : s == 2 ? Q : 2 * Q;
+    const int b = post ? brev_host(2 * t, h - 2) : t;
+    return s == 0 ? b : s == 1 ? b + Q : s == 2 ? Q - b : 2 * Q - b;
+}
+
 // Host-side tables of one non-zero block for the pair kernels (index conventions in sparc_pair.cuh).
 int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t *o0, const uint32_t *o1, PairBlock *pb)
 {
@@ -771,10 +781,20 @@ int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t 
         tsrc[(size_t)k * 4 + 2] = ent(inv0[H - k]);
         tsrc[(size_t)k * 4 + 3] = ent(inv0[H + k]);
     }
+    if (pairfft::fused_inv_rt(h)) {             // per-thread order of the fused first pass (sparc_pair.cuh), then k = 0
+        std::vector<uint16_t> t4((size_t)(4 * kPairThreads + 1) * 4);
+        for (int t = 0; t < kPairThreads; ++t)
+            for (int s = 0; s < 4; ++s) {
+                const int k = pair_fused_k(h, t, s, false);
+                for (int e = 0; e < 4; ++e) t4[((size_t)t * 4 + s) * 4 + e] = tsrc[(size_t)k * 4 + e];
+            }
+        for (int e = 0; e < 4; ++e) t4[(size_t)4 * kPairThreads * 4 + e] = tsrc[e];
+        tsrc.swap(t4);
+    }
     std::vector<uint16_t> tgat(Mc);
     for (int j = 0; j < Mc; ++j) {
         const int m = makhoul((int)o1[j]);
-        tgat[j] = (uint16_t)(2 * pairfft::pswz_rt(h, brev_host(m >> 1, h)) + (m & 1));
+        tgat[j] = (uint16_t)(2 * pairfft::pswz_t_rt(h, brev_host(m >> 1, h)) + (m & 1));
     }
     int rc;
     const uint16_t *p16 = nullptr;
@@ -784,7 +804,8 @@ int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t 
     pb->fgat = reinterpret_cast<const uint2 *>(p16);
     if ((rc = dev_upload(g, &p16, tsrc))) return rc;
     pb->tsrc = reinterpret_cast<const uint2 *>(p16);
-    if ((rc = dev_upload(g, &p16, chunked(tgat)))) return rc;
+    tgat.resize((size_t)pairfft::chunk_count(Mc) * kPairThreads * 4, pairfft::kNone);   // four consecutive columns per thread
+    if ((rc = dev_upload(g, &p16, tgat))) return rc;
     pb->tgat = reinterpret_cast<const uint2 *>(p16);
     return LSB_OK;
 }
@@ -807,6 +828,16 @@ int build_pair_tables(lsb_sparc_design *g, int h)
         post[t] = entry(k);
         const int pa = pairfft::pswz_rt(h, brev_host(k, h)), pb = pairfft::pswz_rt(h, brev_host((H - k) & (H - 1), h));
         slot[t] = (uint32_t)pa | ((uint32_t)pb << 16);
+    }
+    if (pairfft::fused_inv_rt(h)) {
+        pre.assign((size_t)4 * kPairThreads, float2{0.f, 0.f});
+        for (int t = 0; t < kPairThreads; ++t)
+            for (int s = 0; s < 4; ++s) pre[(size_t)t * 4 + s] = entry(pair_fused_k(h, t, s, false));
+    }
+    if (pairfft::fused_fwd_rt(h)) {
+        post.assign((size_t)4 * kPairThreads, float2{0.f, 0.f});
+        for (int t = 0; t < kPairThreads; ++t)
+            for (int s = 0; s < 4; ++s) post[(size_t)t * 4 + s] = entry(pair_fused_k(h, t, s, true));
     }
     g->pair.tb.tw = g->tb32.tw;
     int rc;
@@ -964,7 +995,7 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
     LSB_REQUIRE(pp->modulation >= 0 && pp->modulation <= 2, "modulation must be 1 (none) or 2 (real 2-PSK)");
     if constexpr (sizeof(T) == 4) {
         // throughput path: two frames per CTA on the packed-fp32 transforms (sparc_amp_pair.cuh)
-        if (pair_fits(g) && g->full_columns && pp->modulation != 2 && g->dev.M <= 32 && !po->beta_soft && !po->s_last) {
+        if (pair_fits(g) && g->full_columns && pp->modulation != 2 && g->dev.M >= 4 && g->dev.M <= 32 && !po->beta_soft && !po->s_last) {
             AmpParams p{pp->awgn_var, pp->rtol, pp->atol, pp->t_max, pp->phi_est_method, 1};
             AmpOut o{po->idx, po->t_final, po->psi, po->nmse, nullptr, nullptr, po->tau_trace, po->psi_trace};
             return launch_amp_pair(g, y, n_frames, p, idx0, o, st);

@@ -134,7 +134,7 @@ az_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ y, float *__re
                     const unsigned id[4] = {e.x & 0xFFFFu, e.x >> 16, e.y & 0xFFFFu, e.y >> 16};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int j = tid + (4 * ch + u) * kPairThreads;
+                        const int j = (ch * kPairThreads + tid) * 4 + u;          // tgat: four consecutive columns per thread
                         if (j >= d.Mc) continue;
                         const float2 v = bf2[id[u]];
                         const float va = b.scale * v.x, vb = b.scale * v.y;
@@ -164,8 +164,18 @@ struct OutPre {                    // first chunk of the gather after a transpos
     uint2 ids;
     float2 pv[4];
 };
+__device__ __forceinline__ void ld4_cg(const float2 *p, float2 *o)          // four consecutive float2 (32-byte aligned), L2 only
+{
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(p)), b = __ldcg(reinterpret_cast<const float4 *>(p) + 1);
+    o[0] = make_float2(a.x, a.y); o[1] = make_float2(a.z, a.w); o[2] = make_float2(b.x, b.y); o[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void st4_cg(float2 *p, const float2 *v)
+{
+    __stcg(reinterpret_cast<float4 *>(p), make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+    __stcg(reinterpret_cast<float4 *>(p) + 1, make_float4(v[2].x, v[2].y, v[3].x, v[3].y));
+}
 
-// Requirements checked by the host: fp32, unmodulated (K = 1), M <= 32, every column block has at least
+// Requirements checked by the host: fp32, unmodulated (K = 1), 4 <= M <= 32, every column block has at least
 // one non-zero base-matrix entry, no soft outputs (beta_soft / s_last), H = 2^LOGH.
 // scratch per CTA: [LM] float2 beta (A, B) then [Mc] float2 partial s of the current column.
 template <int LOGH>
@@ -201,9 +211,10 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
     float2 *s2col = beta2 + LM;
     const int secs_per_col = d.Mc / d.M;
     const double sec_norm = (double)d.L / d.Lc;
-    const int M = d.M, logM = d.logM;
-    const unsigned grp_base = (unsigned)lane & ~(unsigned)(M - 1);
-    const unsigned grp_mask = M == 32 ? 0xffffffffu : (((1u << M) - 1u) << grp_base);
+    // denoiser layout: a thread holds four consecutive entries of a section (both frames), LS = M/4 lanes a section
+    const int M = d.M, logM = d.logM, LS = M >> 2;
+    const unsigned grp_base = (unsigned)lane & ~(unsigned)(LS - 1);
+    const unsigned grp_mask = ((1u << LS) - 1u) << grp_base;
     const int col_lines = (d.Mc * (int)sizeof(float2) + 127) / 128;     // 128-byte lines of one column block of beta
 
     for (;;) {
@@ -327,11 +338,8 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     const OutPre pre = pairfft::transposed_run<LOGH>(buf, pd.tb, b, z2 + b.r * d.Mr, tin, tid, [&] {
                         OutPre q;
                         q.ids = pairfft::ldg_na(b.tgat + tid);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = tid + u * kPairThreads;
-                            q.pv[u] = (prev && j < d.Mc) ? __ldcg(prev + j) : make_float2(0.f, 0.f);
-                        }
+                        if (prev && 4 * tid < d.Mc) ld4_cg(prev + 4 * tid, q.pv);
+                        else q.pv[0] = q.pv[1] = q.pv[2] = q.pv[3] = make_float2(0.f, 0.f);
                         return q;
                     });
                     const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
@@ -343,79 +351,88 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     }
                     const bool last = bi == b1 - 1;
                     for (int base = 0, ch = 0; base < d.Mc; base += kPairThreads * 4, ++ch) {     // warp-uniform trip count
+                        const int j0 = base + 4 * tid;
+                        const bool live = j0 < d.Mc;               // Mc is a multiple of M >= 4: uniform over a section's lanes
                         uint2 ide = pre.ids;
                         float2 pv[4] = {pre.pv[0], pre.pv[1], pre.pv[2], pre.pv[3]};
                         if (ch > 0) {
                             ide = pairfft::ldg_na(tgat + ch * kPairThreads + tid);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int j = base + tid + u * kPairThreads;
-                                pv[u] = (prev && j < d.Mc) ? __ldcg(prev + j) : make_float2(0.f, 0.f);
-                            }
+                            if (prev && live) ld4_cg(prev + j0, pv);
+                            else pv[0] = pv[1] = pv[2] = pv[3] = make_float2(0.f, 0.f);
                         }
                         const unsigned id[4] = {ide.x & 0xFFFFu, ide.x >> 16, ide.y & 0xFFFFu, ide.y >> 16};
-                        if (!last) {
+                        float2 v[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int j = base + tid + u * kPairThreads;
-                                if (j < d.Mc) s2col[j] = pairfft::pfma(bf2[id[u]], sc2, pv[u]);
-                            }
+                        for (int u = 0; u < 4; ++u) v[u] = pairfft::pfma(bf2[live ? id[u] : 0], sc2, pv[u]);
+                        if (!last) {
+                            if (live) st4_cg(s2col + j0, v);
                             continue;
                         }
-                        // last block of the column: 32 consecutive j of a warp hold whole sections, the softmax
-                        // runs on the gathered values in registers
+                        // last block of the column: softmax of the sections on the gathered values in registers
+                        float mxA = live ? fmaxf(fmaxf(v[0].x, v[1].x), fmaxf(v[2].x, v[3].x)) : -INFINITY;
+                        float mxB = live ? fmaxf(fmaxf(v[0].y, v[1].y), fmaxf(v[2].y, v[3].y)) : -INFINITY;
+                        if (M == 32) {
+#pragma unroll
+                            for (int off = 4; off > 0; off >>= 1) {
+                                mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
+                                mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
+                            }
+                        } else {
+                            for (int off = LS >> 1; off > 0; off >>= 1) {
+                                mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
+                                mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
+                            }
+                        }
+                        // decision of this iteration: lowest index attaining the section maximum
+                        const int luA = v[0].x == mxA ? 0 : v[1].x == mxA ? 1 : v[2].x == mxA ? 2 : v[3].x == mxA ? 3 : 4;
+                        const int luB = v[0].y == mxB ? 0 : v[1].y == mxB ? 1 : v[2].y == mxB ? 2 : v[3].y == mxB ? 3 : 4;
+                        const unsigned balA = __ballot_sync(0xffffffffu, live && luA < 4) & grp_mask;
+                        const unsigned balB = __ballot_sync(0xffffffffu, live && luB < 4) & grp_mask;
+                        const int srcA = balA ? __ffs(balA) - 1 : (int)grp_base, srcB = balB ? __ffs(balB) - 1 : (int)grp_base;
+                        const int wuA = __shfl_sync(0xffffffffu, luA, srcA), wuB = __shfl_sync(0xffffffffu, luB, srcB);
+                        // e = exp((v - mx) / tau) as 2^((v - mx) log2(e) / tau)
+                        const float2 mx2 = make_float2(mxA, mxB);
+                        float2 e[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int j = base + tid + u * kPairThreads;
-                            const bool live = j < d.Mc;                       // uniform over a section's lanes
-                            const float2 v = pairfft::pfma(bf2[live ? id[u] : 0], sc2, pv[u]);
-                            float mxA = live ? v.x : -INFINITY, mxB = live ? v.y : -INFINITY;
-                            if (M == 32) {
+                            const float2 arg = pairfft::pmul(pairfft::psub(v[u], mx2), itl);
+                            e[u] = make_float2(live ? fast_ex2(arg.x) : 0.f, live ? fast_ex2(arg.y) : 0.f);
+                        }
+                        float2 sum = pairfft::padd(pairfft::padd(e[0], e[1]), pairfft::padd(e[2], e[3]));
+                        if (M == 32) {
 #pragma unroll
-                                for (int off = 16; off > 0; off >>= 1) {
-                                    mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
-                                    mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
-                                }
-                            } else {
-                                for (int off = M >> 1; off > 0; off >>= 1) {
-                                    mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, off));
-                                    mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, off));
-                                }
-                            }
-                            // decision of this iteration: lowest index attaining the section maximum
-                            const unsigned balA = __ballot_sync(0xffffffffu, live && v.x == mxA) & grp_mask;
-                            const unsigned balB = __ballot_sync(0xffffffffu, live && v.y == mxB) & grp_mask;
-                            // e = exp((v - mx) / tau) as 2^((v - mx) log2(e) / tau)
-                            const float2 arg = pairfft::pmul(pairfft::psub(v, make_float2(mxA, mxB)), itl);
-                            const float2 e = make_float2(live ? fast_ex2(arg.x) : 0.f, live ? fast_ex2(arg.y) : 0.f);
-                            float2 sum = e;
-                            if (M == 32) {
+                            for (int off = 4; off > 0; off >>= 1)
+                                sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
+                                                                     __shfl_xor_sync(0xffffffffu, sum.y, off)));
+                        } else {
+                            for (int off = LS >> 1; off > 0; off >>= 1)
+                                sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
+                                                                     __shfl_xor_sync(0xffffffffu, sum.y, off)));
+                        }
+                        if (live) {
+                            const float2 inv = make_float2(fast_rcp(sum.x), fast_rcp(sum.y));
+                            float2 bta[4];
+                            float2 tsum = make_float2(0.f, 0.f);
 #pragma unroll
-                                for (int off = 16; off > 0; off >>= 1)
-                                    sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
-                                                                         __shfl_xor_sync(0xffffffffu, sum.y, off)));
-                            } else {
-                                for (int off = M >> 1; off > 0; off >>= 1)
-                                    sum = pairfft::padd(sum, make_float2(__shfl_xor_sync(0xffffffffu, sum.x, off),
-                                                                         __shfl_xor_sync(0xffffffffu, sum.y, off)));
-                            }
-                            if (live) {
-                                const float2 inv = make_float2(fast_rcp(sum.x), fast_rcp(sum.y));
-                                const float2 bta = pairfft::pmul(e, inv);
-                                __stcg(beta2_c + j, bta);
+                            for (int u = 0; u < 4; ++u) {
+                                bta[u] = pairfft::pmul(e[u], inv);
                                 // 1 - sum beta^2 = sum beta (1 - beta), 1 - beta = (sum - e) / sum: no cancellation
-                                const float2 term = pairfft::pmul(bta, pairfft::pmul(pairfft::psub(sum, e), inv));
-                                psA += (double)term.x;
-                                psB += (double)term.y;
-                                const int sec = c * secs_per_col + (j >> logM);
-                                if (((unsigned)lane & (unsigned)(M - 1)) == 0u) {
-                                    if (actA) o.idx[fA * d.L + sec] = balA ? (int)(__ffs(balA) - 1 - (int)grp_base) : 0;
-                                    if (actB) o.idx[fB * d.L + sec] = balB ? (int)(__ffs(balB) - 1 - (int)grp_base) : 0;
-                                }
-                                if (o.nmse) {
-                                    const int k = j & (M - 1);
-                                    const float dA = bta.x - (k == idx0[fA * d.L + sec] ? 1.f : 0.f);
-                                    const float dB = bta.y - (k == idx0[fB * d.L + sec] ? 1.f : 0.f);
+                                tsum = pairfft::pfma(bta[u], pairfft::pmul(pairfft::psub(sum, e[u]), inv), tsum);
+                            }
+                            st4_cg(beta2_c + j0, bta);
+                            psA += (double)tsum.x;
+                            psB += (double)tsum.y;
+                            const int sec = c * secs_per_col + (j0 >> logM);
+                            if (((unsigned)lane & (unsigned)(LS - 1)) == 0u) {
+                                if (actA) o.idx[fA * d.L + sec] = balA && wuA < 4 ? (srcA - (int)grp_base) * 4 + wuA : 0;
+                                if (actB) o.idx[fB * d.L + sec] = balB && wuB < 4 ? (srcB - (int)grp_base) * 4 + wuB : 0;
+                            }
+                            if (o.nmse) {
+                                const int k0 = j0 & (M - 1), tA = idx0[fA * d.L + sec], tB = idx0[fB * d.L + sec];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float dA = bta[u].x - (k0 + u == tA ? 1.f : 0.f);
+                                    const float dB = bta[u].y - (k0 + u == tB ? 1.f : 0.f);
                                     nmA += (double)dA * (double)dA;
                                     nmB += (double)dB * (double)dB;
                                 }

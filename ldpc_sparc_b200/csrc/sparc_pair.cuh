@@ -88,6 +88,25 @@ template <int LOGH> __host__ __device__ constexpr int pswz(int i)
 }
 inline int pswz_rt(int logh, int i) { return logh == 12 ? pswz<12>(i) : logh == 11 ? pswz<11>(i) : pswz<10>(i); }
 
+// LSB_PAIR_FUSED (bit 0: forward, bit 1: transposed; default 3), H = 2^11 only: the real-FFT post-processing of the forward transform runs inside its
+// last radix-4 pass and the pre-processing of the transposed transform inside its first pass, which is then a radix-4
+// pass as well (plan 4,8,8,8 instead of 8,8,8,4).  A radix-4 butterfly of the H-point DIF FFT holds the frequencies
+// b + {0,1,2,3} H/4 (last pass; b = brev(q)) resp. the inputs j + {0,1,2,3} H/4 (first pass), and the mirror
+// H - k of each of them lies in the butterfly of H/4 - b resp. H/4 - j: a thread that takes both butterflies has
+// every (k, H-k) pair of the split in registers.  Each fusion saves one read and one write of the whole buffer and
+// one CTA barrier per transform (tools/model_pair_fused.py is the numpy model of the index conventions).
+#ifndef LSB_PAIR_FUSED
+#define LSB_PAIR_FUSED 3
+#endif
+template <int LOGH> __host__ __device__ constexpr bool fused_fwd() { return (LSB_PAIR_FUSED & 1) && LOGH == 11; }
+template <int LOGH> __host__ __device__ constexpr bool fused_inv() { return (LSB_PAIR_FUSED & 2) && LOGH == 11; }
+// slot swizzle of the transposed transform: its fused plan ends with a radix-8 pass of stride 1 (bits 3,4,5 -> 0,1,2)
+template <int LOGH> __host__ __device__ constexpr int pswz_t(int i) { return fused_inv<LOGH>() ? (i ^ ((i >> 3) & 7)) : pswz<LOGH>(i); }
+inline int pswz_t_rt(int logh, int i) { return logh == 11 ? pswz_t<11>(i) : pswz_rt(logh, i); }
+inline bool fused_fwd_rt(int logh) { return logh == 11 && fused_fwd<11>(); }
+inline bool fused_inv_rt(int logh) { return logh == 11 && fused_inv<11>(); }
+template <int LOGH, bool TR> __host__ __device__ constexpr int pswz_sel(int i) { return TR ? pswz_t<LOGH>(i) : pswz<LOGH>(i); }
+
 // ---- global loads that do not allocate in L1 (index tables: read once per block)
 __device__ __forceinline__ uint4 ldg_na(const uint4 *p)
 {
@@ -110,21 +129,22 @@ template <int LOGH> __host__ __device__ constexpr int plan_logs(int i)
     for (int k = 0; k < i; ++k) s -= pass_logr(s);
     return s;
 }
-template <int LOGH, int I>
-struct PassInfo {
-    static constexpr int LOGS = plan_logs<LOGH>(I), LOGR = pass_logr(LOGS), LOGQ = LOGS - LOGR;
+template <int LOGH_, int LOGS_, int LOGR_>
+struct PassX {                                                              // one DIF pass: sub-transform size 2^LOGS, radix 2^LOGR
+    static constexpr int LOGH = LOGH_, LOGS = LOGS_, LOGR = LOGR_, LOGQ = LOGS - LOGR;
     static constexpr int NB = (1 << LOGH) >> LOGR;                          // butterflies of the pass
     static constexpr int NQ = NB > kPairThreads ? NB / kPairThreads : 1;    // per thread
     static constexpr int TW_STEP = (1 << LOGH) >> LOGS;
 };
+template <int LOGH, int I>
+struct PassInfo : PassX<LOGH, plan_logs<LOGH>(I), pass_logr(plan_logs<LOGH>(I))> {};
 
 template <int NQ> struct TwPre { float2 w1[NQ], w2[NQ], w4[NQ]; };
 
-// issue the twiddle loads of pass I (nothing for the last pass: stride 1, no twiddles)
-template <int LOGH, int I, bool INV>
-__device__ __forceinline__ TwPre<PassInfo<LOGH, I>::NQ> tw_issue(const float2 *__restrict__ tw, int tid)
+// issue the twiddle loads of a pass (nothing for a pass of stride 1: no twiddles)
+template <typename PI, bool INV>
+__device__ __forceinline__ TwPre<PI::NQ> tw_issue_p(const float2 *__restrict__ tw, int tid)
 {
-    typedef PassInfo<LOGH, I> PI;
     TwPre<PI::NQ> t;
 #pragma unroll
     for (int i = 0; i < PI::NQ; ++i) {
@@ -139,6 +159,11 @@ __device__ __forceinline__ TwPre<PassInfo<LOGH, I>::NQ> tw_issue(const float2 *_
         }
     }
     return t;
+}
+template <int LOGH, int I, bool INV>
+__device__ __forceinline__ TwPre<PassInfo<LOGH, I>::NQ> tw_issue(const float2 *__restrict__ tw, int tid)
+{
+    return tw_issue_p<PassInfo<LOGH, I>, INV>(tw, tid);
 }
 
 template <int LOGR, bool INV> __device__ __forceinline__ void radix_dft(CP *v)
@@ -188,25 +213,39 @@ template <int LOGR> __device__ __forceinline__ void radix_twiddle(CP *v, float2 
     }
 }
 
-// One in-place DIF pass (pass I of the plan) on the pair buffer with its twiddles already in registers.
-template <int LOGH, int I, bool INV>
-__device__ __forceinline__ void pass_run(float4 *buf, const TwPre<PassInfo<LOGH, I>::NQ> &t, int tid)
+// One in-place DIF pass on the pair buffer with its twiddles already in registers (TR: slots of the transposed plan).
+template <typename PI, bool INV, bool TR>
+__device__ __forceinline__ void pass_run_p(float4 *buf, const TwPre<PI::NQ> &t, int tid)
 {
-    typedef PassInfo<LOGH, I> PI;
-    constexpr int R = 1 << PI::LOGR;
+    constexpr int R = 1 << PI::LOGR, LOGH = PI::LOGH;
 #pragma unroll
     for (int i = 0; i < PI::NQ; ++i) {
         const int q = tid + i * kPairThreads;
         if (PI::NB < kPairThreads && q >= PI::NB) break;
         const int j = q & ((1 << PI::LOGQ) - 1);
-        const int sb = pswz<LOGH>(((q >> PI::LOGQ) << PI::LOGS) | j);
+        const int sb = pswz_sel<LOGH, TR>(((q >> PI::LOGQ) << PI::LOGS) | j);
         CP v[R];
 #pragma unroll
-        for (int m = 0; m < R; ++m) v[m] = ld(buf, sb ^ pswz<LOGH>(m << PI::LOGQ));
+        for (int m = 0; m < R; ++m) v[m] = ld(buf, sb ^ pswz_sel<LOGH, TR>(m << PI::LOGQ));
         radix_dft<PI::LOGR, INV>(v);
         if (PI::LOGQ > 0) radix_twiddle<PI::LOGR>(v, t.w1[i], t.w2[i], t.w4[i]);
 #pragma unroll
-        for (int m = 0; m < R; ++m) st(buf, sb ^ pswz<LOGH>(m << PI::LOGQ), v[m]);
+        for (int m = 0; m < R; ++m) st(buf, sb ^ pswz_sel<LOGH, TR>(m << PI::LOGQ), v[m]);
+    }
+}
+template <int LOGH, int I, bool INV>
+__device__ __forceinline__ void pass_run(float4 *buf, const TwPre<PassInfo<LOGH, I>::NQ> &t, int tid)
+{
+    pass_run_p<PassInfo<LOGH, I>, INV, false>(buf, t, tid);
+}
+// barrier of the 64 threads of warps 2k, 2k+1 (named barriers 1..4)
+__device__ __forceinline__ void sync_warp_pair(int tid)
+{
+    switch (tid >> 6) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
     }
 }
 
@@ -216,6 +255,9 @@ struct PairTables {
     const float2 *pre;         // [H/2 + 1] natural k:       0.5 pt[k],  pt[k] = exp(-i pi k / (2N))
     const float2 *post;        // [H/2 + 1] bit-reversed t:  0.5 pt[k],  k = brev_{h-1}(t), last entry k = H/2
     const uint32_t *post_slot; // [H/2 + 1] slot of Z[k] | slot of Z[H-k] << 16 (swizzled, after the FFT)
+    // fused_inv<LOGH>() / fused_fwd<LOGH>(): pre / post are [256][4] instead, 0.5 pt[k] of the four mirror pairs of thread t (Q = H/4):
+    //   pre:  k = t, t + Q, Q - t, 2Q - t;            post: k = b, b + Q, Q - b, 2Q - b with b = brev_{h-2}(2 t);
+    //   row 0 of both: k = Q/2, 3Q/2, Q, H/2 (the two self-mirrored butterflies; k = 0 needs no factor)
 };
 
 // One non-zero block of the design for the pair kernels.  "Chunked" tables hold the entries of
@@ -226,7 +268,9 @@ struct PairBlock {
     const uint4 *fsrc;             // [2][H/8]     forward first-pass sources of butterfly q: elements m = 0..3 | 4..7, (re | im << 16)
     const uint2 *fgat;             // chunked [Mr] float2-view slot of Y[o0[i]] after the post-processing
     const uint2 *tsrc;             // [H/2+1]      transposed sources of pair k: c[k], c[N-k], c[H-k], c[H+k] (rows of the block)
-    const uint2 *tgat;             // chunked [Mc] float2-view slot of X[o1[j]] after the inverse FFT
+                                   //              fused_inv: [256][4] in the k order of PairTables::pre, then the entry of k = 0
+    const uint2 *tgat;             // [Mc] float2-view slot of X[o1[j]] after the inverse FFT, column order (thread t of
+                                   //              chunk c reads columns 1024 c + 4 t .. + 3 as one uint2), padded with kNone
 };
 __host__ __device__ constexpr int chunk_count(int n) { return (n + 4 * kPairThreads - 1) / (4 * kPairThreads); }
 
@@ -276,11 +320,20 @@ __device__ __forceinline__ FwdIn<LOGH> forward_issue(const PairTables &tb, const
     return in;
 }
 
+__device__ __forceinline__ void ld4_f2(const float2 *p, float2 *o)         // four float2 as two 16-byte loads
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    o[0] = make_float2(a.x, a.y); o[1] = make_float2(a.z, a.w); o[2] = make_float2(b.x, b.y); o[3] = make_float2(b.z, b.w);
+}
 struct PostPre { uint32_t slot[kPrePF]; float2 hp[kPrePF]; };
 template <int LOGH> __device__ __forceinline__ PostPre post_issue(const PairTables &tb, int tid)
 {
     constexpr int Hh = 1 << (LOGH - 1);
     PostPre p;
+    if constexpr (fused_fwd<LOGH>()) {
+        ld4_f2(tb.post + 4 * tid, p.hp);
+        return p;
+    }
 #pragma unroll
     for (int i = 0; i < kPrePF; ++i) {
         const int t = tid + i * kPairThreads;
@@ -306,6 +359,62 @@ __device__ __forceinline__ void post_pair(float4 *buf, uint32_t sl, float2 hp)
         const CP t2 = cmulw(Vm, half_pt_mirror(hp));
         st(buf, pb, CP{t2.re, pneg(t2.im)});
     }
+}
+
+// the same split on a mirror pair held in registers: (Z[k], Z[H-k]) -> ((Y[k], Y[N-k]), (Y[H-k], Y[H+k]))
+__device__ __forceinline__ void post_pair_reg(CP &za, CP &zb, float2 hp)
+{
+    const float2 q = q_from_half_pt(hp);
+    const CP E2 = {padd(za.re, zb.re), psub(za.im, zb.im)};
+    const CP O2 = {padd(za.im, zb.im), psub(zb.re, za.re)};
+    const CP qO = cmulw(O2, q);
+    const CP ta = cmulw(cadd(E2, qO), hp);
+    const CP Vm = {psub(E2.re, qO.re), psub(qO.im, E2.im)};
+    const CP t2 = cmulw(Vm, half_pt_mirror(hp));
+    za = CP{ta.re, pneg(ta.im)};
+    zb = CP{t2.re, pneg(t2.im)};
+}
+// Last pass of the forward transform at H = 2^11 (radix 4, stride 1) with the split fused: thread t > 0 takes the
+// butterflies q1 = 2 t (frequencies b + m' Q, b = brev(q1) < Q/2) and q2 = brev(Q - b); position 4 q + m holds the
+// frequency brev(q) + brev_2(m) Q.  Thread 0 takes the self-mirrored butterflies of b = 0 and b = Q/2.
+__device__ __forceinline__ CP csel(bool c, CP a, CP b)
+{
+    return {make_float2(c ? a.re.x : b.re.x, c ? a.re.y : b.re.y), make_float2(c ? a.im.x : b.im.x, c ? a.im.y : b.im.y)};
+}
+template <int LOGH>
+__device__ __forceinline__ void forward_last_fused(float4 *buf, const float2 *hp, int tid)
+{
+    constexpr int Q = 1 << (LOGH - 2);
+    const bool t0 = tid == 0;
+    const int q1 = 2 * tid;
+    const int b = (int)(__brev((unsigned)q1) >> (34 - LOGH));
+    const int q2 = t0 ? 1 : (int)(__brev((unsigned)(Q - b)) >> (34 - LOGH));
+    CP v[4], u[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = ld(buf, pswz<LOGH>(4 * q1 + m));
+#pragma unroll
+    for (int m = 0; m < 4; ++m) u[m] = ld(buf, pswz<LOGH>(4 * q2 + m));
+    radix_dft<2, false>(v);
+    radix_dft<2, false>(u);
+    // mirror pairs (first, second) of thread t > 0:  (v0,u3) k = b, (v2,u1) k = b + Q, (u0,v3) k = Q - b, (u2,v1) k = 2Q - b;
+    // of thread 0 (table row Q/2, 3Q/2, Q, H/2):      (u0,u3),       (u2,u1),           (v2,v3),           (v1,v1);  v0 = Z[0].
+    // Only the first members differ: select them (no divergent path: the warp of thread 0 would run both).
+    CP a0 = csel(t0, u[0], v[0]), a1 = csel(t0, u[2], v[2]), a2 = csel(t0, v[2], u[0]), a3 = csel(t0, v[1], u[2]);
+    const CP z = v[0];
+    post_pair_reg(a0, u[3], hp[0]);
+    post_pair_reg(a1, u[1], hp[1]);
+    post_pair_reg(a2, v[3], hp[2]);
+    post_pair_reg(a3, v[1], hp[3]);
+    const CP z0 = {padd(z.re, z.im), pscale(psub(z.re, z.im), 0.70710678118654752440f)};   // k = 0: (Y[0], Y[H])
+    v[0] = csel(t0, z0, a0);
+    v[2] = csel(t0, a2, a1);
+    u[0] = csel(t0, a0, a2);
+    u[2] = csel(t0, a1, a3);
+    v[1] = csel(t0, a3, v[1]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) st(buf, pswz<LOGH>(4 * q1 + m), v[m]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) st(buf, pswz<LOGH>(4 * q2 + m), u[m]);
 }
 
 struct GatPre { uint2 c[kGatPF]; };
@@ -352,6 +461,17 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
     __syncthreads();
     const auto t2 = tw_issue<LOGH, 2, false>(tb.tw, tid);
     pass_run<LOGH, 1, false>(buf, t1, tid);
+    if constexpr (fused_fwd<LOGH>()) {
+        // passes 1 and 2 of warp w both work on elements [256 w, 256 w + 256): no CTA barrier between them
+        __syncwarp();
+        const PostPre pp = post_issue<LOGH>(tb, tid);
+        pass_run<LOGH, 2, false>(buf, t2, tid);
+        __syncthreads();
+        const GatPre g = gather_issue(b.fgat, n_rows, tid);
+        forward_last_fused<LOGH>(buf, pp.hp, tid);
+        __syncthreads();
+        return g;
+    }
     __syncthreads();
     pass_run<LOGH, 2, false>(buf, t2, tid);
     __syncthreads();
@@ -411,6 +531,13 @@ __device__ __forceinline__ TrIn transposed_issue(const PairTables &tb, const Pai
 {
     constexpr int Hh = 1 << (LOGH - 1);
     TrIn in;
+    if constexpr (fused_inv<LOGH>()) {
+        const uint4 a = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid), c = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid + 1);
+        in.src[0] = make_uint2(a.x, a.y); in.src[1] = make_uint2(a.z, a.w);
+        in.src[2] = make_uint2(c.x, c.y); in.src[3] = make_uint2(c.z, c.w);
+        ld4_f2(tb.pre + 4 * tid, in.hp);
+        return in;
+    }
 #pragma unroll
     for (int i = 0; i < kPrePF; ++i) {
         const int k = tid + i * kPairThreads;
@@ -443,6 +570,69 @@ __device__ __forceinline__ void pre_pair(float4 *buf, const float2 *y2, int k, u
     if (k != Hh) st(buf, pswz<LOGH>(H - k), CP{padd(A.re, B.im), psub(B.re, A.im)});   // conj(A) + i conj(B)
 }
 
+// the pre-processing of one mirror pair into registers: rows (c[k], c[N-k]) and (c[H-k], c[H+k]) -> Z[k], Z[H-k]
+__device__ __forceinline__ void pre_pair_reg(const float2 *y2, uint2 e, float2 hp, CP &zk, CP &zm)
+{
+    const unsigned a0 = e.x & 0xFFFFu, a1 = e.x >> 16, b0 = e.y & 0xFFFFu, b1 = e.y >> 16;
+    const P zero = make_float2(0.f, 0.f);
+    const CP ca = {a0 != kNone ? y2[a0] : zero, a1 != kNone ? y2[a1] : zero};
+    const CP cb = {b0 != kNone ? y2[b0] : zero, b1 != kNone ? y2[b1] : zero};
+    const float2 q = q_from_half_pt(hp);
+    const CP U = cmulw(ca, hp), V = cmulw(cb, half_pt_mirror(hp));
+    const CP A = {padd(U.re, V.re), psub(V.im, U.im)};
+    const CP D = {psub(U.re, V.re), pneg(padd(U.im, V.im))};
+    const CP B = cmulw(D, make_float2(q.x, -q.y));
+    zk = CP{psub(A.re, B.im), padd(A.im, B.re)};
+    zm = CP{padd(A.re, B.im), psub(B.re, A.im)};
+}
+// First pass of the transposed transform at H = 2^11 (radix 4, stride Q = H/4) with the pre-processing fused:
+// thread t > 0 builds the inputs j + m Q of butterfly j = t and jp + m Q of butterfly jp = Q - t from its four
+// mirror pairs; thread 0 takes j = 0 and jp = Q/2 (self-mirrored).  `in` holds the pairs in the order of
+// PairTables::pre.
+template <int LOGH>
+__device__ __forceinline__ void transposed_first_fused(float4 *buf, const float2 *__restrict__ tw, const PairBlock &b,
+                                                       const float2 *y2, const TrIn &in, int tid)
+{
+    constexpr int Q = 1 << (LOGH - 2);
+    const bool t0 = tid == 0;
+    const int j = tid, jp = t0 ? Q / 2 : Q - tid;
+    // inverse twiddles w^j, w^2j (w = exp(2 pi i / H)); those of Q - j follow exactly: w^(Q-j) = i conj(w^j), w^(2Q-2j) = -conj(w^2j)
+    float2 w1j = __ldg(tw + j), w2j = __ldg(tw + 2 * j);
+    w1j.y = -w1j.y; w2j.y = -w2j.y;
+    const float kR = 0.70710678118654752440f;
+    const float2 w1p = t0 ? make_float2(kR, kR) : make_float2(w1j.y, w1j.x);
+    const float2 w2p = t0 ? make_float2(0.f, 1.f) : make_float2(-w2j.x, w2j.y);
+    // mirror pairs of thread t > 0 (rows k = j, j + Q, Q - j, 2Q - j) give (v0,u3), (v1,u2), (u0,v3), (u1,v2);
+    // those of thread 0 (rows k = Q/2, 3Q/2, Q, H/2)                 give (u0,u3), (u1,u2), (v1,v3), (v2,--), v0 from k = 0.
+    // Only the first members land elsewhere: select them (no divergent path: the warp of thread 0 would run both).
+    CP a0, a1, a2, a3, v[4], u[4];
+    pre_pair_reg(y2, in.src[0], in.hp[0], a0, u[3]);
+    pre_pair_reg(y2, in.src[1], in.hp[1], a1, u[2]);
+    pre_pair_reg(y2, in.src[2], in.hp[2], a2, v[3]);
+    pre_pair_reg(y2, in.src[3], in.hp[3], a3, v[2]);
+    CP z0 = a0;
+    if (t0) {
+        const uint2 e0 = ldg_na(b.tsrc + 4 * kPairThreads);      // k = 0: (c[0], c[H])
+        const unsigned r0 = e0.x & 0xFFFFu, r1 = e0.x >> 16;
+        const P zero = make_float2(0.f, 0.f);
+        const P c0 = r0 != kNone ? y2[r0] : zero, wH = pscale(r1 != kNone ? y2[r1] : zero, kR);
+        z0 = CP{padd(c0, wH), psub(c0, wH)};
+    }
+    v[0] = z0;
+    v[1] = csel(t0, a2, a1);
+    u[0] = csel(t0, a0, a2);
+    u[1] = csel(t0, a1, a3);
+    v[2] = csel(t0, a3, v[2]);
+    radix_dft<2, true>(v);
+    radix_dft<2, true>(u);
+    radix_twiddle<2>(v, w1j, w2j, w2j);
+    radix_twiddle<2>(u, w1p, w2p, w2p);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) st(buf, pswz_t<LOGH>(j + m * Q), v[m]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) st(buf, pswz_t<LOGH>(jp + m * Q), u[m]);
+}
+
 // buf <- DCT-III of the row block y2 (shared memory, float2 per entry) scattered to its rows; the inverse
 // FFT leaves X in bit-reversed slots (tgat knows them).  `in` was issued by transposed_issue() for this
 // block.  Overwrites buf from the start; issue_out() is called before the last pass so the caller's loads
@@ -452,6 +642,24 @@ __device__ __forceinline__ auto transposed_run(float4 *buf, const PairTables &tb
                                                const TrIn &in, int tid, IssueOut issue_out) -> decltype(issue_out())
 {
     constexpr int Hh = 1 << (LOGH - 1);
+    if constexpr (fused_inv<LOGH>()) {
+        typedef PassX<LOGH, LOGH - 2, 3> P1;
+        typedef PassX<LOGH, LOGH - 5, 3> P2;
+        typedef PassX<LOGH, LOGH - 8, 3> P3;
+        static_assert(P3::LOGQ == 0 && P1::NQ == 1, "plan 4,8,8,8 with one butterfly per thread");
+        transposed_first_fused<LOGH>(buf, tb.tw, b, y2, in, tid);
+        const auto t1 = tw_issue_p<P1, true>(tb.tw, tid);
+        __syncthreads();
+        const auto t2 = tw_issue_p<P2, true>(tb.tw, tid);
+        pass_run_p<P1, true, true>(buf, t1, tid);
+        sync_warp_pair(tid);                      // pass 1 of warps 2k, 2k+1 covers one 512-element sub-transform
+        pass_run_p<P2, true, true>(buf, t2, tid);
+        __syncwarp();                             // passes 2 and 3 of warp w both work on elements [256 w, 256 w + 256)
+        const auto out = issue_out();
+        pass_run_p<P3, true, true>(buf, TwPre<P3::NQ>(), tid);
+        __syncthreads();
+        return out;
+    }
     const auto t0 = tw_issue<LOGH, 0, true>(tb.tw, tid);
 #pragma unroll
     for (int i = 0; i < kPrePF; ++i) {
