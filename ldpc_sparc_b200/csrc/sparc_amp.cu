@@ -944,8 +944,10 @@ template <int LOGH>
 int launch_amp_pair_h(lsb_sparc_design *g, const float *y, int64_t n_frames, const AmpParams &p, const int32_t *idx0,
                       const AmpOut &o, cudaStream_t st)
 {
+    static_assert(sizeof(PairBlock) % sizeof(uint2) == 0, "descriptor copied as 8-byte words");
+    const bool cached = LSB_PAIR_CACHE && pair_design_cached(g->dev.Lr, g->dev.Lc, g->dev.n_blocks);
     const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc);
-    auto kernel = amp_pair_kernel<LOGH>;
+    auto kernel = cached ? amp_pair_kernel<LOGH, true> : amp_pair_kernel<LOGH, false>;
     LSB_CUDA(lsb::ensure_dynamic_smem(kernel, smem));
     if (g->amp_grid_pair == 0) {
         int per_sm = 0;

@@ -174,6 +174,18 @@ az_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ y, float *__re
 }
 
 // ------------------------------------------------------------------ AMP
+// Base matrix, column offsets and block descriptors of the design, copied into shared memory at kernel start when
+// they fit (CACHED): the block loop reads the next descriptor and immediately uses its table pointers, the column
+// loop branches on col_first, the gamma / tau loops walk W -- from global memory each is an exposed L2 round trip
+// (ncu: long-scoreboard stalls at these loads), from shared memory a 30-cycle load.
+// (Static arrays: their addresses are compile-time constants, so the cache costs no registers; a pointer into dynamic
+// shared memory behind the run-time sized vectors did, and the kernel spilled.)
+#ifndef LSB_PAIR_CACHE
+#define LSB_PAIR_CACHE 1
+#endif
+constexpr int kCacheBlocks = 48, kCacheCols = 63, kCacheW = 64;
+inline bool pair_design_cached(int Lr, int Lc, int n_blocks) { return n_blocks <= kCacheBlocks && Lc <= kCacheCols && Lr * Lc <= kCacheW; }
+
 struct OutPre {                    // first chunk of the gather after a transposed transform: 4 slots + the 4 addends
     uint2 ids;
     float2 pv[4];
@@ -192,7 +204,7 @@ __device__ __forceinline__ void st4_cg(float2 *p, const float2 *v)
 // Requirements checked by the host: fp32, unmodulated (K = 1), 4 <= M <= 32, every column block has at least
 // one non-zero base-matrix entry, no soft outputs (beta_soft / s_last), H = 2^LOGH.
 // scratch per CTA: [LM] float2 beta (A, B) then [Mc] float2 partial s of the current column.
-template <int LOGH>
+template <int LOGH, bool CACHED>
 __global__ void __launch_bounds__(kPairThreads, LSB_AMP_PAIR_OCC)
 amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ y_all,
                 const int32_t *__restrict__ idx0, AmpOut o, float2 *__restrict__ scratch, long long n_frames,
@@ -204,6 +216,20 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
     float4 *buf = reinterpret_cast<float4 *>(smem);           // [H] (re_A, re_B, im_A, im_B)
     float2 *z2 = reinterpret_cast<float2 *>(buf + H + pairfft::stage_slots<LOGH>());         // [n] residual of frame A / frame B
     const PairScalars S{reinterpret_cast<double *>(smem + pair_vec_bytes(LOGH, d.n)), d.Lc, d.Lr};
+    __shared__ __align__(16) PairBlock c_blocks[CACHED ? kCacheBlocks : 1];
+    __shared__ int c_col_first[CACHED ? kCacheCols + 1 : 1];
+    __shared__ double c_W[CACHED ? kCacheW : 1];
+    if (CACHED) {
+        for (int i = threadIdx.x; i < d.Lr * d.Lc; i += kPairThreads) c_W[i] = d.W[i];
+        for (int i = threadIdx.x; i <= d.Lc; i += kPairThreads) c_col_first[i] = d.col_first[i];
+        const int words = d.n_blocks * (int)(sizeof(PairBlock) / sizeof(uint2));
+        for (int i = threadIdx.x; i < words; i += kPairThreads)
+            reinterpret_cast<uint2 *>(c_blocks)[i] = reinterpret_cast<const uint2 *>(pd.blocks)[i];
+        __syncthreads();
+    }
+#define LSB_DV_BLOCKS (CACHED ? (const PairBlock *)c_blocks : pd.blocks)
+#define LSB_DV_COLS (CACHED ? (const int *)c_col_first : d.col_first)
+#define LSB_DV_W (CACHED ? (const double *)c_W : d.W)
     __shared__ double part_psi[2][kWarps][2], part_nm[2][kWarps][2];   // [column parity][warp][frame]
     __shared__ double part_z[kWarps][2];
     __shared__ long long s_frame;
@@ -247,7 +273,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             if (tid < 128) {
                 if (ix < Lr) {
                     double g = 0.0;
-                    for (int c = 0; c < Lc; ++c) g += d.W[ix * Lc + c] * S.psi()[fr * Lc + c];
+                    for (int c = 0; c < Lc; ++c) g += LSB_DV_W[ix * Lc + c] * S.psi()[fr * Lc + c];
                     g /= Lc;
                     S.gam()[fr * Lr + ix] = g;
                     reinterpret_cast<float *>(&S.coef_f()[ix])[fr] = t > 0 ? (float)(g / S.phi()[fr * Lr + ix]) : 0.f;
@@ -259,9 +285,9 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             if (t > 0) {
                 // z = y - A beta + b z (:944-946): z <- y + b z, then every block subtracts its A_rc beta_c.
                 // Row i is owned by thread i mod 256 here and in gather_add: no barrier in between.
-                PairBlock b = pd.blocks[0];
+                PairBlock b = LSB_DV_BLOCKS[0];
                 pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid, buf);
-                if (d.n_blocks > 1 && tid < col_lines) pairfft::prefetch_l2(beta2 + (size_t)pd.blocks[1].c * d.Mc + tid * 16);
+                if (d.n_blocks > 1 && tid < col_lines) pairfft::prefetch_l2(beta2 + (size_t)LSB_DV_BLOCKS[1].c * d.Mc + tid * 16);
                 if (Lr == 1) {
                     const float2 cf = S.coef_f()[0];
                     for (int i = tid; i < d.n; i += kPairThreads) z2[i] = pairfft::pfma(z2[i], cf, make_float2(yA[i], yB[i]));
@@ -274,11 +300,11 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                         pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, fin, d.Mr, tid);
                     PairBlock bn = b;
                     if (bi + 1 < d.n_blocks) {
-                        bn = pd.blocks[bi + 1];
+                        bn = LSB_DV_BLOCKS[bi + 1];
                         fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid, buf);
                         // the column block after that: pull it into L2 (beta streams through DRAM between iterations)
                         if (bi + 2 < d.n_blocks && tid < col_lines)
-                            pairfft::prefetch_l2(beta2 + (size_t)pd.blocks[bi + 2].c * d.Mc + tid * 16);
+                            pairfft::prefetch_l2(beta2 + (size_t)LSB_DV_BLOCKS[bi + 2].c * d.Mc + tid * 16);
                     }
                     pairfft::gather_add(z2 + b.r * d.Mr, buf, g, b.fgat, -b.scale, d.Mr, tid);
                     __syncthreads();
@@ -316,10 +342,10 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             if (tid < 128 && ix < Lc) {
                 double tc;
                 if (Lr == 1) {
-                    tc = ((double)d.L * S.phi()[fr * Lr] / d.n) / d.W[ix];
+                    tc = ((double)d.L * S.phi()[fr * Lr] / d.n) / LSB_DV_W[ix];
                 } else {
                     double acc_w = 0.0;
-                    for (int r = 0; r < Lr; ++r) acc_w += d.W[r * Lc + ix] / S.phi()[fr * Lr + r];
+                    for (int r = 0; r < Lr; ++r) acc_w += LSB_DV_W[r * Lc + ix] / S.phi()[fr * Lr + r];
                     tc = ((double)d.L / d.Mr) / acc_w;
                 }
                 S.tau()[fr * Lc + ix] = tc;
@@ -331,12 +357,12 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             const bool actA = s_active[0] != 0, actB = s_active[1] != 0;
             // ---- s = beta + tau * Az(z / phi) column block by column block (:972), softmax denoiser (:429-432),
             //      MAP decision argmax(s) of this iteration (:997)
-            PairBlock b = pd.blocks[0];
+            PairBlock b = LSB_DV_BLOCKS[0];
             pairfft::TrIn tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid, buf);
             for (int c = 0; c < Lc; ++c) {
                 const float2 tau2 = S.tau_f()[c], itl = S.itau_f()[c];
                 float2 *beta2_c = beta2 + (size_t)c * d.Mc;
-                const int b0 = d.col_first[c], b1 = d.col_first[c + 1];
+                const int b0 = LSB_DV_COLS[c], b1 = LSB_DV_COLS[c + 1];
                 if (t > 0 && c + 1 < Lc && tid < col_lines) pairfft::prefetch_l2(beta2_c + d.Mc + tid * 16);
                 double psA = 0.0, psB = 0.0, nmA = 0.0, nmB = 0.0;
                 for (int bi = b0; bi < b1; ++bi) {
@@ -352,7 +378,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     const float2 sc2 = pairfft::pmul(pairfft::pscale(tau2, b.scale), S.iphi_f()[b.r]);   // scale tau_c / phi_r
                     const uint2 *tgat = b.tgat;
                     if (bi + 1 < d.n_blocks) {                   // next block (this column or the next): start its table loads
-                        b = pd.blocks[bi + 1];
+                        b = LSB_DV_BLOCKS[bi + 1];
                         tin = pairfft::transposed_issue<LOGH>(pd.tb, b, tid, buf);
                     }
                     const bool last = bi == b1 - 1;
@@ -501,3 +527,6 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
         __syncthreads();
     }
 }
+#undef LSB_DV_BLOCKS
+#undef LSB_DV_COLS
+#undef LSB_DV_W

@@ -310,7 +310,7 @@ __device__ __forceinline__ float2 q_from_half_pt(float2 hp)
 #define LSB_PAIR_GAT_EARLY 0
 #endif
 #ifndef LSB_PAIR_OUT_EARLY
-#define LSB_PAIR_OUT_EARLY 0
+#define LSB_PAIR_OUT_EARLY 1
 #endif
 #ifndef LSB_PAIR_PREPF
 #define LSB_PAIR_PREPF 5
