@@ -786,7 +786,7 @@ int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t 
         for (int t = 0; t < kPairThreads; ++t)
             for (int s = 0; s < 4; ++s) {
                 const int k = pair_fused_k(h, t, s, false);
-                for (int e = 0; e < 4; ++e) t4[((size_t)t * 4 + s) * 4 + e] = tsrc[(size_t)k * 4 + e];
+                for (int e = 0; e < 4; ++e) t4[(((size_t)(s / 2) * kPairThreads + t) * 2 + (s % 2)) * 4 + e] = tsrc[(size_t)k * 4 + e];
             }
         for (int e = 0; e < 4; ++e) t4[(size_t)4 * kPairThreads * 4 + e] = tsrc[e];
         tsrc.swap(t4);

@@ -105,10 +105,13 @@ template <int LOGH> __host__ __device__ constexpr int pswz_t(int i) { return fus
 inline int pswz_t_rt(int logh, int i) { return logh == 11 ? pswz_t<11>(i) : pswz_rt(logh, i); }
 inline bool fused_fwd_rt(int logh) { return logh == 11 && fused_fwd<11>(); }
 inline bool fused_inv_rt(int logh) { return logh == 11 && fused_inv<11>(); }
-// LSB_PAIR_STAGE (default 1), H = 2^11: the index tables of the NEXT transform (32 bytes per thread) travel global ->
+// LSB_PAIR_STAGE (default 1), H = 2^11: the index table of the NEXT transform (32 bytes per thread) travels global ->
 // shared memory with cp.async into a staging area behind the FFT buffer instead of waiting in registers: the kernel
 // runs at its register limit, and prefetched table registers that live across the denoiser / the row gather were
 // spilled -- the spill store waits for the load, which defeats the prefetch (ncu: long-scoreboard stalls on STL / LDL).
+// A warp's 16-byte copies read consecutive addresses (an LDGSTS costs one shared-memory wavefront per 32-byte sector it
+// receives: 31 per warp instruction with a 32-byte stride, 11 contiguous).  Measured alternative: one 8 KB
+// cp.async.bulk per table with an mbarrier (thread 0 issues, all threads poll) -- 65.9 k against 68.8 k frames/s.
 #ifndef LSB_PAIR_STAGE
 #define LSB_PAIR_STAGE 1
 #endif
@@ -117,12 +120,20 @@ template <int LOGH> __host__ __device__ constexpr bool stage_inv() { return LSB_
 // float4 slots of the staging area that follows the FFT buffer: [2][256] (thread t owns slots t and 256 + t)
 template <int LOGH> __host__ __device__ constexpr int stage_slots() { return (stage_fwd<LOGH>() || stage_inv<LOGH>()) ? 2 * kPairThreads : 0; }
 inline int stage_slots_rt(int logh) { return logh == 11 ? stage_slots<11>() : 0; }
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+template <int LOGH> __device__ __forceinline__ float4 *stage_of(float4 *buf) { return buf + (1 << LOGH); }
+// thread t: entries t and 256 + t of a [2][256] uint4 table -> its two staging slots (it alone reads them back)
+template <int LOGH> __device__ __forceinline__ void stage_issue(float4 *buf, const void *table, int tid)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+    const uint4 *src = reinterpret_cast<const uint4 *>(table);
+    float4 *stage = stage_of<LOGH>(buf);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(stage + tid)), "l"(src + tid) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(stage + kPairThreads + tid)),
+                 "l"(src + kPairThreads + tid)
+                 : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// this thread's own 32 bytes have landed: no barrier needed
+template <int LOGH> __device__ __forceinline__ void stage_wait(float4 *) { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int LOGH, bool TR> __host__ __device__ constexpr int pswz_sel(int i) { return TR ? pswz_t<LOGH>(i) : pswz<LOGH>(i); }
 
@@ -287,7 +298,7 @@ struct PairBlock {
     const uint4 *fsrc;             // [2][H/8]     forward first-pass sources of butterfly q: elements m = 0..3 | 4..7, (re | im << 16)
     const uint2 *fgat;             // chunked [Mr] float2-view slot of Y[o0[i]] after the post-processing
     const uint2 *tsrc;             // [H/2+1]      transposed sources of pair k: c[k], c[N-k], c[H-k], c[H+k] (rows of the block)
-                                   //              fused_inv: [256][4] in the k order of PairTables::pre, then the entry of k = 0
+                                   //              fused_inv: [2][256] uint4 -- pairs 0,1 then pairs 2,3 of thread t, k order of PairTables::pre --, then the entry of k = 0
     const uint2 *tgat;             // [Mc] float2-view slot of X[o1[j]] after the inverse FFT, column order (thread t of
                                    //              chunk c reads columns 1024 c + 4 t .. + 3 as one uint2), padded with kNone
 };
@@ -333,11 +344,8 @@ __device__ __forceinline__ FwdIn<LOGH> forward_issue(const PairTables &tb, const
     typedef PassInfo<LOGH, 0> PI;
     FwdIn<LOGH> in;
     if constexpr (stage_fwd<LOGH>()) {
-        static_assert(PI::NQ == 1 && PI::NB == kPairThreads, "one first-pass butterfly per thread");
-        float4 *stage = buf + (1 << LOGH);
-        cp_async16(stage + tid, b.fsrc + tid);
-        cp_async16(stage + kPairThreads + tid, b.fsrc + PI::NB + tid);
-        cp_async_commit();
+        static_assert(PI::NQ == 1 && PI::NB == kPairThreads, "one first-pass butterfly per thread: fsrc is [2][256] uint4");
+        stage_issue<LOGH>(buf, b.fsrc, tid);
         return in;
     }
 #pragma unroll
@@ -475,8 +483,8 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
     uint4 sa[P0::NQ], sb4[P0::NQ];
     TwPre<P0::NQ> tw0;
     if constexpr (stage_fwd<LOGH>()) {
-        cp_async_wait_all();                              // this thread's own 32 bytes: no barrier needed
-        const uint4 *stage = reinterpret_cast<const uint4 *>(buf + (1 << LOGH));
+        stage_wait<LOGH>(buf);
+        const uint4 *stage = reinterpret_cast<const uint4 *>(stage_of<LOGH>(buf));
         sa[0] = stage[tid];
         sb4[0] = stage[kPairThreads + tid];
         tw0 = tw_issue<LOGH, 0, false>(tb.tw, tid);
@@ -584,15 +592,11 @@ __device__ __forceinline__ TrIn transposed_issue(const PairTables &tb, const Pai
     constexpr int Hh = 1 << (LOGH - 1);
     TrIn in;
     if constexpr (stage_inv<LOGH>()) {
-        float4 *stage = buf + (1 << LOGH);
-        const uint4 *src = reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid;
-        cp_async16(stage + tid, src);
-        cp_async16(stage + kPairThreads + tid, src + 1);
-        cp_async_commit();
+        stage_issue<LOGH>(buf, b.tsrc, tid);
         return in;
     }
     if constexpr (fused_inv<LOGH>()) {
-        const uint4 a = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid), c = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + 2 * tid + 1);
+        const uint4 a = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + tid), c = ldg_na(reinterpret_cast<const uint4 *>(b.tsrc) + kPairThreads + tid);
         in.src[0] = make_uint2(a.x, a.y); in.src[1] = make_uint2(a.z, a.w);
         in.src[2] = make_uint2(c.x, c.y); in.src[3] = make_uint2(c.z, c.w);
         ld4_f2(tb.pre + 4 * tid, in.hp);
@@ -668,8 +672,8 @@ __device__ __forceinline__ void transposed_first_fused(float4 *buf, const float2
     uint2 src[4];
     float2 hp[4];
     if constexpr (stage_inv<LOGH>()) {
-        cp_async_wait_all();                              // this thread's own 32 bytes: no barrier needed
-        const uint4 *stage = reinterpret_cast<const uint4 *>(buf + (1 << LOGH));
+        stage_wait<LOGH>(buf);
+        const uint4 *stage = reinterpret_cast<const uint4 *>(stage_of<LOGH>(buf));
         const uint4 a = stage[tid], c = stage[kPairThreads + tid];
         src[0] = make_uint2(a.x, a.y); src[1] = make_uint2(a.z, a.w); src[2] = make_uint2(c.x, c.y); src[3] = make_uint2(c.z, c.w);
         ld4_f2(tb_pre + 4 * tid, hp);
