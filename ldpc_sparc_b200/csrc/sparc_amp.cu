@@ -722,18 +722,6 @@ bool pair_fits(const lsb_sparc_design *g)
            pair_amp_dyn_smem(g->dev.h, g->dev.n, g->dev.Lr, g->dev.Lc) + 4096 <= (size_t)lsb::max_smem_optin();
 }
 
-// "chunked" layout of a per-element uint16 table (sparc_pair.cuh): element tid + 256 u sits at [u / 4][tid][u % 4]
-std::vector<uint16_t> chunked(const std::vector<uint16_t> &v)
-{
-    const int n = (int)v.size(), nc = pairfft::chunk_count(n);
-    std::vector<uint16_t> out((size_t)nc * kPairThreads * 4, pairfft::kNone);
-    for (int i = 0; i < n; ++i) {
-        const int tid = i % kPairThreads, u = i / kPairThreads;
-        out[((size_t)(u / 4) * kPairThreads + tid) * 4 + (u % 4)] = v[i];
-    }
-    return out;
-}
-
 // Mirror pair s (0..3) of thread t in the fused first pass of the transposed transform (post = false) or the fused
 // last pass of the forward transform (post = true) at H = 2^h, Q = H/4 (sparc_pair.cuh: PairTables)
 inline int pair_fused_k(int h, int t, int s, bool post)
@@ -742,6 +730,67 @@ inline int pair_fused_k(int h, int t, int s, bool post)
     if (t == 0) return s == 0 ? Q / 2 : s == 1 ? 3 * Q / 2 : s == 2 ? Q : 2 * Q;
     const int b = post ? brev_host(2 * t, h - 2) : t;
     return s == 0 ? b : s == 1 ? b + Q : s == 2 ? Q - b : 2 * Q - b;
+}
+
+// Order of the row gather of one block (sparc_pair.cuh: PairBlock::fgat).  Row i reads the float2 slot id[i] of the FFT
+// buffer and updates entry row0 + i of the residual; a 64-bit shared-memory access of a warp is served one half-warp
+// at a time and is conflict free when its 16 lanes hit 16 different bank pairs.  Rows are the edges of a bipartite
+// multigraph between the bank pairs of the residual ((row0 + i) mod 16) and those of the buffer (id mod 16); a proper
+// edge colouring with Delta = max degree colours (Koenig: alternating-path recolouring) splits them into Delta half-warp
+// groups that are conflict free on both sides.  Group c goes to half-warp c mod 16 of the CTA, slot c / 16 of its
+// threads, lane = the row's residual bank pair.  Returns [chunks][256][4] words row | id << 16, 0xFFFFFFFF = empty.
+std::vector<uint32_t> schedule_row_gather(const std::vector<uint16_t> &id, int row0, int *chunks_out)
+{
+    const int n = (int)id.size();
+    std::vector<int> eu(n), ev(n), col(n, -1);
+    int degu[16] = {0}, degv[16] = {0};
+    for (int i = 0; i < n; ++i) {
+        eu[i] = (row0 + i) & 15;
+        ev[i] = id[i] & 15;
+        ++degu[eu[i]];
+        ++degv[ev[i]];
+    }
+    int delta = 1;
+    for (int k = 0; k < 16; ++k) delta = std::max(delta, std::max(degu[k], degv[k]));
+    std::vector<int> atu((size_t)16 * delta, -1), atv((size_t)16 * delta, -1);     // edge of colour c at a node, or -1
+    std::vector<int> path;
+    for (int e = 0; e < n; ++e) {
+        const int u = eu[e], v = ev[e];
+        int a = 0, b = 0;
+        while (atu[(size_t)u * delta + a] >= 0) ++a;       // free at u
+        while (atv[(size_t)v * delta + b] >= 0) ++b;       // free at v
+        if (a != b) {
+            // alternating a / b path from v (it cannot reach u: left nodes are entered through colour a, free at u)
+            path.clear();
+            int x = v, c = a;
+            bool right = true;
+            for (;;) {
+                const int e2 = right ? atv[(size_t)x * delta + c] : atu[(size_t)x * delta + c];
+                if (e2 < 0) break;
+                path.push_back(e2);
+                x = right ? eu[e2] : ev[e2];
+                right = !right;
+                c = c == a ? b : a;
+            }
+            for (int e2 : path) { atu[(size_t)eu[e2] * delta + col[e2]] = -1; atv[(size_t)ev[e2] * delta + col[e2]] = -1; }
+            for (int e2 : path) {
+                col[e2] = col[e2] == a ? b : a;
+                atu[(size_t)eu[e2] * delta + col[e2]] = e2;
+                atv[(size_t)ev[e2] * delta + col[e2]] = e2;
+            }
+        }
+        col[e] = a;
+        atu[(size_t)u * delta + a] = e;
+        atv[(size_t)v * delta + a] = e;
+    }
+    const int slots = (delta + 15) / 16, chunks = (slots + 3) / 4;
+    std::vector<uint32_t> out((size_t)chunks * kPairThreads * 4, 0xFFFFFFFFu);
+    for (int e = 0; e < n; ++e) {
+        const int c = col[e], slot = c / 16, tid = (c % 16) * 16 + eu[e];
+        out[((size_t)(slot / 4) * kPairThreads + tid) * 4 + (slot % 4)] = (uint32_t)e | ((uint32_t)id[e] << 16);
+    }
+    *chunks_out = chunks;
+    return out;
 }
 
 // Host-side tables of one non-zero block for the pair kernels (index conventions in sparc_pair.cuh).
@@ -800,8 +849,14 @@ int build_pair_block(lsb_sparc_design *g, int h, int Mr, int Mc, const uint32_t 
     const uint16_t *p16 = nullptr;
     if ((rc = dev_upload(g, &p16, fsrc))) return rc;
     pb->fsrc = reinterpret_cast<const uint4 *>(p16);
-    if ((rc = dev_upload(g, &p16, chunked(fgat)))) return rc;
-    pb->fgat = reinterpret_cast<const uint2 *>(p16);
+    {
+        int chunks = 0;
+        const std::vector<uint32_t> sched = schedule_row_gather(fgat, pb->r * Mr, &chunks);
+        const uint32_t *p32 = nullptr;
+        if ((rc = dev_upload(g, &p32, sched))) return rc;
+        pb->fgat = reinterpret_cast<const uint4 *>(p32);
+        pb->gat_chunks = chunks;
+    }
     if ((rc = dev_upload(g, &p16, tsrc))) return rc;
     pb->tsrc = reinterpret_cast<const uint2 *>(p16);
     tgat.resize((size_t)pairfft::chunk_count(Mc) * kPairThreads * 4, pairfft::kNone);   // four consecutive columns per thread

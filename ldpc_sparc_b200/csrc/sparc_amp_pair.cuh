@@ -101,13 +101,13 @@ ab_pair_kernel(DesignDev d, PairDev pd, const float *__restrict__ x, float *__re
         for (int bi = 0; bi < d.n_blocks; ++bi) {
             const size_t off = (size_t)b.c * d.Mc;
             const pairfft::GatPre g =
-                pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcTwo{x + fA * LM + off, x + fB * LM + off}, fin, d.Mr, tid);
+                pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcTwo{x + fA * LM + off, x + fB * LM + off}, fin, tid);
             PairBlock bn = b;
             if (bi + 1 < d.n_blocks) {
                 bn = pd.blocks[bi + 1];
                 fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid, buf);
             }
-            pairfft::gather_add(acc2 + b.r * d.Mr, buf, g, b.fgat, b.scale, d.Mr, tid);
+            pairfft::gather_add(acc2 + b.r * d.Mr, buf, g, b.fgat, b.scale, b.gat_chunks, tid);
             __syncthreads();
             b = bn;
         }
@@ -284,7 +284,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
             __syncthreads();
             if (t > 0) {
                 // z = y - A beta + b z (:944-946): z <- y + b z, then every block subtracts its A_rc beta_c.
-                // Row i is owned by thread i mod 256 here and in gather_add: no barrier in between.
+                // (the barriers inside the first transform order this update before the first row gather)
                 PairBlock b = LSB_DV_BLOCKS[0];
                 pairfft::FwdIn<LOGH> fin = pairfft::forward_issue<LOGH>(pd.tb, b, tid, buf);
                 if (d.n_blocks > 1 && tid < col_lines) pairfft::prefetch_l2(beta2 + (size_t)LSB_DV_BLOCKS[1].c * d.Mc + tid * 16);
@@ -297,7 +297,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                 }
                 for (int bi = 0; bi < d.n_blocks; ++bi) {
                     const pairfft::GatPre g =
-                        pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, fin, d.Mr, tid);
+                        pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, fin, tid);
                     PairBlock bn = b;
                     if (bi + 1 < d.n_blocks) {
                         bn = LSB_DV_BLOCKS[bi + 1];
@@ -306,7 +306,7 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                         if (bi + 2 < d.n_blocks && tid < col_lines)
                             pairfft::prefetch_l2(beta2 + (size_t)LSB_DV_BLOCKS[bi + 2].c * d.Mc + tid * 16);
                     }
-                    pairfft::gather_add(z2 + b.r * d.Mr, buf, g, b.fgat, -b.scale, d.Mr, tid);
+                    pairfft::gather_add(z2 + b.r * d.Mr, buf, g, b.fgat, -b.scale, b.gat_chunks, tid);
                     __syncthreads();
                     b = bn;
                 }

@@ -295,8 +295,12 @@ struct PairTables {
 struct PairBlock {
     int r, c;
     float scale;                   // sqrt(2 W[r,c] / L)
+    int gat_chunks;                // uint4 chunks (4 slots) per thread of fgat
     const uint4 *fsrc;             // [2][H/8]     forward first-pass sources of butterfly q: elements m = 0..3 | 4..7, (re | im << 16)
-    const uint2 *fgat;             // chunked [Mr] float2-view slot of Y[o0[i]] after the post-processing
+    const uint4 *fgat;             // [gat_chunks][256] x 4 slots: row i | float2-view slot of Y[o0[i]] << 16 (after the
+                                   //              post-processing), 0xFFFFFFFF = empty.  The rows are scheduled so that the 16
+                                   //              lanes of a half-warp hit 16 different bank pairs in the buffer AND in the
+                                   //              residual (edge colouring, build_pair_block): no conflict wavefronts
     const uint2 *tsrc;             // [H/2+1]      transposed sources of pair k: c[k], c[N-k], c[H-k], c[H+k] (rows of the block)
                                    //              fused_inv: [2][256] uint4 -- pairs 0,1 then pairs 2,3 of thread t, k order of PairTables::pre --, then the entry of k = 0
     const uint2 *tgat;             // [Mc] float2-view slot of X[o1[j]] after the inverse FFT, column order (thread t of
@@ -327,10 +331,10 @@ __device__ __forceinline__ float2 q_from_half_pt(float2 hp)
 #define LSB_PAIR_PREPF 5
 #endif
 #ifndef LSB_PAIR_GATPF
-#define LSB_PAIR_GATPF 4
+#define LSB_PAIR_GATPF 2
 #endif
 constexpr int kPrePF = LSB_PAIR_PREPF;      // pairs per thread whose tables are prefetched (H/2 + 1 = 1025 pairs at H = 2048)
-constexpr int kGatPF = LSB_PAIR_GATPF;      // gather-id chunks (4 ids each) prefetched
+constexpr int kGatPF = LSB_PAIR_GATPF;      // (row, slot) chunks of the row gather (4 slots each) prefetched
 
 // ------------------------------------------------------------------ forward
 template <int LOGH> struct FwdIn {                       // what the gathering first pass needs
@@ -459,13 +463,13 @@ __device__ __forceinline__ void forward_last_fused(float4 *buf, const float2 *hp
     for (int m = 0; m < 4; ++m) st(buf, pswz<LOGH>(4 * q2 + m), u[m]);
 }
 
-struct GatPre { uint2 c[kGatPF]; };
-__device__ __forceinline__ GatPre gather_issue(const uint2 *__restrict__ tab, int count, int tid)
+struct GatPre { uint4 c[kGatPF]; };
+__device__ __forceinline__ GatPre gather_issue(const uint4 *__restrict__ tab, int chunks, int tid)
 {
     GatPre g;
-    const int nc = chunk_count(count);
 #pragma unroll
-    for (int c = 0; c < kGatPF; ++c) g.c[c] = c < nc ? ldg_na(tab + c * kPairThreads + tid) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (int c = 0; c < kGatPF; ++c)
+        g.c[c] = c < chunks ? ldg_na(tab + c * kPairThreads + tid) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     return g;
 }
 
@@ -475,7 +479,7 @@ __device__ __forceinline__ GatPre gather_issue(const uint2 *__restrict__ tab, in
 // gather ids of the block's rows (issued under the post-processing).
 template <int LOGH, typename Src>
 __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb, const PairBlock &b, const Src x,
-                                              const FwdIn<LOGH> &in, int n_rows, int tid)
+                                              const FwdIn<LOGH> &in, int tid)
 {
     constexpr int H = 1 << LOGH, Hh = H >> 1;
     typedef PassInfo<LOGH, 0> P0;
@@ -521,12 +525,12 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
         __syncwarp();
         const PostPre pp = post_issue<LOGH>(tb, tid);
 #if LSB_PAIR_GAT_EARLY
-        const GatPre g = gather_issue(b.fgat, n_rows, tid);
+        const GatPre g = gather_issue(b.fgat, b.gat_chunks, tid);
 #endif
         pass_run<LOGH, 2, false>(buf, t2, tid);
         __syncthreads();
 #if !LSB_PAIR_GAT_EARLY
-        const GatPre g = gather_issue(b.fgat, n_rows, tid);
+        const GatPre g = gather_issue(b.fgat, b.gat_chunks, tid);
 #endif
         forward_last_fused<LOGH>(buf, pp.hp, tid);
         __syncthreads();
@@ -538,7 +542,7 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
     const PostPre pp = post_issue<LOGH>(tb, tid);
     pass_run<LOGH, 3, false>(buf, TwPre<PassInfo<LOGH, 3>::NQ>(), tid);
     __syncthreads();
-    const GatPre g = gather_issue(b.fgat, n_rows, tid);
+    const GatPre g = gather_issue(b.fgat, b.gat_chunks, tid);
     // real-FFT split + DCT phase, pairs visited in bit-reversed order (consecutive lanes, consecutive slots)
 #pragma unroll
     for (int i = 0; i < kPrePF; ++i) {
@@ -556,31 +560,45 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
     return g;
 }
 
-// dst2[i] += sc * Y[id(i)] for the rows of one block (Y: float2 view of the pair buffer); row tid + 256 u
-// is handled by thread tid, so successive blocks update a row from the same thread (no barrier needed).
-__device__ __forceinline__ void gather_add(float2 *dst2, const float4 *buf, const GatPre &g, const uint2 *__restrict__ tab,
-                                           float sc, int count, int tid)
+// dst2[i] += sc * Y[id(i)] for the rows of one block (Y: float2 view of the pair buffer) in the scheduled order of
+// PairBlock::fgat.  A row changes hands from block to block: the caller's barrier between two blocks orders the updates.
+__device__ __forceinline__ void gather_slot(float2 *dst2, const float2 *bf2, unsigned e, float sc)
+{
+    if (e != 0xFFFFFFFFu) {
+        const unsigned i = e & 0xFFFFu;
+        dst2[i] = pfmas(bf2[e >> 16], sc, dst2[i]);
+    }
+}
+__device__ __forceinline__ void gather_add(float2 *dst2, const float4 *buf, const GatPre &g, const uint4 *__restrict__ tab,
+                                           float sc, int chunks, int tid)
 {
     const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
-    const int nc = chunk_count(count);
+    constexpr int kRest = 3;                             // chunks after the prefetched ones that are loaded up front
+    uint4 rest[kRest];
+#pragma unroll
+    for (int c = 0; c < kRest; ++c)
+        rest[c] = kGatPF + c < chunks ? ldg_na(tab + (kGatPF + c) * kPairThreads + tid) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
 #pragma unroll
     for (int c = 0; c < kGatPF; ++c) {
-        if (c >= nc) break;
-        const unsigned id[4] = {g.c[c].x & 0xFFFFu, g.c[c].x >> 16, g.c[c].y & 0xFFFFu, g.c[c].y >> 16};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = tid + (4 * c + u) * kPairThreads;
-            if (i < count) dst2[i] = pfmas(bf2[id[u]], sc, dst2[i]);
-        }
+        gather_slot(dst2, bf2, g.c[c].x, sc);
+        gather_slot(dst2, bf2, g.c[c].y, sc);
+        gather_slot(dst2, bf2, g.c[c].z, sc);
+        gather_slot(dst2, bf2, g.c[c].w, sc);
     }
-    for (int c = kGatPF; c < nc; ++c) {
-        const uint2 e = ldg_na(tab + c * kPairThreads + tid);
-        const unsigned id[4] = {e.x & 0xFFFFu, e.x >> 16, e.y & 0xFFFFu, e.y >> 16};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = tid + (4 * c + u) * kPairThreads;
-            if (i < count) dst2[i] = pfmas(bf2[id[u]], sc, dst2[i]);
-        }
+    for (int c = 0; c < kRest; ++c) {
+        if (kGatPF + c >= chunks) break;
+        gather_slot(dst2, bf2, rest[c].x, sc);
+        gather_slot(dst2, bf2, rest[c].y, sc);
+        gather_slot(dst2, bf2, rest[c].z, sc);
+        gather_slot(dst2, bf2, rest[c].w, sc);
+    }
+    for (int c = kGatPF + kRest; c < chunks; ++c) {
+        const uint4 e = ldg_na(tab + c * kPairThreads + tid);
+        gather_slot(dst2, bf2, e.x, sc);
+        gather_slot(dst2, bf2, e.y, sc);
+        gather_slot(dst2, bf2, e.z, sc);
+        gather_slot(dst2, bf2, e.w, sc);
     }
 }
 
