@@ -562,43 +562,43 @@ __device__ __forceinline__ GatPre forward_run(float4 *buf, const PairTables &tb,
 
 // dst2[i] += sc * Y[id(i)] for the rows of one block (Y: float2 view of the pair buffer) in the scheduled order of
 // PairBlock::fgat.  A row changes hands from block to block: the caller's barrier between two blocks orders the updates.
-__device__ __forceinline__ void gather_slot(float2 *dst2, const float2 *bf2, unsigned e, float sc)
+// NS slots at a time: all loads first, then the updates (a thread's rows are distinct; written this way the 2 NS
+// shared-memory loads are in flight together -- through one slot at a time the compiler has to keep each load of the
+// residual behind the previous store, whose address it cannot tell apart, and the gather runs at load latency).
+template <int NS>
+__device__ __forceinline__ void gather_slots(float2 *dst2, const float2 *bf2, const unsigned *e, float sc)
 {
-    if (e != 0xFFFFFFFFu) {
-        const unsigned i = e & 0xFFFFu;
-        dst2[i] = pfmas(bf2[e >> 16], sc, dst2[i]);
+    float2 yv[NS], zv[NS];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+        const bool on = e[u] != 0xFFFFFFFFu;
+        yv[u] = on ? bf2[e[u] >> 16] : make_float2(0.f, 0.f);
+        zv[u] = on ? dst2[e[u] & 0xFFFFu] : make_float2(0.f, 0.f);
     }
+#pragma unroll
+    for (int u = 0; u < NS; ++u)
+        if (e[u] != 0xFFFFFFFFu) dst2[e[u] & 0xFFFFu] = pfmas(yv[u], sc, zv[u]);
 }
 __device__ __forceinline__ void gather_add(float2 *dst2, const float4 *buf, const GatPre &g, const uint4 *__restrict__ tab,
                                            float sc, int chunks, int tid)
 {
+    static_assert(kGatPF == 2, "two prefetched chunks form the first group of eight slots");
     const float2 *bf2 = reinterpret_cast<const float2 *>(buf);
-    constexpr int kRest = 3;                             // chunks after the prefetched ones that are loaded up front
-    uint4 rest[kRest];
-#pragma unroll
-    for (int c = 0; c < kRest; ++c)
-        rest[c] = kGatPF + c < chunks ? ldg_na(tab + (kGatPF + c) * kPairThreads + tid) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-#pragma unroll
-    for (int c = 0; c < kGatPF; ++c) {
-        gather_slot(dst2, bf2, g.c[c].x, sc);
-        gather_slot(dst2, bf2, g.c[c].y, sc);
-        gather_slot(dst2, bf2, g.c[c].z, sc);
-        gather_slot(dst2, bf2, g.c[c].w, sc);
+    const uint4 none = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    const uint4 r0 = 2 < chunks ? ldg_na(tab + 2 * kPairThreads + tid) : none;     // second group: loaded under the first
+    const uint4 r1 = 3 < chunks ? ldg_na(tab + 3 * kPairThreads + tid) : none;
+    {
+        const unsigned e[8] = {g.c[0].x, g.c[0].y, g.c[0].z, g.c[0].w, g.c[1].x, g.c[1].y, g.c[1].z, g.c[1].w};
+        gather_slots<8>(dst2, bf2, e, sc);
     }
-#pragma unroll
-    for (int c = 0; c < kRest; ++c) {
-        if (kGatPF + c >= chunks) break;
-        gather_slot(dst2, bf2, rest[c].x, sc);
-        gather_slot(dst2, bf2, rest[c].y, sc);
-        gather_slot(dst2, bf2, rest[c].z, sc);
-        gather_slot(dst2, bf2, rest[c].w, sc);
+    if (2 < chunks) {
+        const unsigned e[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        gather_slots<8>(dst2, bf2, e, sc);
     }
-    for (int c = kGatPF + kRest; c < chunks; ++c) {
-        const uint4 e = ldg_na(tab + c * kPairThreads + tid);
-        gather_slot(dst2, bf2, e.x, sc);
-        gather_slot(dst2, bf2, e.y, sc);
-        gather_slot(dst2, bf2, e.z, sc);
-        gather_slot(dst2, bf2, e.w, sc);
+    for (int c = 4; c < chunks; ++c) {
+        const uint4 q = ldg_na(tab + c * kPairThreads + tid);
+        const unsigned e[4] = {q.x, q.y, q.z, q.w};
+        gather_slots<4>(dst2, bf2, e, sc);
     }
 }
 
