@@ -394,10 +394,36 @@ def main():
         # headline e2e: the step's result is the decoded bits (what ldpc_awgn.py keeps: app < 0) + iteration
         # counts; the APP-LLR variant above returns the reference's raw decode() output and is host-bandwidth
         # bound once 8 ranks each write 510 MB per step into host memory
-        out["e2e"] = {"value": world * F * K * n_e2e / float(th.item()), "unit": "info bits/s",
+        out["e2e_u8_decisions"] = {"value": world * F * K * n_e2e / float(th.item()), "unit": "info bits/s",
                       "h2d_bytes_per_step": F * N * 4, "d2h_bytes_per_step": F * N + F * 4,
                       "ms_per_step": 1e3 * float(th.item()) / n_e2e,
                       "api": "lsb_ldpc_decode_host_f32 (C-ABI, pinned host LLR in, uint8 decisions + iteration counts out)"}
+
+        # the same result as packed bits (32 decisions per word): 1/8 of the decision bytes back to the host
+        pitch = (N + 31) // 32
+        h_bits = torch.empty((F, pitch), dtype=torch.int32).pin_memory()
+
+        def e2e_bits_step():
+            _lib.check(L.lsb_ldpc_decode_host_bits_f32(g, h_llr.data_ptr(), h_bits.data_ptr(), h_it.data_ptr(), F,
+                                                       args.max_it, 0, 1.0), "decode_host_bits")
+
+        e2e_bits_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_bits_step()
+        tb = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        shifts = torch.arange(32, device=dev, dtype=torch.int32)
+        unpacked = ((h_bits.to(dev)[:, :, None] >> shifts) & 1).reshape(F, -1)[:, :N]
+        assert torch.equal(unpacked != 0, app < 0), "bit-packed host-path decisions differ from the device path"
+        assert torch.equal(h_it.to(dev), iters), "host-path iteration counts differ from the device path"
+        del unpacked
+        out["e2e"] = {"value": world * F * K * n_e2e / float(tb.item()), "unit": "info bits/s",
+                      "h2d_bytes_per_step": F * N * 4, "d2h_bytes_per_step": F * pitch * 4 + F * 4,
+                      "ms_per_step": 1e3 * float(tb.item()) / n_e2e,
+                      "api": "lsb_ldpc_decode_host_bits_f32 (C-ABI, pinned host LLR in, bit-packed decisions + iteration counts out)"}
 
     out["clocks"] = clocks.summary()
     # Secondary rooflines (what the kernel is really bound by; messages never leave shared memory).

@@ -146,6 +146,14 @@ int lsb_ldpc_decode_host_f32(const lsb_ldpc_graph *g, const float *llr,
                              float *app, uint8_t *hard, int32_t *iters,
                              int64_t n_frames, int max_it, int algo,
                              double scale);
+/* The same with bit-packed hard decisions as the only output besides the
+ * iteration counts: bits[f * ceil(N / 32) + v / 32] >> (v % 32) & 1 = (app[f, v] < 0),
+ * what the reference's Monte-Carlo loop keeps of a decode (ldpc_awgn.py:97);
+ * 1/8 of the device->host bytes of `hard`, 1/32 of `app`. */
+int lsb_ldpc_decode_host_bits_f32(const lsb_ldpc_graph *g, const float *llr,
+                                  uint32_t *bits, int32_t *iters,
+                                  int64_t n_frames, int max_it, int algo,
+                                  double scale);
 int lsb_ldpc_decode_host_f64(const lsb_ldpc_graph *g, const double *llr,
                              double *app, uint8_t *hard, int32_t *iters,
                              int64_t n_frames, int max_it, int algo,

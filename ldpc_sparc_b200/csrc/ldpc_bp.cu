@@ -104,6 +104,7 @@ struct lsb_ldpc_graph {
         cudaStream_t stream = nullptr;
         void *d_in = nullptr, *d_app = nullptr, *d_in32 = nullptr, *d_app32 = nullptr;
         uint8_t *d_hard = nullptr;
+        uint32_t *d_bits = nullptr;
         int32_t *d_iters = nullptr;
         size_t frames = 0;
         int elem = 0;
@@ -146,6 +147,13 @@ size_t qc_smem_bytes(const lsb_ldpc_graph *g, size_t elem)
     return ((size_t)g->qc_edges * g->z + 2 * (size_t)g->nv) * elem;
 }
 
+// the graph runs on the shared-memory QC kernel (else: generic kernel)
+bool qc_path(const lsb_ldpc_graph *g, size_t elem)
+{
+    return g->is_qc && g->max_dc <= kMaxDcQc &&
+           qc_smem_bytes(g, elem) + sizeof(QcTables) + 64 <= (size_t)lsb::max_smem_optin();
+}
+
 template <typename T>
 int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, int32_t *iters,
                int64_t n_frames, int max_it, int algo, double scale, cudaStream_t st, const McParams *mc = nullptr)
@@ -166,10 +174,7 @@ int decode_dev(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, in
     else LSB_CUDA(cudaEventCreateWithFlags(&g->queue_ev[slot], cudaEventDisableTiming));
     LSB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st));
 
-    const bool qc_ok = g->is_qc && g->max_dc <= kMaxDcQc &&
-                       qc_smem_bytes(g, sizeof(T)) + sizeof(QcTables) + 64 <=
-                           (size_t)lsb::max_smem_optin();
-    if (qc_ok) {
+    if (qc_path(g, sizeof(T))) {
         QcLaunch<T> a;
         a.tabs = g->d_tabs;
         a.llr = llr;
@@ -243,9 +248,11 @@ void free_stage(lsb_ldpc_graph::Stage &s)
     cudaFree(s.d_in32);
     cudaFree(s.d_app32);
     cudaFree(s.d_hard);
+    cudaFree(s.d_bits);
     cudaFree(s.d_iters);
     s.d_in = s.d_app = s.d_in32 = s.d_app32 = nullptr;
     s.d_hard = nullptr;
+    s.d_bits = nullptr;
     s.d_iters = nullptr;
     s.frames = 0;
 }
@@ -265,17 +272,35 @@ int ensure_stage(lsb_ldpc_graph *g, lsb_ldpc_graph::Stage &s, size_t frames, int
         LSB_CUDA(cudaMalloc(&s.d_app32, n * sizeof(float)));
     }
     LSB_CUDA(cudaMalloc((void **)&s.d_hard, n));
+    LSB_CUDA(cudaMalloc((void **)&s.d_bits, frames * (size_t)((g->nv + 31) / 32) * sizeof(uint32_t)));
     LSB_CUDA(cudaMalloc((void **)&s.d_iters, frames * sizeof(int32_t)));
     s.frames = frames;
     s.elem = elem;
     return LSB_OK;
 }
 
+// hard decisions [frames][nv] bytes -> [frames][ceil(nv / 32)] words, bit v of a frame = word v / 32, bit v % 32.
+// Only behind the generic kernel; the QC kernel packs in its epilogue (McParams::hard_bits) -- a second kernel on the
+// chunk's stream queues behind the persistent decode grids of the other two chunks (measured: e2e 2.79 instead of
+// 3.19 Gbit/s).
+__global__ void pack_bits_kernel(const uint8_t *__restrict__ hard, uint32_t *__restrict__ bits, long long n_frames, int nv)
+{
+    const int pitch = (nv + 31) / 32, lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_frames * pitch; w += warps) {
+        const long long f = w / pitch;
+        const int v = (int)(w - f * pitch) * 32 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, v < nv && hard[f * nv + v] != 0);
+        if (lane == 0) bits[w] = m;
+    }
+}
+
 // Host-pointer decode: chunks of frames rotate over three streams so the H2D
 // copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap.
 template <typename T>
 int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, int32_t *iters,
-                int64_t n_frames, int max_it, int algo, double scale, bool compute_f32_from_f64)
+                int64_t n_frames, int max_it, int algo, double scale, bool compute_f32_from_f64,
+                uint32_t *bits = nullptr)
 {
     lsb_ldpc_graph *g = const_cast<lsb_ldpc_graph *>(cg);
     if (n_frames == 0) return LSB_OK;                  // an empty batch is valid with any pointers
@@ -298,6 +323,10 @@ int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, i
         const size_t nf = (size_t)((n_frames - f0 < (int64_t)chunk) ? n_frames - f0 : chunk);
         if ((rc = ensure_stage(g, s, chunk, sizeof(T), compute_f32_from_f64))) return rc;
         const size_t n = nf * nv;
+        const bool bits_in_kernel = bits && algo == LSB_BP_SUMPROD2 && (compute_f32_from_f64 || sizeof(T) == 4) &&
+                                    qc_path(g, sizeof(float));
+        McParams mcb;
+        mcb.hard_bits = s.d_bits;
         LSB_CUDA(cudaMemcpyAsync(s.d_in, llr + (size_t)f0 * nv, n * sizeof(T),
                                  cudaMemcpyHostToDevice, s.stream));
         if (compute_f32_from_f64) {
@@ -306,8 +335,8 @@ int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, i
                                                                    (float *)s.d_in32, (long long)n);
             lsb::count_launch();
             rc = decode_dev<float>(g, (const float *)s.d_in32, app ? (float *)s.d_app32 : nullptr,
-                                   hard ? s.d_hard : nullptr, s.d_iters, (int64_t)nf, max_it, algo,
-                                   scale, s.stream);
+                                   (hard || (bits && !bits_in_kernel)) ? s.d_hard : nullptr, s.d_iters, (int64_t)nf,
+                                   max_it, algo, scale, s.stream, bits_in_kernel ? &mcb : nullptr);
             if (!rc && app) {
                 convert_kernel<float, T><<<blocks, 256, 0, s.stream>>>((const float *)s.d_app32,
                                                                        (T *)s.d_app, (long long)n);
@@ -315,8 +344,8 @@ int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, i
             }
         } else {
             rc = decode_dev<T>(g, (const T *)s.d_in, app ? (T *)s.d_app : nullptr,
-                               hard ? s.d_hard : nullptr, s.d_iters, (int64_t)nf, max_it, algo,
-                               scale, s.stream);
+                               (hard || (bits && !bits_in_kernel)) ? s.d_hard : nullptr, s.d_iters, (int64_t)nf, max_it,
+                               algo, scale, s.stream, bits_in_kernel ? &mcb : nullptr);
         }
         if (rc) return rc;
         if (app)
@@ -325,6 +354,16 @@ int decode_host(const lsb_ldpc_graph *cg, const T *llr, T *app, uint8_t *hard, i
         if (hard)
             LSB_CUDA(cudaMemcpyAsync(hard + (size_t)f0 * nv, s.d_hard, n, cudaMemcpyDeviceToHost,
                                      s.stream));
+        if (bits) {
+            const size_t pitch = (nv + 31) / 32;
+            if (!bits_in_kernel) {
+                pack_bits_kernel<<<lsb::sm_count() * 8, 256, 0, s.stream>>>(s.d_hard, s.d_bits, (long long)nf, (int)nv);
+                lsb::count_launch();
+                LSB_CUDA(cudaGetLastError());
+            }
+            LSB_CUDA(cudaMemcpyAsync(bits + (size_t)f0 * pitch, s.d_bits, nf * pitch * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, s.stream));
+        }
         LSB_CUDA(cudaMemcpyAsync(iters + f0, s.d_iters, nf * sizeof(int32_t),
                                  cudaMemcpyDeviceToHost, s.stream));
     }
@@ -604,6 +643,13 @@ int lsb_ldpc_decode_dev_f64(const lsb_ldpc_graph *g, const double *llr, double *
 {
     return decode_dev<double>(g, llr, app, hard, iters, n_frames, max_it, algo, scale,
                               (cudaStream_t)stream);
+}
+
+int lsb_ldpc_decode_host_bits_f32(const lsb_ldpc_graph *g, const float *llr, uint32_t *bits, int32_t *iters,
+                                  int64_t n_frames, int max_it, int algo, double scale)
+{
+    LSB_REQUIRE(bits || n_frames == 0, "null bits pointer");
+    return decode_host<float>(g, llr, nullptr, nullptr, iters, n_frames, max_it, algo, scale, false, bits);
 }
 
 int lsb_ldpc_decode_host_f32(const lsb_ldpc_graph *g, const float *llr, float *app, uint8_t *hard,

@@ -34,6 +34,8 @@ struct McParams {
     int32_t *bit_errors = nullptr;     // [F] wrong bits of the frame (optional)
     float *llr_out = nullptr;          // [F, N] the channel LLRs that were generated (optional; tests)
     unsigned long long *counters = nullptr;   // [4] += bit errors, frame errors, frames, iterations (optional)
+    // independent of cw: hard decisions as packed bits, [F][ceil(N / 32)] words, bit v % 32 of word v / 32 (optional)
+    uint32_t *hard_bits = nullptr;
 };
 
 template <typename T>

@@ -454,7 +454,9 @@ struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
     static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? LSB_BP_OCC8 : (MAXDC <= 16 ? 4 : 3));
 };
 
-template <typename T, int ALGO, int MAXDC>
+// BITS: the epilogue also writes the hard decisions as packed bits (McParams::hard_bits).  A template parameter --
+// as a run-time branch the extra epilogue changed the register allocation of the main loop (19.25 -> 19.43 ms).
+template <typename T, int ALGO, int MAXDC, bool BITS = false>
 __global__ void __launch_bounds__(kThreads, QcOccupancy<MAXDC, sizeof(T)>::value)
 bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *__restrict__ app,
              uint8_t *__restrict__ hard, int32_t *__restrict__ iters, long long n_frames,
@@ -588,6 +590,14 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
             uint8_t *o = hard + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
         }
+        if (BITS) {                               // one warp ballot per 32 decisions (uniform trip count)
+            uint32_t *o = mc.hard_bits + f * ((nv + 31) >> 5);
+            for (int v0 = 0; v0 < nv; v0 += kThreads) {
+                const int v = v0 + tid;
+                const unsigned m = __ballot_sync(0xffffffffu, v < nv && ap[v] < (T)0);
+                if ((tid & 31) == 0 && v < nv) o[v >> 5] = m;
+            }
+        }
         if (mc.cw) {
             // wrong hard decisions over all N code bits (ldpc_awgn.py:97-103), summed in a fixed order
             int wrong = 0;
@@ -680,7 +690,12 @@ bp_generic_kernel(const int *__restrict__ voff, const int *__restrict__ coff,
 template <typename T, int ALGO, int MAXDC>
 int launch_qc_bucket(const QcLaunch<T> &a)
 {
-    auto kern = bp_qc_kernel<T, ALGO, MAXDC>;
+    constexpr bool kBitsVariant = sizeof(T) == 4 && ALGO == LSB_BP_SUMPROD2;     // the throughput mode only
+    if (a.mc.hard_bits && !kBitsVariant) {
+        lsb::set_error("packed decisions are built for the fp32 sumprod2 kernel only");
+        return LSB_ERR_INVALID;
+    }
+    auto kern = (kBitsVariant && a.mc.hard_bits) ? bp_qc_kernel<T, ALGO, MAXDC, kBitsVariant> : bp_qc_kernel<T, ALGO, MAXDC, false>;
     const size_t smem = a.smem;
     LSB_CUDA(lsb::ensure_dynamic_smem(kern, smem));       // per (kernel, device), raise-only: other codes share kern
     if (*a.cached_grid == 0) {

@@ -253,6 +253,42 @@ def test_generic_graph_equals_qc_kernel():
     assert np.array_equal(hard.astype(bool), app < 0)
 
 
+def test_host_decode_with_bit_packed_decisions():
+    """lsb_ldpc_decode_host_bits_f32: bit v of frame f = (app[f, v] < 0), words of 32 decisions, LSB first;
+    N = 1944 is not a multiple of 32 (61 words, 24 decisions in the last); several pipeline chunks."""
+    import ctypes as ct
+    L = _lib.lib()
+    c = ldpc.code("802.11n", "1/2", 81)
+    rng = np.random.RandomState(11)
+    x, llr = awgn_llr(c, rng, 1.5, 5000)
+    llr = np.ascontiguousarray(llr, dtype=np.float32)
+    app, it = c.decode(llr, 30, precision="fp32")
+    pitch = (c.N + 31) // 32
+    bits = np.full((len(llr), pitch), 0xFFFFFFFF, dtype=np.uint32)
+    it_b = np.zeros(len(llr), dtype=np.int32)
+    with __import__("torch").cuda.device(0):
+        g = c._handle()
+        _lib.check(L.lsb_ldpc_decode_host_bits_f32(g, llr.ctypes.data, bits.ctypes.data, it_b.ctypes.data, len(llr),
+                                                   30, 0, 1.0), "decode_host_bits")
+    unpacked = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(len(llr), -1)
+    assert np.array_equal(unpacked[:, :c.N].astype(bool), np.asarray(app) < 0)
+    assert not unpacked[:, c.N:].any()                      # padding bits are zero
+    assert np.array_equal(it_b, np.asarray(it))
+    _lib.check(L.lsb_ldpc_decode_host_bits_f32(g, llr.ctypes.data, None, it_b.ctypes.data, 0, 30, 0, 1.0), "empty batch")
+    # the same graph through the generic kernel (handle built from vdeg / cdeg / intrlv): packed by a second kernel
+    h = ct.c_void_p()
+    vd, cd, il = (np.ascontiguousarray(a, dtype=np.int64) for a in (c.vdeg, c.cdeg, c.intrlv))
+    _lib.check(L.lsb_ldpc_graph_create(vd.ctypes.data_as(_lib.c_i64p), cd.ctypes.data_as(_lib.c_i64p),
+                                       il.ctypes.data_as(_lib.c_i64p), c.Nv, c.Nc, c.Nmsg, ct.byref(h)), "create")
+    bits_g = np.zeros((64, pitch), dtype=np.uint32)
+    it_g = np.zeros(64, dtype=np.int32)
+    _lib.check(L.lsb_ldpc_decode_host_bits_f32(h, llr.ctypes.data, bits_g.ctypes.data, it_g.ctypes.data, 64, 30, 0, 1.0),
+               "decode_host_bits (generic)")
+    L.lsb_ldpc_graph_destroy(h)
+    conv = np.asarray(it)[:64] < 30                         # fp32 orders of operation differ between the two kernels
+    assert np.array_equal(bits_g[conv], bits[:64][conv]) and np.array_equal(it_g[conv], it_b[:64][conv])
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases():
     c = ldpc.code("802.11n", "1/2", 27)
