@@ -238,6 +238,29 @@ class code:
             return app[0], int(iters[0])
         return app, iters
 
+    def decode_bits(self, ch, max_itcount=200, corr_factor=0.7):
+        """Host-array Monte-Carlo entry (``lsb_ldpc_decode_host_bits_f32``): numpy float32 LLRs ``[F, N]`` in,
+        ``(bits uint32 [F, ceil(N / 32)], it int32 [F])`` out, sum-product (`sumprod2`) in fp32.  Bit ``v % 32`` of
+        word ``v // 32`` of a frame is ``app[v] < 0`` -- what the reference's loop keeps of a decode
+        (ldpc_awgn.py:97) -- so 1/32 of the APP bytes come back to the host; `unpack_bits` undoes the packing."""
+        ch = np.asarray(ch)
+        if ch.ndim != 2 or ch.shape[1] != len(self.vdeg):
+            raise NameError("Channel inputs not consistent with variable degrees")
+        llr = np.ascontiguousarray(ch, dtype=np.float32)
+        F = llr.shape[0]
+        bits = np.zeros((F, (self.Nv + 31) // 32), dtype=np.uint32)
+        iters = np.zeros(F, dtype=np.int32)
+        rc = _lib.lib().lsb_ldpc_decode_host_bits_f32(self._handle(), llr.ctypes.data, bits.ctypes.data, iters.ctypes.data,
+                                                      F, int(max_itcount), _lib.ALGO["sumprod2"], float(corr_factor))
+        _lib.check(rc, "lsb_ldpc_decode_host_bits")
+        return bits, iters
+
+    def unpack_bits(self, bits):
+        """``[F, ceil(N / 32)]`` words of `decode_bits` -> uint8 ``[F, N]`` hard decisions."""
+        bits = np.asarray(bits, dtype=np.uint32)
+        out = (bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)
+        return out.reshape(bits.shape[0], -1)[:, :self.Nv].astype(np.uint8)
+
     def _decode_tensor(self, ch, max_itcount, algo, corr_factor, precision):
         import torch
         if not ch.is_cuda:

@@ -47,3 +47,17 @@ def test_batched_encode_is_linear():
     u, v = rng.randint(0, 2, (2, 8, c.K))
     assert np.array_equal((c.encode(u) + c.encode(v)) % 2, c.encode((u + v) % 2))
     assert np.array_equal(c.encode(u)[:, :c.K], u)   # systematic
+
+
+def test_unpack_bits_layout():
+    """Bit v % 32 of word v // 32, padding ignored (host helper of decode_bits; no GPU)."""
+    from ldpc_sparc_b200 import ldpc
+    c = ldpc.code("802.11n", "1/2", 27)                      # N = 648 = 20 words + 8 bits
+    rng = np.random.RandomState(0)
+    hard = rng.randint(0, 2, size=(5, c.N)).astype(np.uint8)
+    pitch = (c.N + 31) // 32
+    words = np.zeros((5, pitch), dtype=np.uint32)
+    for v in range(c.N):
+        words[:, v // 32] |= hard[:, v].astype(np.uint32) << np.uint32(v % 32)
+    words[:, -1] |= np.uint32(0xFF000000)                    # garbage in the padding bits is dropped
+    assert np.array_equal(c.unpack_bits(words), hard)

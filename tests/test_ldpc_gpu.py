@@ -275,6 +275,9 @@ def test_host_decode_with_bit_packed_decisions():
     assert not unpacked[:, c.N:].any()                      # padding bits are zero
     assert np.array_equal(it_b, np.asarray(it))
     _lib.check(L.lsb_ldpc_decode_host_bits_f32(g, llr.ctypes.data, None, it_b.ctypes.data, 0, 30, 0, 1.0), "empty batch")
+    bits_f, it_f = c.decode_bits(llr, 30, 1.0)              # the facade of the same call
+    assert np.array_equal(bits_f, bits) and np.array_equal(it_f, it_b)
+    assert np.array_equal(c.unpack_bits(bits_f).astype(bool), np.asarray(app) < 0)
     # the same graph through the generic kernel (handle built from vdeg / cdeg / intrlv): packed by a second kernel
     h = ct.c_void_p()
     vd, cd, il = (np.ascontiguousarray(a, dtype=np.int64) for a in (c.vdeg, c.cdeg, c.intrlv))
