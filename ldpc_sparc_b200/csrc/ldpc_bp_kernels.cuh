@@ -454,6 +454,18 @@ struct QcOccupancy {   // resident CTAs per SM the register budget is tuned for
     static constexpr int value = ELEM == 8 ? 2 : (MAXDC <= 8 ? LSB_BP_OCC8 : (MAXDC <= 16 ? 4 : 3));
 };
 
+// hard decisions of one frame as packed bits: one warp ballot per 32 decisions (uniform trip count).  Not inlined: the
+// epilogue of the BITS variant then leaves the register allocation of the decode loop as it is without it.
+template <typename T>
+__device__ __noinline__ void pack_decisions(const T *ap, uint32_t *o, int nv, int tid)
+{
+    for (int v0 = 0; v0 < nv; v0 += kThreads) {
+        const int v = v0 + tid;
+        const unsigned m = __ballot_sync(0xffffffffu, v < nv && ap[v] < (T)0);
+        if ((tid & 31) == 0 && v < nv) o[v >> 5] = m;
+    }
+}
+
 // BITS: the epilogue also writes the hard decisions as packed bits (McParams::hard_bits).  A template parameter --
 // as a run-time branch the extra epilogue changed the register allocation of the main loop (19.25 -> 19.43 ms).
 template <typename T, int ALGO, int MAXDC, bool BITS = false>
@@ -590,14 +602,7 @@ bp_qc_kernel(const QcTables *__restrict__ g_tabs, const T *__restrict__ llr, T *
             uint8_t *o = hard + f * nv;
             for (int v = tid; v < nv; v += kThreads) o[v] = ap[v] < (T)0;
         }
-        if (BITS) {                               // one warp ballot per 32 decisions (uniform trip count)
-            uint32_t *o = mc.hard_bits + f * ((nv + 31) >> 5);
-            for (int v0 = 0; v0 < nv; v0 += kThreads) {
-                const int v = v0 + tid;
-                const unsigned m = __ballot_sync(0xffffffffu, v < nv && ap[v] < (T)0);
-                if ((tid & 31) == 0 && v < nv) o[v >> 5] = m;
-            }
-        }
+        if (BITS) pack_decisions<T>(ap, mc.hard_bits + f * ((nv + 31) >> 5), nv, tid);
         if (mc.cw) {
             // wrong hard decisions over all N code bits (ldpc_awgn.py:97-103), summed in a fixed order
             int wrong = 0;
