@@ -719,7 +719,7 @@ bool pair_enabled()
 bool pair_fits(const lsb_sparc_design *g)
 {
     return g->has_pair && pair_enabled() &&
-           pair_amp_dyn_smem(g->dev.h, g->dev.n, g->dev.Lr, g->dev.Lc) + 4096 <= (size_t)lsb::max_smem_optin();
+           pair_amp_dyn_smem(g->dev.h, g->dev.n, g->dev.Lr, g->dev.Lc, false) + 4096 <= (size_t)lsb::max_smem_optin();
 }
 
 // Mirror pair s (0..3) of thread t in the fused first pass of the transposed transform (post = false) or the fused
@@ -1001,8 +1001,12 @@ int launch_amp_pair_h(lsb_sparc_design *g, const float *y, int64_t n_frames, con
 {
     static_assert(sizeof(PairBlock) % sizeof(uint2) == 0, "descriptor copied as 8-byte words");
     const bool cached = LSB_PAIR_CACHE && pair_design_cached(g->dev.Lr, g->dev.Lc, g->dev.n_blocks);
-    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc);
-    auto kernel = cached ? amp_pair_kernel<LOGH, true> : amp_pair_kernel<LOGH, false>;
+    // beta column staged in shared memory (2 CTAs per SM): transforms with staged tables, column block <= 8 KB
+    const bool bstage = LSB_PAIR_BSTAGE && cached && pairfft::stage_fwd<LOGH>() && g->dev.Mc <= kBetaStageBytes / 8 &&
+                        g->dev.Mc % 2 == 0 &&
+                        2 * (pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc, true) + 8192) <= (size_t)lsb::max_smem_optin() * 2;
+    const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc, bstage);
+    auto kernel = bstage ? amp_pair_kernel<LOGH, true, true> : cached ? amp_pair_kernel<LOGH, true, false> : amp_pair_kernel<LOGH, false, false>;
     LSB_CUDA(lsb::ensure_dynamic_smem(kernel, smem));
     if (g->amp_grid_pair == 0) {
         int per_sm = 0;

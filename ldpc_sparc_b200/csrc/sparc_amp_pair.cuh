@@ -33,6 +33,10 @@ struct SrcPair {                   // column block stored as float2 (A, B) per e
     const float2 *p;
     __device__ __forceinline__ P get(unsigned i) const { return __ldcg(p + i); }     // written by this CTA: L2, no L1 allocation
 };
+struct SrcStage {                  // column block staged in shared memory (BSTAGE variant of the AMP kernel)
+    const float2 *p;
+    __device__ __forceinline__ P get(unsigned i) const { return p[i]; }
+};
 struct SrcTwo {                    // the two frames' column blocks in two separate arrays
     const float *a, *b;
     __device__ __forceinline__ P get(unsigned i) const { return make_float2(__ldg(a + i), __ldg(b + i)); }
@@ -73,13 +77,17 @@ __host__ __device__ inline size_t pair_scalar_bytes(int Lr, int Lc)
 {
     return (size_t)(4 * 2 * Lc + 3 * 2 * Lr) * sizeof(double) + (size_t)(2 * Lc + 2 * Lr) * sizeof(float2);
 }
+constexpr int kBetaStageBytes = 8192;     // BSTAGE variant of the AMP kernel: one column block of beta (float2 per entry)
 // FFT buffer, table staging area (sparc_pair.cuh: LSB_PAIR_STAGE), residual
 __host__ __device__ inline size_t pair_vec_bytes(int h, int n)
 {
     return ((size_t)16 << h) + (h == 11 ? (size_t)16 * pairfft::stage_slots<11>() : 0) + (((size_t)n * sizeof(float2) + 15) & ~(size_t)15);
 }
 size_t pair_op_dyn_smem(int h, int n) { return pair_vec_bytes(h, n); }
-size_t pair_amp_dyn_smem(int h, int n, int Lr, int Lc) { return pair_vec_bytes(h, n) + pair_scalar_bytes(Lr, Lc); }
+size_t pair_amp_dyn_smem(int h, int n, int Lr, int Lc, bool bstage)
+{
+    return pair_vec_bytes(h, n) + (bstage ? ((pair_scalar_bytes(Lr, Lc) + 15) & ~(size_t)15) + kBetaStageBytes : pair_scalar_bytes(Lr, Lc));
+}
 
 // ------------------------------------------------------------------ operators
 // out[f, n] = A x[f, LM] for frame pairs (reference Ab, sparc.py:786-789,811-819,851-862)
@@ -204,8 +212,15 @@ __device__ __forceinline__ void st4_cg(float2 *p, const float2 *v)
 // Requirements checked by the host: fp32, unmodulated (K = 1), 4 <= M <= 32, every column block has at least
 // one non-zero base-matrix entry, no soft outputs (beta_soft / s_last), H = 2^LOGH.
 // scratch per CTA: [LM] float2 beta (A, B) then [Mc] float2 partial s of the current column.
-template <int LOGH, bool CACHED>
-__global__ void __launch_bounds__(kPairThreads, LSB_AMP_PAIR_OCC)
+// BSTAGE: the column block of beta that the NEXT forward transform gathers from travels L2 -> shared memory with
+// cp.async (issued next to that transform's index table, one row gather ahead) into 8 KB behind the scalar state, so the
+// first pass gathers from shared memory instead of waiting for 16 random L2 loads per thread.  Needs Mc <= 1024 and
+// runs 2 CTAs per SM (the third CTA's shared memory pays for the buffer; the 2-CTA build is as fast).
+#ifndef LSB_PAIR_BSTAGE
+#define LSB_PAIR_BSTAGE 1
+#endif
+template <int LOGH, bool CACHED, bool BSTAGE>
+__global__ void __launch_bounds__(kPairThreads, BSTAGE ? 2 : LSB_AMP_PAIR_OCC)
 amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ y_all,
                 const int32_t *__restrict__ idx0, AmpOut o, float2 *__restrict__ scratch, long long n_frames,
                 unsigned long long *__restrict__ queue)
@@ -216,6 +231,19 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
     float4 *buf = reinterpret_cast<float4 *>(smem);           // [H] (re_A, re_B, im_A, im_B)
     float2 *z2 = reinterpret_cast<float2 *>(buf + H + pairfft::stage_slots<LOGH>());         // [n] residual of frame A / frame B
     const PairScalars S{reinterpret_cast<double *>(smem + pair_vec_bytes(LOGH, d.n)), d.Lc, d.Lr};
+    float4 *bstage = reinterpret_cast<float4 *>(smem + pair_vec_bytes(LOGH, d.n) + ((pair_scalar_bytes(d.Lr, d.Lc) + 15) & ~(size_t)15));
+    // thread t copies 16-byte pieces t and 256 + t of column block c (Mc float2 = Mc / 2 pieces)
+    auto beta_issue = [&](int c) {
+        const float4 *src = reinterpret_cast<const float4 *>(scratch + (size_t)blockIdx.x * ((size_t)d.L * d.M + d.Mc) + (size_t)c * d.Mc);
+        const int pieces = d.Mc >> 1, t = threadIdx.x;
+        if (t < pieces)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(bstage + t)), "l"(src + t) : "memory");
+        if (t + kPairThreads < pieces)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(bstage + kPairThreads + t)),
+                         "l"(src + kPairThreads + t)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     __shared__ __align__(16) PairBlock c_blocks[CACHED ? kCacheBlocks : 1];
     __shared__ int c_col_first[CACHED ? kCacheCols + 1 : 1];
     __shared__ double c_W[CACHED ? kCacheW : 1];
@@ -295,18 +323,26 @@ amp_pair_kernel(DesignDev d, PairDev pd, AmpParams p, const float *__restrict__ 
                     for (int i = tid; i < d.n; i += kPairThreads)
                         z2[i] = pairfft::pfma(z2[i], S.coef_f()[i / d.Mr], make_float2(yA[i], yB[i]));
                 }
+                if (BSTAGE) {                        // (issued after the table of block 0; the update of z above ran under both)
+                    beta_issue(b.c);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();
+                }
                 for (int bi = 0; bi < d.n_blocks; ++bi) {
                     const pairfft::GatPre g =
-                        pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, fin, tid);
+                        BSTAGE ? pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcStage{reinterpret_cast<const float2 *>(bstage)}, fin, tid)
+                               : pairfft::forward_run<LOGH>(buf, pd.tb, b, SrcPair{beta2 + (size_t)b.c * d.Mc}, fin, tid);
                     PairBlock bn = b;
                     if (bi + 1 < d.n_blocks) {
                         bn = LSB_DV_BLOCKS[bi + 1];
                         fin = pairfft::forward_issue<LOGH>(pd.tb, bn, tid, buf);
+                        if (BSTAGE) beta_issue(bn.c);
                         // the column block after that: pull it into L2 (beta streams through DRAM between iterations)
                         if (bi + 2 < d.n_blocks && tid < col_lines)
                             pairfft::prefetch_l2(beta2 + (size_t)LSB_DV_BLOCKS[bi + 2].c * d.Mc + tid * 16);
                     }
                     pairfft::gather_add(z2 + b.r * d.Mr, buf, g, b.fgat, -b.scale, b.gat_chunks, tid);
+                    if (BSTAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");   // the next column block, before the barrier publishes it
                     __syncthreads();
                     b = bn;
                 }
