@@ -199,19 +199,19 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
         "clocks": clocks,
     }
     if precision == "fp32" and config == "c1":
-        # the pipe the FFT kernel keeps busiest: shared-memory wavefronts.  97.0 k wavefronts per frame-iteration
+        # the pipe the FFT kernel keeps busiest: shared-memory wavefronts.  100.2 k wavefronts per frame-iteration
         # (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of amp_pair_kernel<11> over 8192 frames x 23.86
-        # iterations, profiles/r2_amp_pair_v6_ncu_full.csv; 125.7 k before the fused passes) against one wavefront
+        # iterations, profiles/r2_amp_pair_v7_ncu_full.csv; 125.7 k before the fused passes) against one wavefront
         # per SM per clock
-        wf = 97.0e3 * frame_iters_rank / (ms * 1e-3)
+        wf = 100.2e3 * frame_iters_rank / (ms * 1e-3)
         sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
         peak_wf = float(torch.cuda.get_device_properties(ctx.dev).multi_processor_count) * float(sm_mhz) * 1e6
         out["roofline_smem"] = {"bound": "shared memory", "achieved": wf / 1e9, "peak": peak_wf / 1e9,
                                 "unit": "G wavefronts/s", "frac": wf / peak_wf,
-                                "wavefronts_per_frame_iteration": 97.0e3,
+                                "wavefronts_per_frame_iteration": 100.2e3,
                                 "note": "64 length-4096 transforms per frame-iteration through a 32 KB shared-memory buffer; "
                                         "15 % of the wavefronts are bank conflicts of the random gathers; the kernel is "
-                                        "latency-bound below this pipe's peak (3 CTAs per SM in barrier lockstep; DESIGN.md 4)"}
+                                        "latency-bound below this pipe's peak (2 CTAs per SM in barrier lockstep; DESIGN.md 4)"}
     if precision == "tc":
         # explicit block-banded design on the tensor cores (csrc/sparc_band_tc.cu): the bound is the tcgen05 pipe.
         # Algorithmic flops: 2 per stored design entry per product; a frame that runs T iterations does T products
