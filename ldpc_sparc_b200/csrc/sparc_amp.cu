@@ -1004,7 +1004,7 @@ int launch_amp_pair_h(lsb_sparc_design *g, const float *y, int64_t n_frames, con
     // beta column staged in shared memory (2 CTAs per SM): transforms with staged tables, column block <= 8 KB
     const bool bstage = LSB_PAIR_BSTAGE && cached && pairfft::stage_fwd<LOGH>() && g->dev.Mc <= kBetaStageBytes / 8 &&
                         g->dev.Mc % 2 == 0 &&
-                        2 * (pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc, true) + 8192) <= (size_t)lsb::max_smem_optin() * 2;
+                        pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc, true) + 4096 <= (size_t)lsb::max_smem_optin();
     const size_t smem = pair_amp_dyn_smem(LOGH, g->dev.n, g->dev.Lr, g->dev.Lc, bstage);
     auto kernel = bstage ? amp_pair_kernel<LOGH, true, true> : cached ? amp_pair_kernel<LOGH, true, false> : amp_pair_kernel<LOGH, false, false>;
     LSB_CUDA(lsb::ensure_dynamic_smem(kernel, smem));
