@@ -276,7 +276,9 @@ def main():
                 out[i] = buf[brev(N - K, LOGH)].imag
         return out
     yu, yf, yd = read_fwd(bu), read_fwd(bf), D @ x
+    res = {}
     su = (yu @ yd) / (yd @ yd)
+    res.update(fwd_scale=su, fwd_err_dense=np.abs(yu / su - yd).max(), fwd_err_fused=np.abs(bf - bu).max(), fwd_conflicts=extra)
     print("forward: unfused vs dense (scale %.6f) max err %.3e; fused vs unfused max err %.3e; fused-pass extra conflict wavefronts %d"
           % (su, np.abs(yu / su - yd).max(), np.abs(bf - bu).max(), extra))
     # transposed
@@ -294,11 +296,15 @@ def main():
         return out
     xu, xf, xd = read_tr(tu), read_tr(tf), D.T @ z
     st = (xu @ xd) / (xd @ xd)
+    res.update(tr_scale=st, tr_err_dense=np.abs(xu / st - xd).max(), tr_err_fused=np.abs(tf - tu).max(), tr_conflicts=extra_t)
     print("transposed: unfused vs dense (scale %.6f) max err %.3e; fused vs unfused max err %.3e; fused-pass extra conflict wavefronts %d"
           % (st, np.abs(xu / st - xd).max(), np.abs(tf - tu).max(), extra_t))
     for name, plan, swz in (("forward (8,8,8,4) pswz<11>", ((11, 3), (8, 3), (5, 3), (2, 2)), pswz_fwd),
                             ("transposed (4,8,8,8) i^((i>>3)&7)", ((11, 2), (9, 3), (6, 3), (3, 3)), pswz_inv)):
-        print(name, "extra conflict wavefronts per pass:", [pass_conflicts(s, r, swz) for s, r in plan])
+        pc = [int(pass_conflicts(s, r, swz)) for s, r in plan]
+        res.setdefault("pass_conflicts", []).append(pc)
+        print(name, "extra conflict wavefronts per pass:", pc)
+    return res
 
 
 if __name__ == "__main__":
