@@ -194,7 +194,7 @@ def amp_workload(ctx, config="c1", frames=16384, steps=5, warmup=2, precision="f
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "peak_source": src, "traffic": traffic_entry("amp_%s" % config),
                      "model": "%d B per frame-iteration (state-streaming model of SURVEY 8(d): beta r+w, z r+w, y r); "
-                              "the kernel is bound by shared-memory bandwidth of its FFT passes, not by HBM (DESIGN.md)"
+                              "the FFT kernels are latency-bound under their shared-memory pipe (roofline_smem), not HBM-bound (DESIGN.md 4)"
                               % bytes_per_frame_iter},
         "clocks": clocks,
     }
