@@ -264,6 +264,14 @@ int lsb_band_az_dev_f32(lsb_band_design *g, const float *y, float *out, int64_t 
 int lsb_band_amp_dev_f32(lsb_band_design *g, const float *y, int64_t n_frames,
                          const lsb_sparc_amp_params *p, const int32_t *idx0,
                          const lsb_sparc_amp_out *out, void *stream);
+/* Diagnostic (host only, no GPU call): the order in which the fp32 AMP kernel adds one design block's rows into the
+ * residual.  slot_ids[i] = shared-memory slot (8-byte units) row i reads, row0 = first residual row of the block.
+ * words[(chunk * 256 + thread) * 4 + s] = row | slot << 16 or 0xFFFFFFFF; within every half-warp (16 consecutive
+ * threads) of a slot position the rows' residual bank pairs ((row0 + row) % 16) and the slots' bank pairs (slot % 16)
+ * are all different, and every row appears once.  max_words >= 4096 * ceil(degree / 64) (16384 suffices for 4095 rows). */
+int lsb_sparc_schedule_row_gather(const uint16_t *slot_ids, int n_rows, int row0,
+                                  uint32_t *words, int64_t max_words, int *chunks);
+
 /* host-pointer form, as lsb_sparc_amp_host_f32 */
 int lsb_band_amp_host_f32(lsb_band_design *g, const float *y, int64_t n_frames,
                           const lsb_sparc_amp_params *p, int32_t *idx, int32_t *t_final, double *psi);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "lsb_band_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_band_az_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_band_amp_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_int64, ct.POINTER(AmpParams), ct.c_void_p, ct.POINTER(AmpOut), ct.c_void_p]),
+    "lsb_sparc_schedule_row_gather": (ct.c_int, [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p, ct.c_int64, ct.POINTER(ct.c_int)]),
     "lsb_sparc_design_info": (ct.c_int, [ct.c_void_p, c_i64p]),
     "lsb_sparc_ab_dev_f32": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),
     "lsb_sparc_ab_dev_f64": (ct.c_int, [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p]),

@@ -1104,6 +1104,19 @@ int run_amp(lsb_sparc_design *g, const T *y, int64_t n_frames, const lsb_sparc_a
 
 extern "C" {
 
+int lsb_sparc_schedule_row_gather(const uint16_t *slot_ids, int n_rows, int row0, uint32_t *words, int64_t max_words,
+                                  int *chunks)
+{
+    LSB_REQUIRE(slot_ids && words && chunks && n_rows > 0 && n_rows <= 65535 && row0 >= 0, "bad argument");
+    int c = 0;
+    const std::vector<uint32_t> out = schedule_row_gather(std::vector<uint16_t>(slot_ids, slot_ids + n_rows), row0, &c);
+    LSB_REQUIRE((int64_t)out.size() <= max_words, "output needs %zu words", out.size());
+    std::copy(out.begin(), out.end(), words);
+    *chunks = c;
+    return LSB_OK;
+}
+
+
 int lsb_sparc_design_create(const double *W, int Lr, int Lc, int L, int M, int n, const uint32_t *order0,
                             const uint32_t *order1, lsb_sparc_design **out)
 {

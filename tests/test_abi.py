@@ -57,3 +57,32 @@ def test_no_cpu_fallback_without_gpu():
         c.decode(np.ones(c.N))
     with pytest.raises(_lib.LibraryError):
         c.Lxor(1.0, 2.0)
+
+
+def test_row_gather_schedule_is_conflict_free():
+    """lsb_sparc_schedule_row_gather (host only): the AMP kernel's row-gather order is a proper edge colouring of
+    (residual bank pair, buffer bank pair): every row once, no two rows of a half-warp share a bank pair on either side."""
+    import ctypes as ct
+    import numpy as np
+    from ldpc_sparc_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(7)
+    for n_rows, row0 in ((3413, 0), (3413, 3413), (1000, 5), (17, 3), (4095, 1)):
+        ids = rng.permutation(4096)[:n_rows].astype(np.uint16)
+        words = np.zeros(16384 * 2, dtype=np.uint32)
+        chunks = ct.c_int(0)
+        _lib.check(L.lsb_sparc_schedule_row_gather(ids.ctypes.data, n_rows, row0, words.ctypes.data, words.size,
+                                                   ct.byref(chunks)), "schedule")
+        w = words[:chunks.value * 256 * 4].reshape(chunks.value, 16, 16, 4)     # [chunk][half-warp][lane][slot]
+        live = w != 0xFFFFFFFF
+        rows, slots = (w & 0xFFFF).astype(np.int64), (w >> 16).astype(np.int64)
+        assert np.array_equal(np.sort(rows[live]), np.arange(n_rows))            # every row exactly once
+        assert np.array_equal(slots[live], ids[rows[live]])                      # with its own slot
+        for c in range(chunks.value):
+            for hw in range(16):
+                for s in range(4):
+                    m = live[c, hw, :, s]
+                    rb, sb = (row0 + rows[c, hw, m, s]) % 16, slots[c, hw, m, s] % 16
+                    assert len(set(rb)) == len(rb) and len(set(sb)) == len(sb)
+        degree = max(np.bincount((row0 + np.arange(n_rows)) % 16, minlength=16).max(), np.bincount(ids % 16, minlength=16).max())
+        assert chunks.value == (((degree + 15) // 16) + 3) // 4                   # Delta colours: no slot wasted
